@@ -1,0 +1,179 @@
+"""ctypes binding of oracle/libvfx_oracle.so (the CPU oracle -- test infrastructure only).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "libvfx_oracle.so")
+
+FMT = {"RGBx": 0, "xRGB": 1, "BGRx": 2, "xBGR": 3, "RGBA": 4, "ARGB": 5, "BGRA": 6, "ABGR": 7,
+       "RGB": 8, "BGR": 9, "RGBA64_LE": 10, "RGBA64_BE": 11, "I420": 12, "A420": 13}
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(ORACLE_DIR, "vfx_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        f32p, u8p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+        _lib.orc_cube_parse.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        C.POINTER(f32p), f32p, f32p, C.c_char_p, C.c_size_t]
+        _lib.orc_cube_parse_file.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                             C.POINTER(f32p), f32p, f32p, C.c_char_p, C.c_size_t]
+        _lib.orc_free.argtypes = [C.c_void_p]
+        _lib.orc_colorlut_apply.argtypes = [C.c_int, C.c_int, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        _lib.orc_hsvfilter.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_float] * 5 + [C.c_int]
+        _lib.orc_hsvdetector.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_int] + [C.c_float] * 6 + [C.c_int]
+        _lib.orc_blockhash_sums.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                            u32p, C.c_int]
+        _lib.orc_blockhash_bits.argtypes = [u32p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+        _lib.orc_hamming.argtypes = [u8p, u8p, C.c_int]
+        _lib.orc_roundmask.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p]
+        for n in ("orc_hsv_from_rgb", "orc_hsv_from_bgr"):
+            getattr(_lib, n).argtypes = [u8p, f32p]
+            getattr(_lib, n).restype = None
+        for n in ("orc_hsv_to_rgb", "orc_hsv_to_bgr"):
+            getattr(_lib, n).argtypes = [f32p, u8p]
+            getattr(_lib, n).restype = None
+    return _lib
+
+
+def _f32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class CubeError(Exception):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+class Cube:
+    """Parsed LUT: kind (1|3), size, values (n,3) f32, scale/offset (3,) f32."""
+
+    def __init__(self, kind, size, values, scale, offset):
+        self.kind, self.size = kind, size
+        self.values = np.ascontiguousarray(values, np.float32)
+        self.scale = np.ascontiguousarray(scale, np.float32)
+        self.offset = np.ascontiguousarray(offset, np.float32)
+
+
+def cube_parse(text) -> Cube:
+    data = text.encode("utf-8") if isinstance(text, str) else bytes(text)
+    kind, size = C.c_int(), C.c_int()
+    vals = C.POINTER(C.c_float)()
+    scale = np.zeros(3, np.float32)
+    offset = np.zeros(3, np.float32)
+    err = C.create_string_buffer(512)
+    rc = lib().orc_cube_parse(data, len(data), C.byref(kind), C.byref(size), C.byref(vals), _f32p(scale),
+                              _f32p(offset), err, 512)
+    if rc != 0:
+        raise CubeError(rc, err.value.decode("utf-8", "replace"))
+    n = size.value if kind.value == 1 else size.value ** 3
+    values = np.ctypeslib.as_array(vals, shape=(n, 3)).copy()
+    lib().orc_free(vals)
+    return Cube(kind.value, size.value, values, scale, offset)
+
+
+def cube_from_values(kind, size, values, scale=(1, 1, 1), offset=(-0.0, -0.0, -0.0)) -> Cube:
+    return Cube(kind, size, np.asarray(values, np.float32).reshape(-1, 3), np.asarray(scale, np.float32),
+                np.asarray(offset, np.float32))
+
+
+def colorlut_apply(cube: Cube, fmt: str, width: int, height: int, src: np.ndarray, dst_stride=None,
+                   threads: int = 1, dst_fill: int = 0x5A) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    sstride = src.shape[1]
+    dstride = dst_stride or sstride
+    dst = np.full((height, dstride), dst_fill, np.uint8)
+    rc = lib().orc_colorlut_apply(cube.kind, cube.size, _f32p(cube.values), _f32p(cube.scale), _f32p(cube.offset),
+                                  FMT[fmt], width, height, src.ctypes.data, sstride, dst.ctypes.data, dstride,
+                                  threads)
+    if rc:
+        raise RuntimeError("orc_colorlut_apply rc=%d" % rc)
+    return dst
+
+
+def hsvfilter(fmt, width, height, data: np.ndarray, hue_shift=0.0, sat_mul=1.0, sat_off=0.0, val_mul=1.0,
+              val_off=0.0, threads=1) -> np.ndarray:
+    out = np.ascontiguousarray(data, np.uint8).copy()
+    rc = lib().orc_hsvfilter(FMT[fmt], width, height, out.ctypes.data, out.shape[1], hue_shift, sat_mul, sat_off,
+                             val_mul, val_off, threads)
+    if rc:
+        raise RuntimeError("orc_hsvfilter rc=%d" % rc)
+    return out
+
+
+def hsvdetector(in_fmt, out_fmt, width, height, src: np.ndarray, dst_stride=None, hue_ref=0.0, hue_var=10.0,
+                sat_ref=0.0, sat_var=0.15, val_ref=0.0, val_var=0.3, threads=1, dst_fill=0x5A) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    dstride = dst_stride or 4 * width
+    dst = np.full((height, dstride), dst_fill, np.uint8)
+    rc = lib().orc_hsvdetector(FMT[in_fmt], FMT[out_fmt], width, height, src.ctypes.data, src.shape[1],
+                               dst.ctypes.data, dstride, hue_ref, hue_var, sat_ref, sat_var, val_ref, val_var,
+                               threads)
+    if rc:
+        raise RuntimeError("orc_hsvdetector rc=%d" % rc)
+    return dst
+
+
+def blockhash_sums(fmt, width, height, src: np.ndarray, hw=8, hh=8) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    sums = np.zeros(hw * hh, np.uint32)
+    rc = lib().orc_blockhash_sums(FMT[fmt], width, height, src.ctypes.data, src.shape[1], hw, hh,
+                                  sums.ctypes.data_as(C.POINTER(C.c_uint32)), 1)
+    if rc:
+        raise RuntimeError("orc_blockhash_sums rc=%d" % rc)
+    return sums
+
+
+def blockhash_bits(sums: np.ndarray, width, height, hw=8, hh=8) -> np.ndarray:
+    sums = np.ascontiguousarray(sums, np.uint32)
+    bits = np.zeros(hw * hh, np.uint8)
+    lib().orc_blockhash_bits(sums.ctypes.data_as(C.POINTER(C.c_uint32)), hw, hh, width, height,
+                             bits.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return bits
+
+
+def roundmask(width, height, stride, radius) -> np.ndarray:
+    rows = (height + 1) & ~1
+    a8 = np.full((rows, stride), 0x77, np.uint8)
+    rc = lib().orc_roundmask(width, height, stride, radius, a8.ctypes.data)
+    if rc:
+        raise RuntimeError("orc_roundmask rc=%d" % rc)
+    return a8
+
+
+def hsv_from(rgb, bgr=False):
+    p = (C.c_uint8 * 3)(*rgb)
+    o = (C.c_float * 3)()
+    (lib().orc_hsv_from_bgr if bgr else lib().orc_hsv_from_rgb)(p, o)
+    return [o[0], o[1], o[2]]
+
+
+def hsv_to(hsv, bgr=False):
+    p = (C.c_float * 3)(*hsv)
+    o = (C.c_uint8 * 3)()
+    (lib().orc_hsv_to_bgr if bgr else lib().orc_hsv_to_rgb)(p, o)
+    return [o[0], o[1], o[2]]
