@@ -1,0 +1,241 @@
+"""b200vfx -- thin ctypes binding of libb200vfx.so (include/b200vfx.h).
+
+This is plumbing for tests/ and bench.py: every call goes straight through the C ABI that a
+gstreamer-rs element would bind.  There is no Python or CPU implementation of
+the pixel path here -- if the CUDA library is missing or no GPU is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.dirname(HERE)
+REPO_ROOT = os.path.dirname(PKG_ROOT)
+LIB_PATH = os.path.join(PKG_ROOT, "lib", "libb200vfx.so")
+HEADER = os.path.join(REPO_ROOT, "include", "b200vfx.h")
+
+FMT = {"RGBx": 0, "xRGB": 1, "BGRx": 2, "xBGR": 3, "RGBA": 4, "ARGB": 5, "BGRA": 6, "ABGR": 7,
+       "RGB": 8, "BGR": 9, "RGBA64_LE": 10, "RGBA64_BE": 11, "I420": 12, "A420": 13}
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NOT_NEGOTIATED, ERR_UNSUPPORTED, ERR_PARSE, ERR_IO = 0, -1, -2, -3, -4, -5, -6
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+SOURCES = ["csrc/b200vfx.cu", "csrc/cube_parser.cpp", "csrc/elements.cpp"]
+
+
+class B200VfxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("b200vfx error %d: %s" % (code, msg))
+        self.code = code
+        self.msg = msg
+
+
+def build(force: bool = False) -> str:
+    """Compile libb200vfx.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(PKG_ROOT, s) for s in SOURCES if os.path.exists(os.path.join(PKG_ROOT, s))]
+    deps = srcs + [os.path.join(PKG_ROOT, "csrc", f) for f in os.listdir(os.path.join(PKG_ROOT, "csrc"))
+                   if f.endswith((".cuh", ".h", ".hpp"))] + [HEADER]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc")
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
+    subprocess.check_call(cmd, cwd=PKG_ROOT)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cf, cu = C.c_void_p, C.c_int, C.c_float, C.c_uint
+    f32p = C.POINTER(C.c_float)
+    sigs = {
+        "b200vfx_abi_version": ([], ci),
+        "b200vfx_device_count": ([], ci),
+        "b200vfx_ctx_create": ([C.POINTER(vp), ci], ci),
+        "b200vfx_ctx_destroy": ([vp], None),
+        "b200vfx_last_error": ([vp], C.c_char_p),
+        "b200vfx_ctx_set_stream": ([vp, vp], ci),
+        "b200vfx_ctx_synchronize": ([vp], ci),
+        "b200vfx_ctx_set_chunk_rows": ([vp, ci], ci),
+        "b200vfx_ctx_kernel_launches": ([vp], C.c_uint64),
+        "b200vfx_host_alloc": ([C.c_size_t], vp),
+        "b200vfx_host_free": ([vp], None),
+        "b200vfx_cube_parse": ([C.c_char_p, C.c_size_t, C.POINTER(ci), C.POINTER(ci), C.POINTER(f32p), f32p, f32p,
+                                C.c_char_p, C.c_size_t], ci),
+        "b200vfx_cube_parse_file": ([C.c_char_p, C.POINTER(ci), C.POINTER(ci), C.POINTER(f32p), f32p, f32p,
+                                     C.c_char_p, C.c_size_t], ci),
+        "b200vfx_cube_free": ([f32p], None),
+        "b200vfx_colorlut_load_file": ([vp, C.c_char_p], ci),
+        "b200vfx_colorlut_set_lut": ([vp, ci, ci, f32p, f32p, f32p], ci),
+        "b200vfx_colorlut_clear": ([vp], ci),
+        "b200vfx_colorlut_set_mode": ([vp, ci], ci),
+        "b200vfx_colorlut_process": ([vp, ci, ci, ci, vp, ci, vp, ci], ci),
+        "b200vfx_hsvfilter_process": ([vp, ci, ci, ci, vp, ci] + [cf] * 5, ci),
+        "b200vfx_hsvdetector_process": ([vp, ci, ci, ci, ci, vp, ci, vp, ci] + [cf] * 6, ci),
+        "b200vfx_roundmask_generate": ([vp, ci, ci, ci, cu, vp], ci),
+        "b200vfx_blockhash_sums": ([vp, ci, ci, ci, vp, ci, ci, ci, vp], ci),
+        "b200vfx_blockhash_bits": ([vp, ci, ci, ci, ci, vp], None),
+        "b200vfx_hash_distance": ([vp, vp, ci], ci),
+    }
+    for name, (args, res) in sigs.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = L
+    return L
+
+
+def exported_symbols_in_header():
+    """Names of every function include/b200vfx.h declares (used by the symbol-export test)."""
+    import re
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200vfx_[a-z0-9_]+)\s*\(", text)))
+
+
+def device_count() -> int:
+    return lib().b200vfx_device_count()
+
+
+def _ptr(x) -> int:
+    """raw address of a numpy array / torch tensor / int / ctypes pointer"""
+    if x is None:
+        return 0
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return int(x.data_ptr())
+    if hasattr(x, "ctypes"):
+        return int(x.ctypes.data)
+    return int(C.cast(x, C.c_void_p).value or 0)
+
+
+def cube_parse(text):
+    """-> (kind, size, values ndarray (n,3) f32, scale (3,), offset (3,)) via the product's C++ parser."""
+    import numpy as np
+    data = text.encode("utf-8") if isinstance(text, str) else bytes(text)
+    kind, size = C.c_int(), C.c_int()
+    vals = C.POINTER(C.c_float)()
+    scale = np.zeros(3, np.float32)
+    offset = np.zeros(3, np.float32)
+    err = C.create_string_buffer(512)
+    rc = lib().b200vfx_cube_parse(data, len(data), C.byref(kind), C.byref(size), C.byref(vals),
+                                  scale.ctypes.data_as(C.POINTER(C.c_float)),
+                                  offset.ctypes.data_as(C.POINTER(C.c_float)), err, 512)
+    if rc:
+        raise B200VfxError(rc, err.value.decode("utf-8", "replace"))
+    n = size.value if kind.value == 1 else size.value ** 3
+    values = np.ctypeslib.as_array(vals, shape=(n, 3)).copy()
+    lib().b200vfx_cube_free(vals)
+    return kind.value, size.value, values, scale, offset
+
+
+class Context:
+    """One b200vfx_ctx (= one element instance)."""
+
+    def __init__(self, device: int = -1):
+        self._h = C.c_void_p()
+        rc = lib().b200vfx_ctx_create(C.byref(self._h), device)
+        if rc:
+            raise B200VfxError(rc, (lib().b200vfx_last_error(None) or b"").decode())
+
+    def close(self):
+        if self._h:
+            lib().b200vfx_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc):
+        if rc:
+            raise B200VfxError(rc, (lib().b200vfx_last_error(self._h) or b"").decode())
+
+    # context ------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int):
+        self._chk(lib().b200vfx_ctx_set_stream(self._h, cuda_stream))
+
+    def synchronize(self):
+        self._chk(lib().b200vfx_ctx_synchronize(self._h))
+
+    def set_chunk_rows(self, rows: int):
+        self._chk(lib().b200vfx_ctx_set_chunk_rows(self._h, rows))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().b200vfx_ctx_kernel_launches(self._h))
+
+    # colorlut -----------------------------------------------------------------------------
+    def colorlut_load_file(self, location: str):
+        self._chk(lib().b200vfx_colorlut_load_file(self._h, location.encode() if location is not None else None))
+
+    def colorlut_set_lut(self, kind, size, values, scale, offset):
+        import numpy as np
+        v = np.ascontiguousarray(values, np.float32)
+        s = np.ascontiguousarray(scale, np.float32)
+        o = np.ascontiguousarray(offset, np.float32)
+        p = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        self._chk(lib().b200vfx_colorlut_set_lut(self._h, kind, size, p(v), p(s), p(o)))
+
+    def colorlut_clear(self):
+        self._chk(lib().b200vfx_colorlut_clear(self._h))
+
+    def colorlut_set_mode(self, mode: int):
+        self._chk(lib().b200vfx_colorlut_set_mode(self._h, mode))
+
+    def colorlut_process(self, fmt, width, height, src, sstride, dst, dstride):
+        self._chk(lib().b200vfx_colorlut_process(self._h, FMT[fmt], width, height, _ptr(src), sstride, _ptr(dst), dstride))
+
+    # hsv ----------------------------------------------------------------------------------
+    def hsvfilter_process(self, fmt, width, height, data, stride, hue_shift=0.0, saturation_mul=1.0,
+                          saturation_off=0.0, value_mul=1.0, value_off=0.0):
+        self._chk(lib().b200vfx_hsvfilter_process(self._h, FMT[fmt], width, height, _ptr(data), stride, hue_shift,
+                                                  saturation_mul, saturation_off, value_mul, value_off))
+
+    def hsvdetector_process(self, in_fmt, out_fmt, width, height, src, sstride, dst, dstride, hue_ref=0.0,
+                            hue_var=10.0, saturation_ref=0.0, saturation_var=0.15, value_ref=0.0, value_var=0.3):
+        self._chk(lib().b200vfx_hsvdetector_process(self._h, FMT[in_fmt], FMT[out_fmt], width, height, _ptr(src),
+                                                    sstride, _ptr(dst), dstride, hue_ref, hue_var, saturation_ref,
+                                                    saturation_var, value_ref, value_var))
+
+    # videofx ------------------------------------------------------------------------------
+    def roundmask_generate(self, width, height, stride, radius, a8_out):
+        self._chk(lib().b200vfx_roundmask_generate(self._h, width, height, stride, radius, _ptr(a8_out)))
+
+    def blockhash_sums(self, fmt, width, height, src, stride, sums, hw=8, hh=8):
+        self._chk(lib().b200vfx_blockhash_sums(self._h, FMT[fmt], width, height, _ptr(src), stride, hw, hh, _ptr(sums)))
+
+
+def blockhash_bits(sums, width, height, hw=8, hh=8):
+    import numpy as np
+    s = np.ascontiguousarray(sums, np.uint32)
+    bits = np.zeros(hw * hh, np.uint8)
+    lib().b200vfx_blockhash_bits(s.ctypes.data, hw, hh, width, height, bits.ctypes.data)
+    return bits
+
+
+def hash_distance(a, b) -> int:
+    import numpy as np
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return int(lib().b200vfx_hash_distance(a.ctypes.data, b.ctypes.data, a.size))

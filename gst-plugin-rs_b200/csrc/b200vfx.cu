@@ -1,0 +1,637 @@
+// b200vfx.cu -- C ABI (include/b200vfx.h) over the sm_100a kernels in kernels.cuh.
+//
+// Host-pointer calls run a row-chunked H2D -> kernel -> D2H pipeline on three streams so the two
+// PCIe directions and the kernel overlap inside ONE synchronous transform_frame call.
+// Device-pointer calls enqueue the kernel on the context stream and return.
+// There is no CPU fallback anywhere in this file.
+#include "../../include/b200vfx.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace b200vfx;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+  uint8_t *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct b200vfx_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;   // default stream for device-pointer calls
+  cudaStream_t user_stream = nullptr;
+  bool use_user_stream = false;
+  cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;  // host-pointer pipeline
+  std::vector<cudaEvent_t> ev_in, ev_k;
+  DevBuf stage_in, stage_out, stage_sums;
+  int chunk_rows = 0;
+  uint64_t launches = 0;
+  std::string err;
+
+  // colorlut state (State{lut}, colorlut/imp.rs:50-53)
+  bool have_lut = false;
+  int lut_kind = 0, lut_size = 0;
+  int mode = 0;  // 0 auto (memo for u8), 1 direct
+  float scale[3] = {1, 1, 1}, offset[3] = {0, 0, 0};
+  float4 *d_lut3d = nullptr;
+  float *d_lut1d = nullptr;
+  float2 *d_axis = nullptr;
+  uint32_t *d_memo = nullptr;   // 2^24 x u32 (3D)
+  uint8_t *d_memo1d = nullptr;  // 768 bytes (1D)
+  bool memo_ready = false;
+
+  cudaStream_t stream() const { return use_user_stream ? user_stream : own_stream; }
+};
+
+namespace {
+
+int fail(b200vfx_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define CU(ctx, call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(ctx, B200VFX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));     \
+  } while (0)
+
+bool is_device_ptr(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+struct FmtInfo { int bpp, coff; bool bgr, alpha; };
+bool fmt8_info(int fmt, FmtInfo *o) {
+  switch (fmt) {
+    case B200VFX_FORMAT_RGBX: *o = {4, 0, false, false}; return true;
+    case B200VFX_FORMAT_RGBA: *o = {4, 0, false, true}; return true;
+    case B200VFX_FORMAT_XRGB: *o = {4, 1, false, false}; return true;
+    case B200VFX_FORMAT_ARGB: *o = {4, 1, false, true}; return true;
+    case B200VFX_FORMAT_BGRX: *o = {4, 0, true, false}; return true;
+    case B200VFX_FORMAT_BGRA: *o = {4, 0, true, true}; return true;
+    case B200VFX_FORMAT_XBGR: *o = {4, 1, true, false}; return true;
+    case B200VFX_FORMAT_ABGR: *o = {4, 1, true, true}; return true;
+    case B200VFX_FORMAT_RGB: *o = {3, 0, false, false}; return true;
+    case B200VFX_FORMAT_BGR: *o = {3, 0, true, false}; return true;
+    default: return false;
+  }
+}
+
+inline bool aligned(const void *p, long stride, int a) {
+  return ((uintptr_t)p % (uintptr_t)a) == 0 && (stride % a) == 0;
+}
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline unsigned grid_rows(int height) { return (unsigned)std::min(height, 65535); }
+
+LutParams lut_params(const b200vfx_ctx *c) {
+  LutParams p;
+  p.lut3d = c->d_lut3d; p.lut1d = c->d_lut1d; p.axis = c->d_axis;
+  p.size = c->lut_size; p.kind = c->lut_kind;
+  for (int i = 0; i < 3; i++) { p.scale[i] = c->scale[i]; p.offset[i] = c->offset[i]; }
+  return p;
+}
+
+// ---- per-element kernel launchers on DEVICE frames ------------------------------------------
+struct Frame { const uint8_t *src; long sstride; uint8_t *dst; long dstride; int width, height; };
+
+int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
+  if (f.width == 0 || f.height == 0) return 0;
+  const LutParams p = lut_params(c);
+  if (fmt == B200VFX_FORMAT_RGBA && c->mode == 0) {
+    if (!c->memo_ready) {  // once per LUT: evaluate all 2^24 colours with the exact direct evaluator
+      if (c->lut_kind == 3) {
+        if (!c->d_memo) CU(c, cudaMalloc(&c->d_memo, sizeof(uint32_t) << 24));
+        colorlut_memo_build_kernel<<<(1u << 24) / 256, 256, 0, st>>>(p, c->d_memo);
+      } else {
+        if (!c->d_memo1d) CU(c, cudaMalloc(&c->d_memo1d, 768));
+        colorlut_memo1d_build_kernel<<<3, 256, 0, st>>>(p, c->d_memo1d);
+      }
+      c->launches++;
+      CU(c, cudaGetLastError());
+      c->memo_ready = true;
+    }
+    const bool al = aligned(f.src, f.sstride, 4) && aligned(f.dst, f.dstride, 4);
+    int w = f.width, h = f.height;
+    long ss = f.sstride, ds = f.dstride;
+    if (al && ss == 4L * w && ds == 4L * w && (long long)w * h < (1LL << 30)) { w = w * h; h = 1; }  // packed: 1-D
+    if (al) {
+      constexpr int PX = 4;
+      dim3 grid((unsigned)ceil_div(w, 8 * 32 * PX), grid_rows(h));
+      if (c->lut_kind == 3)
+        colorlut_memo_apply_kernel<PX><<<grid, 256, 0, st>>>(c->d_memo, f.src, ss, f.dst, ds, w, h);
+      else
+        colorlut_memo1d_apply_kernel<PX><<<grid, 256, 0, st>>>(c->d_memo1d, f.src, ss, f.dst, ds, w, h);
+    } else {
+      dim3 grid((unsigned)ceil_div(w, 256), grid_rows(h));
+      colorlut_memo_apply_bytes_kernel<<<grid, 256, 0, st>>>(c->lut_kind == 3 ? c->d_memo : nullptr, c->d_memo1d,
+                                                             f.src, ss, f.dst, ds, w, h);
+    }
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return 0;
+  }
+  dim3 grid((unsigned)ceil_div(f.width, 256), grid_rows(f.height));
+  const bool al4 = aligned(f.src, f.sstride, 4) && aligned(f.dst, f.dstride, 4);
+  const bool al8 = aligned(f.src, f.sstride, 8) && aligned(f.dst, f.dstride, 8);
+  if (((uintptr_t)f.src | (uintptr_t)f.dst) & 1u && fmt != B200VFX_FORMAT_RGBA)
+    return fail(c, B200VFX_ERR_INVALID, "RGBA64 planes must be 2-byte aligned (as_slice_of::<u16>, imp.rs:323-324)");
+#define LAUNCH_DIRECT(F, A) colorlut_direct_kernel<F, A><<<grid, 256, 0, st>>>(p, f.src, f.sstride, f.dst, f.dstride, f.width, f.height)
+  switch (fmt) {
+    case B200VFX_FORMAT_RGBA: if (al4) LAUNCH_DIRECT(0, true); else LAUNCH_DIRECT(0, false); break;
+    case B200VFX_FORMAT_RGBA64_LE: if (al8) LAUNCH_DIRECT(1, true); else LAUNCH_DIRECT(1, false); break;
+    case B200VFX_FORMAT_RGBA64_BE: if (al8) LAUNCH_DIRECT(2, true); else LAUNCH_DIRECT(2, false); break;
+    default: return fail(c, B200VFX_ERR_UNSUPPORTED, "colorlut: unsupported format %d", fmt);
+  }
+#undef LAUNCH_DIRECT
+  c->launches++;
+  CU(c, cudaGetLastError());
+  return 0;
+}
+
+template <int BPP, int COFF, bool BGR>
+void launch_hsvfilter_t(const HsvFilterSettings &s, uint8_t *data, long stride, int w, int h, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(w, 256), grid_rows(h));
+  if (BPP == 4 && aligned(data, stride, 4)) hsvfilter_kernel<BPP, COFF, BGR, true><<<grid, 256, 0, st>>>(s, data, stride, w, h);
+  else hsvfilter_kernel<BPP, COFF, BGR, false><<<grid, 256, 0, st>>>(s, data, stride, w, h);
+}
+
+int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings &s, uint8_t *data, long stride,
+                     int w, int h, cudaStream_t st) {
+  if (w == 0 || h == 0) return 0;
+  if (fi.bpp == 3) { if (fi.bgr) launch_hsvfilter_t<3, 0, true>(s, data, stride, w, h, st); else launch_hsvfilter_t<3, 0, false>(s, data, stride, w, h, st); }
+  else if (fi.coff == 0) { if (fi.bgr) launch_hsvfilter_t<4, 0, true>(s, data, stride, w, h, st); else launch_hsvfilter_t<4, 0, false>(s, data, stride, w, h, st); }
+  else { if (fi.bgr) launch_hsvfilter_t<4, 1, true>(s, data, stride, w, h, st); else launch_hsvfilter_t<4, 1, false>(s, data, stride, w, h, st); }
+  c->launches++;
+  CU(c, cudaGetLastError());
+  return 0;
+}
+
+template <int IBPP, int ICOFF, bool IBGR>
+void launch_hsvdetector_t(const FmtInfo &fo, const HsvDetectSettings &s, const Frame &f, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(f.width, 256), grid_rows(f.height));
+  const bool al = aligned(f.dst, f.dstride, 4) && (IBPP == 3 || aligned(f.src, f.sstride, 4));
+#define L(OC, OB)                                                                                                   \
+  do {                                                                                                              \
+    if (al) hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, true><<<grid, 256, 0, st>>>(s, f.src, f.sstride, f.dst, f.dstride, f.width, f.height); \
+    else hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, false><<<grid, 256, 0, st>>>(s, f.src, f.sstride, f.dst, f.dstride, f.width, f.height);  \
+  } while (0)
+  if (fo.coff == 0) { if (fo.bgr) L(0, true); else L(0, false); }
+  else { if (fo.bgr) L(1, true); else L(1, false); }
+#undef L
+}
+
+int launch_hsvdetector(b200vfx_ctx *c, const FmtInfo &fi, const FmtInfo &fo, const HsvDetectSettings &s,
+                       const Frame &f, cudaStream_t st) {
+  if (f.width == 0 || f.height == 0) return 0;
+  if (fi.bpp == 3) { if (fi.bgr) launch_hsvdetector_t<3, 0, true>(fo, s, f, st); else launch_hsvdetector_t<3, 0, false>(fo, s, f, st); }
+  else if (fi.coff == 0) { if (fi.bgr) launch_hsvdetector_t<4, 0, true>(fo, s, f, st); else launch_hsvdetector_t<4, 0, false>(fo, s, f, st); }
+  else { if (fi.bgr) launch_hsvdetector_t<4, 1, true>(fo, s, f, st); else launch_hsvdetector_t<4, 1, false>(fo, s, f, st); }
+  c->launches++;
+  CU(c, cudaGetLastError());
+  return 0;
+}
+
+// ---- host-pointer pipeline -------------------------------------------------------------------
+// Copies rows [r0,r1) of a host/device plane pair through device staging in chunks; `launch`
+// enqueues the element kernel for one chunk of DEVICE rows on the given stream.
+struct Staged {
+  const uint8_t *src; long sstride; size_t in_row_bytes;   // src == nullptr: no input plane
+  uint8_t *dst; long dstride; size_t out_row_bytes;        // in place: dst == src plane
+  int height;
+  bool in_place;
+};
+
+template <typename LaunchFn>
+int run_staged(b200vfx_ctx *c, const Staged &s, LaunchFn launch) {
+  if (s.height == 0) return 0;
+  const bool src_dev = !s.src || is_device_ptr(s.src);  // no input plane counts as "nothing to upload"
+  const bool dst_dev = is_device_ptr(s.dst);
+  if (s.in_place ? dst_dev : (src_dev && dst_dev)) {  // everything already in HBM: just enqueue
+    return launch(s.src, s.sstride, s.dst, s.dstride, 0, s.height, c->stream());
+  }
+  // device staging strides: tightly packed rows rounded up to 16 B so vector paths apply
+  const long in_ds = (long)((s.in_row_bytes + 15) & ~(size_t)15);
+  const long out_ds = s.in_place ? in_ds : (long)((s.out_row_bytes + 15) & ~(size_t)15);
+  const uint8_t *d_in = nullptr;
+  uint8_t *d_out = nullptr;
+  long d_in_stride = 0, d_out_stride = 0;
+  if (s.in_place) {
+    CU(c, c->stage_in.reserve((size_t)in_ds * s.height));
+    d_in = d_out = c->stage_in.p; d_in_stride = d_out_stride = in_ds;
+  } else {
+    if (src_dev) { d_in = s.src; d_in_stride = s.sstride; }
+    else { CU(c, c->stage_in.reserve((size_t)in_ds * s.height)); d_in = c->stage_in.p; d_in_stride = in_ds; }
+    if (dst_dev) { d_out = s.dst; d_out_stride = s.dstride; }
+    else { CU(c, c->stage_out.reserve((size_t)out_ds * s.height)); d_out = c->stage_out.p; d_out_stride = out_ds; }
+  }
+  const bool need_h2d = s.in_place ? true : !src_dev;
+  const bool need_d2h = s.in_place ? true : !dst_dev;
+  int rows = c->chunk_rows;
+  if (rows <= 0) {
+    const size_t per_row = std::max(s.in_row_bytes, s.out_row_bytes);
+    rows = (int)std::max<size_t>(1, ((size_t)2 << 20) / std::max<size_t>(per_row, 1));
+  }
+  const int nchunks = ceil_div(s.height, rows);
+  while ((int)c->ev_in.size() < nchunks) {
+    cudaEvent_t a, b;
+    CU(c, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CU(c, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    c->ev_in.push_back(a); c->ev_k.push_back(b);
+  }
+  for (int k = 0; k < nchunks; k++) {
+    const int r0 = k * rows, r1 = std::min(s.height, r0 + rows);
+    if (need_h2d) {
+      const uint8_t *hp = s.src + (size_t)r0 * s.sstride;
+      uint8_t *dp = const_cast<uint8_t *>(d_in) + (size_t)r0 * d_in_stride;
+      if ((size_t)s.sstride == s.in_row_bytes && (size_t)d_in_stride == s.in_row_bytes)
+        CU(c, cudaMemcpyAsync(dp, hp, s.in_row_bytes * (size_t)(r1 - r0), cudaMemcpyHostToDevice, c->s_h2d));
+      else
+        CU(c, cudaMemcpy2DAsync(dp, (size_t)d_in_stride, hp, (size_t)s.sstride, s.in_row_bytes, (size_t)(r1 - r0),
+                                cudaMemcpyHostToDevice, c->s_h2d));
+      CU(c, cudaEventRecord(c->ev_in[k], c->s_h2d));
+      CU(c, cudaStreamWaitEvent(c->s_k, c->ev_in[k], 0));
+    }
+    int rc = launch(d_in ? d_in + (size_t)r0 * d_in_stride : nullptr, d_in_stride, d_out + (size_t)r0 * d_out_stride,
+                    d_out_stride, r0, r1 - r0, c->s_k);
+    if (rc) return rc;
+    if (need_d2h) {
+      CU(c, cudaEventRecord(c->ev_k[k], c->s_k));
+      CU(c, cudaStreamWaitEvent(c->s_d2h, c->ev_k[k], 0));
+      uint8_t *hp = s.dst + (size_t)r0 * s.dstride;
+      const uint8_t *dp = d_out + (size_t)r0 * d_out_stride;
+      if ((size_t)s.dstride == s.out_row_bytes && (size_t)d_out_stride == s.out_row_bytes)
+        CU(c, cudaMemcpyAsync(hp, dp, s.out_row_bytes * (size_t)(r1 - r0), cudaMemcpyDeviceToHost, c->s_d2h));
+      else
+        CU(c, cudaMemcpy2DAsync(hp, (size_t)s.dstride, dp, (size_t)d_out_stride, s.out_row_bytes, (size_t)(r1 - r0),
+                                cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+  }
+  if (need_d2h) CU(c, cudaStreamSynchronize(c->s_d2h));
+  else CU(c, cudaStreamSynchronize(c->s_k));
+  return 0;
+}
+
+int check_frame(b200vfx_ctx *c, int width, int height, const void *a, long astride, size_t a_row, const void *b,
+                long bstride, size_t b_row) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (width < 0 || height < 0) return fail(c, B200VFX_ERR_INVALID, "negative frame size");
+  if (height > 0 && width > 0) {
+    if (!a || (b_row && !b)) return fail(c, B200VFX_ERR_INVALID, "null plane pointer");
+    if (astride < 0 || (size_t)astride < a_row) return fail(c, B200VFX_ERR_INVALID, "stride %ld < row bytes %zu", astride, a_row);
+    if (b_row && (bstride < 0 || (size_t)bstride < b_row)) return fail(c, B200VFX_ERR_INVALID, "stride %ld < row bytes %zu", bstride, b_row);
+  }
+  return 0;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int b200vfx_abi_version(void) { return B200VFX_ABI_VERSION; }
+
+int b200vfx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char *b200vfx_last_error(const b200vfx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int b200vfx_ctx_create(b200vfx_ctx **out, int device) {
+  if (!out) return fail(nullptr, B200VFX_ERR_INVALID, "null out pointer");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(nullptr, B200VFX_ERR_CUDA, "no CUDA device available (%s); libb200vfx has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0) CU(nullptr, cudaGetDevice(&device));
+  if (device >= n) return fail(nullptr, B200VFX_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+  DeviceGuard g(device);
+  b200vfx_ctx *c = new b200vfx_ctx();
+  c->device = device;
+  cudaError_t err = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
+  if (err != cudaSuccess) {
+    int rc = fail(nullptr, B200VFX_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(err));
+    b200vfx_ctx_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+void b200vfx_ctx_destroy(b200vfx_ctx *c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  cudaDeviceSynchronize();
+  b200vfx_colorlut_clear(c);
+  for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
+  c->stage_in.release(); c->stage_out.release(); c->stage_sums.release();
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_k) cudaStreamDestroy(c->s_k);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  delete c;
+}
+
+int b200vfx_ctx_set_stream(b200vfx_ctx *c, void *cuda_stream) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  c->user_stream = (cudaStream_t)cuda_stream;
+  c->use_user_stream = true;
+  return 0;
+}
+
+int b200vfx_ctx_synchronize(b200vfx_ctx *c) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  DeviceGuard g(c->device);
+  CU(c, cudaStreamSynchronize(c->stream()));
+  return 0;
+}
+
+int b200vfx_ctx_set_chunk_rows(b200vfx_ctx *c, int rows) {
+  if (!c || rows < 0) return fail(c, B200VFX_ERR_INVALID, "bad chunk rows");
+  c->chunk_rows = rows;
+  return 0;
+}
+
+uint64_t b200vfx_ctx_kernel_launches(const b200vfx_ctx *c) { return c ? c->launches : 0; }
+
+void *b200vfx_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void b200vfx_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- colorlut --------------------------------------------------------------------------------
+int b200vfx_colorlut_clear(b200vfx_ctx *c) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  DeviceGuard g(c->device);
+  if (c->d_lut3d) cudaFree(c->d_lut3d);
+  if (c->d_lut1d) cudaFree(c->d_lut1d);
+  if (c->d_axis) cudaFree(c->d_axis);
+  if (c->d_memo) cudaFree(c->d_memo);
+  if (c->d_memo1d) cudaFree(c->d_memo1d);
+  c->d_lut3d = nullptr; c->d_lut1d = nullptr; c->d_axis = nullptr; c->d_memo = nullptr; c->d_memo1d = nullptr;
+  c->have_lut = false; c->memo_ready = false; c->lut_kind = 0; c->lut_size = 0;
+  return 0;
+}
+
+int b200vfx_colorlut_set_mode(b200vfx_ctx *c, int mode) {
+  if (!c || (mode != 0 && mode != 1)) return fail(c, B200VFX_ERR_INVALID, "colorlut mode must be 0 (auto) or 1 (direct)");
+  c->mode = mode;
+  return 0;
+}
+
+int b200vfx_colorlut_set_lut(b200vfx_ctx *c, int kind, int size, const float *values, const float scale[3],
+                             const float offset[3]) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (!values || !scale || !offset) return fail(c, B200VFX_ERR_INVALID, "null LUT argument");
+  if (kind == 1) { if (size < 2 || size > 65536) return fail(c, B200VFX_ERR_INVALID, "Invalid LUT size %d, expected 2..=65536", size); }
+  else if (kind == 3) { if (size < 2 || size > 256) return fail(c, B200VFX_ERR_INVALID, "Invalid LUT size %d, expected 2..=256", size); }
+  else return fail(c, B200VFX_ERR_INVALID, "LUT kind must be 1 or 3");
+  DeviceGuard g(c->device);
+  cudaStream_t st = c->stream();
+  CU(c, cudaStreamSynchronize(st));
+  b200vfx_colorlut_clear(c);
+  const size_t n = kind == 1 ? (size_t)size : (size_t)size * size * size;
+  if (kind == 3) {
+    std::vector<float4> h(n);
+    for (size_t i = 0; i < n; i++) h[i] = make_float4(values[3 * i], values[3 * i + 1], values[3 * i + 2], 1.0f);  // parser.rs:253-256
+    CU(c, cudaMalloc(&c->d_lut3d, n * sizeof(float4)));
+    CU(c, cudaMemcpyAsync(c->d_lut3d, h.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CU(c, cudaStreamSynchronize(st));
+  } else {
+    std::vector<float> h(3 * n);
+    for (size_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) h[(size_t)k * n + i] = values[3 * i + k];  // parser.rs:232-236
+    CU(c, cudaMalloc(&c->d_lut1d, 3 * n * sizeof(float)));
+    CU(c, cudaMemcpyAsync(c->d_lut1d, h.data(), 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(c, cudaStreamSynchronize(st));
+  }
+  for (int i = 0; i < 3; i++) { c->scale[i] = scale[i]; c->offset[i] = offset[i]; }
+  c->lut_kind = kind; c->lut_size = size;
+  CU(c, cudaMalloc(&c->d_axis, 768 * sizeof(float2)));
+  colorlut_axis_table_kernel<<<3, 256, 0, st>>>(c->d_axis, lut_params(c));
+  c->launches++;
+  CU(c, cudaGetLastError());
+  CU(c, cudaStreamSynchronize(st));
+  c->have_lut = true;
+  return 0;
+}
+
+int b200vfx_colorlut_load_file(b200vfx_ctx *c, const char *location) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (!location) return fail(c, B200VFX_ERR_INVALID, "LUT file location is not configured");  // imp.rs:175-180
+  int kind = 0, size = 0;
+  float *values = nullptr, scale[3], offset[3];
+  char err[400];
+  int rc = b200vfx_cube_parse_file(location, &kind, &size, &values, scale, offset, err, sizeof err);
+  if (rc) return fail(c, rc, "Failed to parse LUT file %s: %s", location, err);  // imp.rs:182-187
+  rc = b200vfx_colorlut_set_lut(c, kind, size, values, scale, offset);
+  b200vfx_cube_free(values);
+  return rc;
+}
+
+int b200vfx_colorlut_process(b200vfx_ctx *c, int fmt, int width, int height, const void *src, int src_stride,
+                             void *dst, int dst_stride) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (!c->have_lut) return fail(c, B200VFX_ERR_NOT_NEGOTIATED, "No LUT configured");  // imp.rs:210-213
+  int bpp;
+  if (fmt == B200VFX_FORMAT_RGBA) bpp = 4;
+  else if (fmt == B200VFX_FORMAT_RGBA64_LE || fmt == B200VFX_FORMAT_RGBA64_BE) bpp = 8;
+  else return fail(c, B200VFX_ERR_UNSUPPORTED, "colorlut: format %d is not RGBA / RGBA64_LE / RGBA64_BE", fmt);
+  const size_t row = (size_t)width * bpp;
+  if (int rc = check_frame(c, width, height, src, src_stride, row, dst, dst_stride, row)) return rc;
+  if (width == 0 || height == 0) return 0;
+  DeviceGuard g(c->device);
+  Staged s{(const uint8_t *)src, src_stride, row, (uint8_t *)dst, dst_stride, row, height, false};
+  return run_staged(c, s, [&](const uint8_t *ds, long dss, uint8_t *dd, long dds, int, int rows, cudaStream_t st) {
+    return launch_colorlut(c, fmt, Frame{ds, dss, dd, dds, width, rows}, st);
+  });
+}
+
+// ---- hsvfilter / hsvdetector ------------------------------------------------------------------
+int b200vfx_hsvfilter_process(b200vfx_ctx *c, int fmt, int width, int height, void *data, int stride,
+                              float hue_shift, float saturation_mul, float saturation_off, float value_mul,
+                              float value_off) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  FmtInfo fi;
+  if (!fmt8_info(fmt, &fi)) return fail(c, B200VFX_ERR_UNSUPPORTED, "hsvfilter: unsupported format %d", fmt);
+  const size_t row = (size_t)width * fi.bpp;
+  if (int rc = check_frame(c, width, height, data, stride, row, nullptr, 0, 0)) return rc;
+  if (width == 0 || height == 0) return 0;
+  DeviceGuard g(c->device);
+  const HsvFilterSettings hs{hue_shift, saturation_mul, saturation_off, value_mul, value_off};
+  Staged s{(const uint8_t *)data, stride, row, (uint8_t *)data, stride, row, height, true};
+  return run_staged(c, s, [&](const uint8_t *, long, uint8_t *dd, long dds, int, int rows, cudaStream_t st) {
+    return launch_hsvfilter(c, fi, hs, dd, dds, width, rows, st);
+  });
+}
+
+int b200vfx_hsvdetector_process(b200vfx_ctx *c, int in_fmt, int out_fmt, int width, int height, const void *src,
+                                int src_stride, void *dst, int dst_stride, float hue_ref, float hue_var,
+                                float saturation_ref, float saturation_var, float value_ref, float value_var) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  FmtInfo fi, fo;
+  if (!fmt8_info(in_fmt, &fi) || fi.alpha)  // sink caps hsvdetector/imp.rs:78-87
+    return fail(c, B200VFX_ERR_UNSUPPORTED, "hsvdetector: input format %d not in RGBx,xRGB,BGRx,xBGR,RGB,BGR", in_fmt);
+  if (!fmt8_info(out_fmt, &fo) || !fo.alpha)  // src caps :89-96
+    return fail(c, B200VFX_ERR_UNSUPPORTED, "hsvdetector: output format %d not in RGBA,ARGB,BGRA,ABGR", out_fmt);
+  const size_t irow = (size_t)width * fi.bpp, orow = (size_t)width * 4;
+  if (int rc = check_frame(c, width, height, src, src_stride, irow, dst, dst_stride, orow)) return rc;
+  if (width == 0 || height == 0) return 0;
+  DeviceGuard g(c->device);
+  const HsvDetectSettings hs{hue_ref, hue_var, saturation_ref, saturation_var, value_ref, value_var};
+  Staged s{(const uint8_t *)src, src_stride, irow, (uint8_t *)dst, dst_stride, orow, height, false};
+  return run_staged(c, s, [&](const uint8_t *ds, long dss, uint8_t *dd, long dds, int, int rows, cudaStream_t st) {
+    return launch_hsvdetector(c, fi, fo, hs, Frame{ds, dss, dd, dds, width, rows}, st);
+  });
+}
+
+// ---- roundedcorners ---------------------------------------------------------------------------
+int b200vfx_roundmask_generate(b200vfx_ctx *c, int width, int height, int stride, unsigned border_radius_px,
+                               void *a8_out) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (width <= 0 || height <= 0 || stride < width || !a8_out) return fail(c, B200VFX_ERR_INVALID, "roundmask: bad geometry");
+  DeviceGuard g(c->device);
+  const int total_rows = (height + 1) & ~1;  // border/imp.rs:469-470
+  int r = -1;
+  if (border_radius_px != 0) {
+    const long lim = std::min(width, height) / 2;
+    r = (int)std::min<long>((long)std::min<unsigned>(border_radius_px, 0x7FFFFFFFu), lim);
+  }
+  Staged s{nullptr, 0, 0, (uint8_t *)a8_out, stride, (size_t)stride, total_rows, false};
+  return run_staged(c, s, [&](const uint8_t *, long, uint8_t *dd, long dds, int r0, int rows, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(stride, 256), (unsigned)rows);
+    roundmask_kernel<<<grid, 256, 0, st>>>(dd, dds, width, height, stride, r0, rows, r);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return 0;
+  });
+}
+
+// ---- videocompare / blockhash -----------------------------------------------------------------
+int b200vfx_blockhash_sums(b200vfx_ctx *c, int fmt, int width, int height, const void *src, int stride, int hw,
+                           int hh, uint32_t *sums) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (fmt != B200VFX_FORMAT_RGB && fmt != B200VFX_FORMAT_RGBA)
+    return fail(c, B200VFX_ERR_UNSUPPORTED, "videocompare: format %d is not RGB / RGBA", fmt);
+  if (hw <= 0 || hh <= 0 || hw > 4096 || hh > 4096 || !sums) return fail(c, B200VFX_ERR_INVALID, "blockhash: bad hash size");
+  const int bpp = fmt == B200VFX_FORMAT_RGB ? 3 : 4;
+  const size_t row = (size_t)width * bpp;
+  if (int rc = check_frame(c, width, height, src, stride, row, nullptr, 0, 0)) return rc;
+  if (width <= 0 || height <= 0 || width % hw || height % hh)
+    return fail(c, B200VFX_ERR_UNSUPPORTED,
+                "blockhash: %dx%d is not a multiple of the %dx%d hash grid (image_hasher's fractional-weight path is not implemented)",
+                width, height, hw, hh);
+  DeviceGuard g(c->device);
+  const int bw = width / hw, bh = height / hh;
+  const bool src_dev = is_device_ptr(src), sums_dev = is_device_ptr(sums);
+  cudaStream_t st = src_dev ? c->stream() : c->s_k;
+  const uint8_t *d_src = (const uint8_t *)src;
+  long d_stride = stride;
+  if (!src_dev) {  // upload (chunked so the copy engine and the reduction overlap is not needed: single pass, copy-bound)
+    d_stride = (long)((row + 15) & ~(size_t)15);
+    CU(c, c->stage_in.reserve((size_t)d_stride * height));
+    if ((size_t)stride == row && (size_t)d_stride == row)
+      CU(c, cudaMemcpyAsync(c->stage_in.p, src, row * (size_t)height, cudaMemcpyHostToDevice, st));
+    else
+      CU(c, cudaMemcpy2DAsync(c->stage_in.p, (size_t)d_stride, src, (size_t)stride, row, (size_t)height, cudaMemcpyHostToDevice, st));
+    d_src = c->stage_in.p;
+  }
+  uint32_t *d_sums = sums;
+  const size_t nb = sizeof(uint32_t) * (size_t)hw * hh;
+  if (!sums_dev) { CU(c, c->stage_sums.reserve(nb)); d_sums = (uint32_t *)c->stage_sums.p; }
+  CU(c, cudaMemsetAsync(d_sums, 0, nb, st));
+  // rows per CTA: aim for >= ~8 CTAs per SM
+  int rows_per_cta = bh;
+  const long ctas_target = 148L * 8;
+  if ((long)hw * hh < ctas_target) rows_per_cta = std::max(1, (int)((long)bh * hw * hh / ctas_target));
+  dim3 grid((unsigned)hw, (unsigned)hh, (unsigned)ceil_div(bh, rows_per_cta));
+  const bool vec = bpp == 4 && (bw % 4) == 0 && aligned(d_src, d_stride, 16);
+  if (vec) blockhash_sums_kernel<4, true><<<grid, 128, 0, st>>>(d_src, d_stride, bw, bh, hw, rows_per_cta, d_sums);
+  else if (bpp == 4) blockhash_sums_kernel<4, false><<<grid, 128, 0, st>>>(d_src, d_stride, bw, bh, hw, rows_per_cta, d_sums);
+  else blockhash_sums_kernel<3, false><<<grid, 128, 0, st>>>(d_src, d_stride, bw, bh, hw, rows_per_cta, d_sums);
+  c->launches++;
+  CU(c, cudaGetLastError());
+  if (!sums_dev) {
+    CU(c, cudaMemcpyAsync(sums, d_sums, nb, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+  } else if (!src_dev) {
+    CU(c, cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+void b200vfx_blockhash_bits(const uint32_t *sums, int hw, int hh, int width, int height, uint8_t *bits_out) {
+  // image_hasher 3.1.1 blockhash bit rule (recalled; parity unpinned -- SURVEY A.7): four bands,
+  // band median = element len/2 of the sorted band, bit = v > m || (v == m && m > half).
+  const int n = hw * hh, band = n / 4;
+  if (band <= 0) { for (int i = 0; i < n; i++) bits_out[i] = 0; return; }
+  const uint32_t half = (uint32_t)(((uint64_t)765 * (uint64_t)(width / hw) * (uint64_t)(height / hh)) / 2);
+  std::vector<uint32_t> tmp((size_t)band);
+  int b0 = 0;
+  for (; b0 + band <= n; b0 += band) {
+    std::copy(sums + b0, sums + b0 + band, tmp.begin());
+    std::nth_element(tmp.begin(), tmp.begin() + band / 2, tmp.end());
+    const uint32_t m = tmp[(size_t)band / 2];
+    for (int i = 0; i < band; i++) {
+      const uint32_t v = sums[b0 + i];
+      bits_out[b0 + i] = (uint8_t)(v > m || (v == m && m > half));
+    }
+  }
+  for (; b0 < n; b0++) bits_out[b0] = 0;
+}
+
+int b200vfx_hash_distance(const uint8_t *a, const uint8_t *b, int nbits) {
+  int d = 0;
+  for (int i = 0; i < nbits; i++) d += (a[i] != 0) != (b[i] != 0);
+  return d;
+}
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+// kernels.cuh -- sm_100a kernels of the per-pixel hot path (one kernel per element).
+//
+// All of these are HBM-streaming integer/byte kernels: no dense contraction, hence no tensor
+// cores.  What matters: coalesced full-sector accesses, enough loads in
+// flight per thread, grids that fill 148 SMs, and keeping the per-pixel instruction count
+// under the issue budget that the HBM roofline leaves (~55 thread-instr per 8 B pixel).
+#pragma once
+#include "pixel_math.cuh"
+
+namespace b200vfx {
+
+// streaming (read-once / write-once) accesses: keep them from displacing the L2-resident tables
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v) { __stcs(p, v); }
+__device__ __forceinline__ uint2 ld_stream_u2(const uint2 *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream_u2(uint2 *p, uint2 v) { __stcs(p, v); }
+
+// --------------------------------------------------------------------------------------------
+// colorlut: per-axis coefficient table for 8-bit input (exact partial evaluation of norm_comp:
+// only 256 inputs exist per channel, so the IEEE division leaves the pixel loop)
+// --------------------------------------------------------------------------------------------
+__global__ void colorlut_axis_table_kernel(float2 *axis, LutParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..767
+  if (i >= 768) return;
+  const int c = i >> 8, v = i & 255;
+  const float size_m1 = __fsub_rn((float)p.size, 1.0f);
+  axis[i] = make_float2(lut_pos((float)v, 255.0f, p.scale[c], p.offset[c], size_m1), 0.0f);
+}
+
+// --------------------------------------------------------------------------------------------
+// colorlut direct evaluation: one pixel per thread.
+// FMT 0 = RGBA (u8), 1 = RGBA64_LE, 2 = RGBA64_BE.   imp.rs:237-397
+// ALIGNED: rows are 4-byte (u8) / 8-byte (u16) aligned -> one vector load/store per pixel.
+// --------------------------------------------------------------------------------------------
+template <int FMT, bool ALIGNED>
+__global__ void __launch_bounds__(256) colorlut_direct_kernel(LutParams p, const uint8_t *__restrict__ src,
+                                                              long sstride, uint8_t *__restrict__ dst,
+                                                              long dstride, int width, int height) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= width) return;
+  for (int row = blockIdx.y; row < height; row += gridDim.y) {
+    if (FMT == 0) {
+      const uint8_t *s = src + (size_t)row * sstride + (size_t)x * 4;
+      uint8_t *d = dst + (size_t)row * dstride + (size_t)x * 4;
+      uint32_t px;
+      if (ALIGNED) px = ld_stream_u32(reinterpret_cast<const uint32_t *>(s));
+      else px = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
+      unsigned o[3];
+      colorlut_eval<255>(p, __ldg(&p.axis[px & 255u]).x, __ldg(&p.axis[256 + ((px >> 8) & 255u)]).x,
+                         __ldg(&p.axis[512 + ((px >> 16) & 255u)]).x, o);
+      const uint32_t out = o[0] | (o[1] << 8) | (o[2] << 16) | (px & 0xFF000000u);  // d[3] = s[3]
+      if (ALIGNED) st_stream_u32(reinterpret_cast<uint32_t *>(d), out);
+      else { d[0] = (uint8_t)out; d[1] = (uint8_t)(out >> 8); d[2] = (uint8_t)(out >> 16); d[3] = (uint8_t)(out >> 24); }
+    } else {
+      // rows are addressed in u16 units = stride/2 (imp.rs:317-318)
+      const uint8_t *s = src + (size_t)row * ((sstride / 2) * 2) + (size_t)x * 8;
+      uint8_t *d = dst + (size_t)row * ((dstride / 2) * 2) + (size_t)x * 8;
+      uint2 px;
+      if (ALIGNED) px = ld_stream_u2(reinterpret_cast<const uint2 *>(s));
+      else {
+        const uint16_t *s16 = reinterpret_cast<const uint16_t *>(s);
+        px.x = (uint32_t)s16[0] | ((uint32_t)s16[1] << 16);
+        px.y = (uint32_t)s16[2] | ((uint32_t)s16[3] << 16);
+      }
+      uint32_t w0 = px.x, w1 = px.y;
+      if (FMT == 2) { w0 = __byte_perm(w0, 0, 0x2301); w1 = __byte_perm(w1, 0, 0x2301); }  // from_be on an LE device
+      const float size_m1 = __fsub_rn((float)p.size, 1.0f);
+      const float fx = lut_pos((float)(w0 & 0xFFFFu), 65535.0f, p.scale[0], p.offset[0], size_m1);
+      const float fy = lut_pos((float)(w0 >> 16), 65535.0f, p.scale[1], p.offset[1], size_m1);
+      const float fz = lut_pos((float)(w1 & 0xFFFFu), 65535.0f, p.scale[2], p.offset[2], size_m1);
+      unsigned o[3];
+      colorlut_eval<65535>(p, fx, fy, fz, o);
+      uint32_t o0 = o[0] | (o[1] << 16), o1 = o[2];
+      if (FMT == 2) { o0 = __byte_perm(o0, 0, 0x2301); o1 = __byte_perm(o1, 0, 0x2301); }
+      o1 = (o1 & 0xFFFFu) | (px.y & 0xFFFF0000u);  // alpha word copied raw, never byte-swapped (imp.rs:345,394)
+      if (ALIGNED) st_stream_u2(reinterpret_cast<uint2 *>(d), make_uint2(o0, o1));
+      else {
+        uint16_t *d16 = reinterpret_cast<uint16_t *>(d);
+        d16[0] = (uint16_t)o0; d16[1] = (uint16_t)(o0 >> 16); d16[2] = (uint16_t)o1; d16[3] = (uint16_t)(o1 >> 16);
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// colorlut memoisation for 8-bit RGBA.  apply_1d/apply_3d are pure functions of the 24-bit
+// colour, and `location` is only mutable in READY (imp.rs:72-76), so the element evaluates
+// them ONCE per start() for all 2^24 colours with the exact direct evaluator above and keeps
+// the 64 MiB answer table resident in B200's 126 MB L2.  Bit-exact by construction.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colorlut_memo_build_kernel(LutParams p, uint32_t *__restrict__ memo) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;  // idx = r | g<<8 | b<<16
+  unsigned o[3];
+  colorlut_eval<255>(p, __ldg(&p.axis[idx & 255u]).x, __ldg(&p.axis[256 + ((idx >> 8) & 255u)]).x,
+                     __ldg(&p.axis[512 + (idx >> 16)]).x, o);
+  memo[idx] = o[0] | (o[1] << 8) | (o[2] << 16);
+}
+
+// per-channel 256-entry answer tables for a 1D LUT (768 bytes, lives in shared memory)
+__global__ void colorlut_memo1d_build_kernel(LutParams p, uint8_t *__restrict__ memo1d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 768) return;
+  const int c = i >> 8;
+  memo1d[i] = (uint8_t)quantize_round<255>(sample_1d(p.lut1d + c * p.size, p.size - 1, __ldg(&p.axis[i]).x));
+}
+
+// The pixel loop for RGBA with a memo table: out = memo[px & 0xFFFFFF] | (px & 0xFF000000).
+// A warp owns 32*PX consecutive pixels; lane L touches pixels L, L+32, ... so every gather
+// instruction covers 32 CONSECUTIVE pixels (spatially coherent colours -> few distinct L1
+// lines per gather) while the frame loads/stores stay fully coalesced 128 B per instruction.
+template <int PX>
+__global__ void __launch_bounds__(256) colorlut_memo_apply_kernel(const uint32_t *__restrict__ memo,
+                                                                  const uint8_t *__restrict__ src, long sstride,
+                                                                  uint8_t *__restrict__ dst, long dstride,
+                                                                  int width, int height) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x0 = (blockIdx.x * (blockDim.x >> 5) + warp) * (32 * PX) + lane;
+  if (x0 - lane >= width) return;
+  for (int row = blockIdx.y; row < height; row += gridDim.y) {
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)row * sstride);
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst + (size_t)row * dstride);
+    uint32_t px[PX], o[PX];
+#pragma unroll
+    for (int k = 0; k < PX; k++) px[k] = (x0 + 32 * k < width) ? ld_stream_u32(s + x0 + 32 * k) : 0u;
+#pragma unroll
+    for (int k = 0; k < PX; k++) o[k] = __ldg(memo + (px[k] & 0x00FFFFFFu));
+#pragma unroll
+    for (int k = 0; k < PX; k++)
+      if (x0 + 32 * k < width) st_stream_u32(d + x0 + 32 * k, o[k] | (px[k] & 0xFF000000u));
+  }
+}
+
+// 1D LUT: three 256-byte tables in shared memory
+template <int PX>
+__global__ void __launch_bounds__(256) colorlut_memo1d_apply_kernel(const uint8_t *__restrict__ memo1d,
+                                                                    const uint8_t *__restrict__ src, long sstride,
+                                                                    uint8_t *__restrict__ dst, long dstride,
+                                                                    int width, int height) {
+  __shared__ uint8_t tab[768];
+  for (int i = threadIdx.x; i < 768 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t *>(tab)[i] = __ldg(reinterpret_cast<const uint32_t *>(memo1d) + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x0 = (blockIdx.x * (blockDim.x >> 5) + warp) * (32 * PX) + lane;
+  if (x0 - lane >= width) return;
+  for (int row = blockIdx.y; row < height; row += gridDim.y) {
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)row * sstride);
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst + (size_t)row * dstride);
+    uint32_t px[PX];
+#pragma unroll
+    for (int k = 0; k < PX; k++) px[k] = (x0 + 32 * k < width) ? ld_stream_u32(s + x0 + 32 * k) : 0u;
+#pragma unroll
+    for (int k = 0; k < PX; k++) {
+      const uint32_t r = tab[px[k] & 255u], g = tab[256 + ((px[k] >> 8) & 255u)], b = tab[512 + ((px[k] >> 16) & 255u)];
+      if (x0 + 32 * k < width) st_stream_u32(d + x0 + 32 * k, r | (g << 8) | (b << 16) | (px[k] & 0xFF000000u));
+    }
+  }
+}
+
+// generic byte-addressed fallback for rows that are not 4-byte aligned
+__global__ void colorlut_memo_apply_bytes_kernel(const uint32_t *__restrict__ memo, const uint8_t *__restrict__ memo1d,
+                                                 const uint8_t *__restrict__ src, long sstride,
+                                                 uint8_t *__restrict__ dst, long dstride, int width, int height) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= width) return;
+  for (int row = blockIdx.y; row < height; row += gridDim.y) {
+    const uint8_t *s = src + (size_t)row * sstride + (size_t)x * 4;
+    uint8_t *d = dst + (size_t)row * dstride + (size_t)x * 4;
+    const uint32_t r = s[0], g = s[1], b = s[2];
+    if (memo) {
+      const uint32_t o = __ldg(memo + (r | (g << 8) | (b << 16)));
+      d[0] = (uint8_t)o; d[1] = (uint8_t)(o >> 8); d[2] = (uint8_t)(o >> 16);
+    } else {
+      d[0] = __ldg(memo1d + r); d[1] = __ldg(memo1d + 256 + g); d[2] = __ldg(memo1d + 512 + b);
+    }
+    d[3] = s[3];
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// hsvfilter (in place) and hsvdetector.   hsvfilter/imp.rs:76-120, hsvdetector/imp.rs:100-160
+// BPP 3|4; COFF = byte offset of the first colour byte (1 for xRGB/ARGB/xBGR/ABGR); BGR = byte order.
+// 4-bpp pixels move as one 32-bit word when the rows are 4-byte aligned.
+// --------------------------------------------------------------------------------------------
+template <int BPP, int COFF, bool BGR, bool ALIGNED>
+__global__ void __launch_bounds__(256) hsvfilter_kernel(HsvFilterSettings st, uint8_t *__restrict__ data,
+                                                        long stride, int width, int height) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= width) return;
+  for (int row = blockIdx.y; row < height; row += gridDim.y) {
+    uint8_t *p = data + (size_t)row * stride + (size_t)x * BPP;
+    if (BPP == 4 && ALIGNED) {
+      const uint32_t px = *reinterpret_cast<const uint32_t *>(p);
+      unsigned c0 = (px >> (8 * COFF)) & 255u, c1 = (px >> (8 * COFF + 8)) & 255u, c2 = (px >> (8 * COFF + 16)) & 255u;
+      unsigned r = BGR ? c2 : c0, g = c1, b = BGR ? c0 : c2;
+      hsvfilter_px(st, r, g, b);
+      c0 = BGR ? b : r; c1 = g; c2 = BGR ? r : b;
+      const uint32_t keep = COFF ? (px & 0x000000FFu) : (px & 0xFF000000u);
+      *reinterpret_cast<uint32_t *>(p) = keep | (c0 << (8 * COFF)) | (c1 << (8 * COFF + 8)) | (c2 << (8 * COFF + 16));
+    } else {
+      unsigned c0 = p[COFF], c1 = p[COFF + 1], c2 = p[COFF + 2];
+      unsigned r = BGR ? c2 : c0, g = c1, b = BGR ? c0 : c2;
+      hsvfilter_px(st, r, g, b);
+      p[COFF] = (uint8_t)(BGR ? b : r); p[COFF + 1] = (uint8_t)g; p[COFF + 2] = (uint8_t)(BGR ? r : b);
+    }
+  }
+}
+
+// IBPP/ICOFF/IBGR describe the input pixel; OCOFF/OBGR the 4-byte output pixel (alpha at 3 if OCOFF==0 else 0)
+template <int IBPP, int ICOFF, bool IBGR, int OCOFF, bool OBGR, bool ALIGNED>
+__global__ void __launch_bounds__(256) hsvdetector_kernel(HsvDetectSettings st, const uint8_t *__restrict__ src,
+                                                          long sstride, uint8_t *__restrict__ dst, long dstride,
+                                                          int width, int height) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= width) return;
+  for (int row = blockIdx.y; row < height; row += gridDim.y) {
+    const uint8_t *ip = src + (size_t)row * sstride + (size_t)x * IBPP;
+    uint8_t *op = dst + (size_t)row * dstride + (size_t)x * 4;
+    unsigned c0, c1, c2;
+    if (IBPP == 4 && ALIGNED) {
+      const uint32_t px = ld_stream_u32(reinterpret_cast<const uint32_t *>(ip));
+      c0 = (px >> (8 * ICOFF)) & 255u; c1 = (px >> (8 * ICOFF + 8)) & 255u; c2 = (px >> (8 * ICOFF + 16)) & 255u;
+    } else {
+      c0 = ip[ICOFF]; c1 = ip[ICOFF + 1]; c2 = ip[ICOFF + 2];
+    }
+    const unsigned r = IBGR ? c2 : c0, g = c1, b = IBGR ? c0 : c2;
+    const unsigned a = hsvdetect_px(st, r, g, b) ? 255u : 0u;
+    const unsigned o0 = OBGR ? b : r, o1 = g, o2 = OBGR ? r : b;
+    const uint32_t out = (o0 << (8 * OCOFF)) | (o1 << (8 * OCOFF + 8)) | (o2 << (8 * OCOFF + 16)) | (OCOFF ? a : (a << 24));
+    if (ALIGNED) st_stream_u32(reinterpret_cast<uint32_t *>(op), out);
+    else { op[0] = (uint8_t)out; op[1] = (uint8_t)(out >> 8); op[2] = (uint8_t)(out >> 16); op[3] = (uint8_t)(out >> 24); }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// videocompare / blockhash block sums.  hashed_image.rs:24-64 -> image_hasher blockhash fast path.
+// One CTA reduces a (bw x rows) tile that lies inside ONE hash block: registers -> warp shuffle
+// -> shared -> a single atomicAdd on the bin.  Integer adds are order independent => exact.
+// VEC: RGBA rows 16-byte aligned and bw % 4 == 0 -> uint4 loads, R+G+B by one dp4a per pixel.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
+
+template <int BPP, bool VEC>
+__global__ void __launch_bounds__(128) blockhash_sums_kernel(const uint8_t *__restrict__ src, long stride, int bw,
+                                                             int bh, int hw, int rows_per_cta,
+                                                             uint32_t *__restrict__ sums) {
+  const int bx = blockIdx.x, by = blockIdx.y;
+  const int y0 = by * bh + blockIdx.z * rows_per_cta;
+  const int y1 = min(y0 + rows_per_cta, (by + 1) * bh);
+  uint32_t acc = 0;
+  if (VEC) {  // BPP == 4
+    const int n4 = bw >> 2;
+    for (int y = y0; y < y1; y++) {
+      const uint4 *row = reinterpret_cast<const uint4 *>(src + (size_t)y * stride + (size_t)bx * bw * 4);
+      for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const uint4 q = __ldcs(row + i);
+        acc += (q.x >> 24) ? __dp4a(q.x, 0x00010101u, 0u) : 765u;   // A==0 counts as white (765)
+        acc += (q.y >> 24) ? __dp4a(q.y, 0x00010101u, 0u) : 765u;
+        acc += (q.z >> 24) ? __dp4a(q.z, 0x00010101u, 0u) : 765u;
+        acc += (q.w >> 24) ? __dp4a(q.w, 0x00010101u, 0u) : 765u;
+      }
+    }
+  } else {
+    for (int y = y0; y < y1; y++) {
+      const uint8_t *row = src + (size_t)y * stride + (size_t)bx * bw * BPP;
+      for (int i = threadIdx.x; i < bw; i += blockDim.x) {
+        const uint8_t *p = row + (size_t)i * BPP;
+        uint32_t s = (uint32_t)p[0] + p[1] + p[2];
+        if (BPP == 4 && p[3] == 0) s = 765u;
+        acc += s;
+      }
+    }
+  }
+  __shared__ uint32_t wsum[4];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += wsum[w];
+    atomicAdd(sums + by * hw + bx, t);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// roundedcorners A8 mask.  border/imp.rs:57-180 (cairo fill + 1px stroke), restated analytically:
+// only the four r x r corner boxes are partially covered; coverage on a 16x16 integer sample grid.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned mul_un8(unsigned a, unsigned b) {  // pixman MUL_UN8
+  const unsigned t = a * b + 0x80u;
+  return ((t >> 8) + t) >> 8;
+}
+
+// a8 points at absolute row y0 of the plane; `pitch` is the byte distance between rows of a8,
+// `stride` the number of bytes per row that belong to the plane (A420 stride[3]).
+__global__ void __launch_bounds__(256) roundmask_kernel(uint8_t *__restrict__ a8, long pitch, int width, int height,
+                                                        int stride, int y0, int rows, int r) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= stride || (int)blockIdx.y >= rows) return;
+  const int y = y0 + (int)blockIdx.y;
+  uint8_t v;
+  if (r < 0) v = 0xFF;                       // border-radius-px == 0: alpha_mem.fill(0xff) (:123-128)
+  else if (x >= width || y >= height) v = 0; // pre-zeroed memory outside the surface (:130)
+  else {
+    const int i = (x < r) ? (r - 1 - x) : ((x >= width - r) ? (x - (width - r)) : -1);
+    const int j = (y < r) ? (r - 1 - y) : ((y >= height - r) ? (y - (height - r)) : -1);
+    if (i < 0 || j < 0) v = 0xFF;
+    else {
+      const long long S = 16;
+      const long long rf = 2 * S * r, ro = rf + S, ri = rf - S;
+      const long long R2f = rf * rf, R2o = ro * ro, R2i = ri * ri;
+      int nf = 0, ns = 0;
+      for (int b = 0; b < 16; b++) {
+        const long long dy = 2 * S * j + 2 * b + 1;
+        for (int a = 0; a < 16; a++) {
+          const long long dx = 2 * S * i + 2 * a + 1;
+          const long long d2 = dx * dx + dy * dy;
+          nf += (d2 <= R2f);
+          ns += (d2 <= R2o && d2 >= R2i);
+        }
+      }
+      const unsigned af = (unsigned)((nf * 255 + 128) / 256), as = (unsigned)((ns * 255 + 128) / 256);
+      v = (uint8_t)min(as + mul_un8(af, 255u - as), 255u);
+    }
+  }
+  a8[(size_t)blockIdx.y * pitch + x] = v;
+}
+
+}  // namespace b200vfx

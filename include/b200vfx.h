@@ -1,0 +1,159 @@
+/*
+ * b200vfx.h -- C ABI of libb200vfx.so: the B200 (sm_100a) implementation of the
+ * per-pixel video-filter hot path of sdroege/gst-plugin-rs.
+ *
+ * This is the drop-in boundary: a gstreamer-rs BaseTransform / VideoFilter /
+ * VideoAggregator subclass keeps the reference's element surface (factory
+ * names, caps, GObject properties) and replaces the body of its
+ * transform_frame* / aggregate_frames vfunc with ONE call below.  Every entry
+ * point cites the reference code it replaces (paths relative to the
+ * gst-plugins-rs tree).  INTEGRATION.md shows the Rust `extern "C"` binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; frames are {format, width, height, data,
+ *    stride} exactly as a mapped GstVideoFrame exposes them (plane 0).
+ *  - `src`/`dst`/`data` may be HOST pointers (pageable or pinned) or DEVICE
+ *    pointers; the library detects which (cudaPointerGetAttributes).
+ *      host   : synchronous call; H2D copy, kernel and D2H copy are pipelined
+ *               by row chunks on internal streams; on return `dst` is filled.
+ *      device : the kernel is enqueued on the context's stream
+ *               (b200vfx_ctx_set_stream) and the call returns immediately;
+ *               use b200vfx_ctx_synchronize() or your own stream sync.
+ *  - return 0 on success, <0 on error (maps to gst::FlowError::Error /
+ *    NotNegotiated); b200vfx_last_error() gives the message.
+ *  - one context per element instance; a context is not re-entrant (GStreamer
+ *    serialises transform calls per element with the pad stream lock).
+ *  - there is NO CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef B200VFX_H
+#define B200VFX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VFX_ABI_VERSION 1
+
+/* video/x-raw formats on this path (names follow GstVideoFormat) */
+typedef enum {
+  B200VFX_FORMAT_RGBX = 0,
+  B200VFX_FORMAT_XRGB = 1,
+  B200VFX_FORMAT_BGRX = 2,
+  B200VFX_FORMAT_XBGR = 3,
+  B200VFX_FORMAT_RGBA = 4,
+  B200VFX_FORMAT_ARGB = 5,
+  B200VFX_FORMAT_BGRA = 6,
+  B200VFX_FORMAT_ABGR = 7,
+  B200VFX_FORMAT_RGB = 8,
+  B200VFX_FORMAT_BGR = 9,
+  B200VFX_FORMAT_RGBA64_LE = 10,
+  B200VFX_FORMAT_RGBA64_BE = 11,
+  B200VFX_FORMAT_I420 = 12,
+  B200VFX_FORMAT_A420 = 13
+} b200vfx_format;
+
+typedef enum {
+  B200VFX_OK = 0,
+  B200VFX_ERR_INVALID = -1,      /* bad argument                 -> FlowError::Error         */
+  B200VFX_ERR_CUDA = -2,         /* CUDA runtime / no device     -> FlowError::Error         */
+  B200VFX_ERR_NOT_NEGOTIATED = -3, /* e.g. colorlut without a LUT -> FlowError::Error (imp.rs:210-213) */
+  B200VFX_ERR_UNSUPPORTED = -4,  /* format not on this element's caps                        */
+  B200VFX_ERR_PARSE = -5,        /* .cube InvalidLut             -> ResourceError::Read      */
+  B200VFX_ERR_IO = -6            /* .cube Io error               -> ResourceError::Read      */
+} b200vfx_status;
+
+typedef struct b200vfx_ctx b200vfx_ctx;
+
+/* ---- library / context -------------------------------------------------- */
+int b200vfx_abi_version(void);
+int b200vfx_device_count(void); /* <=0: no usable CUDA device */
+
+/* Created in BaseTransformImpl::start() (or first set_caps), destroyed in stop().
+ * device < 0 selects the current CUDA device. */
+int b200vfx_ctx_create(b200vfx_ctx **out, int device);
+void b200vfx_ctx_destroy(b200vfx_ctx *ctx);
+const char *b200vfx_last_error(const b200vfx_ctx *ctx); /* ctx may be NULL: last create/parse error of this thread */
+
+/* stream used for DEVICE-pointer calls (a cudaStream_t / CUstream handle; NULL = legacy default stream).
+ * Default: a non-blocking stream owned by the context. */
+int b200vfx_ctx_set_stream(b200vfx_ctx *ctx, void *cuda_stream);
+int b200vfx_ctx_synchronize(b200vfx_ctx *ctx);
+/* rows per H2D/kernel/D2H pipeline chunk for HOST-pointer calls (0 = auto) */
+int b200vfx_ctx_set_chunk_rows(b200vfx_ctx *ctx, int rows);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t b200vfx_ctx_kernel_launches(const b200vfx_ctx *ctx);
+
+/* Page-locked host memory for a GstAllocator handed out in
+ * propose_allocation()/decide_allocation(): buffers allocated here are copied
+ * with full-speed asynchronous DMA. */
+void *b200vfx_host_alloc(size_t bytes);
+void b200vfx_host_free(void *p);
+
+/* ---- .cube parser -------------------------------------------------------
+ * replaces CubeLut::parse / parse_file, video/colorlut/src/parser.rs:105-281
+ * (same grammar, same error cases).  kind: 1 = LUT_1D, 3 = LUT_3D.
+ * values: n x [r,g,b] f32 in file order, n = size (1D) or size^3 (3D, R
+ * fastest); release with b200vfx_cube_free().  err may be NULL. */
+int b200vfx_cube_parse(const char *text, size_t len, int *kind, int *size, float **values,
+                       float domain_scale[3], float domain_offset[3], char *err, size_t errlen);
+int b200vfx_cube_parse_file(const char *path, int *kind, int *size, float **values,
+                            float domain_scale[3], float domain_offset[3], char *err, size_t errlen);
+void b200vfx_cube_free(float *values);
+
+/* ---- colorlut -----------------------------------------------------------
+ * ColorLut::start  (video/colorlut/src/colorlut/imp.rs:168-194): parse `location` and upload. */
+int b200vfx_colorlut_load_file(b200vfx_ctx *ctx, const char *location);
+/* upload an already parsed LUT (State{lut}, imp.rs:50-53,191) */
+int b200vfx_colorlut_set_lut(b200vfx_ctx *ctx, int kind, int size, const float *values,
+                             const float domain_scale[3], const float domain_offset[3]);
+/* ColorLut::stop (imp.rs:196-199) */
+int b200vfx_colorlut_clear(b200vfx_ctx *ctx);
+/* evaluation strategy for 8-bit RGBA: 0 = auto (memoised 2^24-entry table, L2 resident),
+ * 1 = direct (trilinear evaluated per pixel).  Results are bit-identical. */
+int b200vfx_colorlut_set_mode(b200vfx_ctx *ctx, int mode);
+/* ColorLut::transform_frame (imp.rs:203-224) incl. transform_rgba / transform_rgba64<LE|BE>
+ * 1D and 3D (imp.rs:226-397).  fmt: RGBA, RGBA64_LE, RGBA64_BE.  Never in place. */
+int b200vfx_colorlut_process(b200vfx_ctx *ctx, int fmt, int width, int height, const void *src,
+                             int src_stride, void *dst, int dst_stride);
+
+/* ---- hsvfilter ----------------------------------------------------------
+ * HsvFilter::transform_frame_ip + hsv_filter (video/hsv/src/hsvfilter/imp.rs:76-120,323-376).
+ * In place.  Settings by value = the per-frame snapshot of imp.rs:85.
+ * fmt: RGBx xRGB BGRx xBGR RGBA ARGB BGRA ABGR RGB BGR. */
+int b200vfx_hsvfilter_process(b200vfx_ctx *ctx, int fmt, int width, int height, void *data,
+                              int stride, float hue_shift, float saturation_mul,
+                              float saturation_off, float value_mul, float value_off);
+
+/* ---- hsvdetector --------------------------------------------------------
+ * HsvDetector::transform_frame + hsv_detect (video/hsv/src/hsvdetector/imp.rs:100-160,423-707).
+ * in_fmt: RGBx xRGB BGRx xBGR RGB BGR; out_fmt: RGBA ARGB BGRA ABGR. */
+int b200vfx_hsvdetector_process(b200vfx_ctx *ctx, int in_fmt, int out_fmt, int width, int height,
+                                const void *src, int src_stride, void *dst, int dst_stride,
+                                float hue_ref, float hue_var, float saturation_ref,
+                                float saturation_var, float value_ref, float value_var);
+
+/* ---- roundedcorners -----------------------------------------------------
+ * RoundedCorners::generate_alpha_mask + draw_rounded_corners
+ * (video/videofx/src/border/imp.rs:57-180).  Writes stride * round_up_2(height) bytes (A8). */
+int b200vfx_roundmask_generate(b200vfx_ctx *ctx, int width, int height, int stride,
+                               unsigned border_radius_px, void *a8_out);
+
+/* ---- videocompare -------------------------------------------------------
+ * HasherEngine::hash_image for HashAlg::Blockhash (video/videofx/src/videocompare/
+ * hashed_image.rs:24-64,110-130 -> image_hasher 3.1.1): the hw*hh u32 block sums of
+ * (A==0 ? 765 : R+G+B).  fmt: RGB or RGBA.  Requires width%hw==0 && height%hh==0
+ * (image_hasher's integer fast path).  `sums` may be a host or device pointer. */
+int b200vfx_blockhash_sums(b200vfx_ctx *ctx, int fmt, int width, int height, const void *src,
+                           int stride, int hw, int hh, uint32_t *sums);
+/* median/bit rule + Hamming distance (host side, tiny): bits_out hw*hh bytes of 0/1 */
+void b200vfx_blockhash_bits(const uint32_t *sums, int hw, int hh, int width, int height,
+                            uint8_t *bits_out);
+int b200vfx_hash_distance(const uint8_t *bits_a, const uint8_t *bits_b, int nbits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VFX_H */

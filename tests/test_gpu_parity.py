@@ -1,0 +1,369 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs.  Bit-exact everywhere (all outputs are u8/u16/u32)."""
+import os
+
+import numpy as np
+import pytest
+
+import b200vfx
+import oracle_binding as orc
+from b200vfx import synth
+
+pytestmark = pytest.mark.gpu
+NT = max(1, min(32, os.cpu_count() or 1))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = b200vfx.Context(0)
+    yield c
+    c.close()
+
+
+def all_colors_frame(fmt="RGBA"):
+    idx = np.arange(1 << 24, dtype=np.uint32)
+    r, g, b = (idx & 0xFF).astype(np.uint8), ((idx >> 8) & 0xFF).astype(np.uint8), ((idx >> 16) & 0xFF).astype(np.uint8)
+    a = (idx * 7 + 3).astype(np.uint8)
+    planes = {"R": r, "G": g, "B": b, "A": a}
+    order = synth._ORDER[fmt]
+    return np.stack([planes[ch] for ch in order], axis=-1).reshape(4096, 4096 * len(order))
+
+
+def set_cube(ctx, cube):
+    ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+
+
+def gpu_colorlut(ctx, fmt, w, h, src, dstride=None, fill=0x5A):
+    dstride = dstride or src.shape[1]
+    dst = np.full((h, dstride), fill, np.uint8)
+    ctx.colorlut_process(fmt, w, h, src, src.shape[1], dst, dstride)
+    return dst
+
+
+# ---- colorlut ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n,kind,dom", [(33, "mix", None), (65, "mix", None), (2, "invert", None),
+                                        (17, "mix", ((-0.25, 0.0, 0.1), (1.5, 0.75, 0.9)))])
+def test_colorlut_rgba_all_colors(ctx, mode, n, kind, dom):
+    cube = orc.cube_parse(synth.cube_text_3d(n, kind, domain=dom))
+    set_cube(ctx, cube)
+    ctx.colorlut_set_mode(mode)
+    frame = all_colors_frame("RGBA")
+    exp = orc.colorlut_apply(cube, "RGBA", 4096, 4096, frame, threads=NT)
+    got = gpu_colorlut(ctx, "RGBA", 4096, 4096, frame)
+    ctx.colorlut_set_mode(0)
+    assert (got == exp).all()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_colorlut_1d_rgba_all_values(ctx, mode):
+    cube = orc.cube_parse(synth.cube_text_1d(1024, 2.2, domain=((0.0, -0.5, 0.1), (1.0, 1.5, 0.6))))
+    set_cube(ctx, cube)
+    ctx.colorlut_set_mode(mode)
+    frame = all_colors_frame("RGBA")[:512]
+    exp = orc.colorlut_apply(cube, "RGBA", 4096, 512, frame, threads=NT)
+    got = gpu_colorlut(ctx, "RGBA", 4096, 512, frame)
+    ctx.colorlut_set_mode(0)
+    assert (got == exp).all()
+
+
+def test_colorlut_appendix_c_vectors(ctx):
+    px = np.array([[95, 130, 194, 1, 217, 207, 235, 2, 15, 163, 33, 3]], np.uint8)
+    for n, exp in ((33, [(35, 182, 140), (185, 230, 220), (1, 204, 70)]), (2, [(95, 130, 140), (217, 207, 220), (15, 163, 70)])):
+        set_cube(ctx, orc.cube_from_values(3, n, synth.lut_values_3d(n, "mix")))
+        for mode in (0, 1):
+            ctx.colorlut_set_mode(mode)
+            out = gpu_colorlut(ctx, "RGBA", 3, 1, px)[0].reshape(3, 4)
+            assert [tuple(p[:3]) for p in out.tolist()] == exp and out[:, 3].tolist() == [1, 2, 3]
+    ctx.colorlut_set_mode(0)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("w,h,spad,dpad,off", [(1, 1, 0, 0, 0), (3, 2, 4, 8, 0), (129, 7, 12, 4, 0), (640, 9, 0, 16, 0),
+                                               (257, 5, 3, 5, 1), (1000, 3, 0, 0, 2), (4097, 2, 4, 0, 0)])
+def test_colorlut_rgba_strides_and_alignment(ctx, mode, w, h, spad, dpad, off):
+    cube = orc.cube_parse(synth.cube_text_3d(9, "mix"))
+    set_cube(ctx, cube)
+    ctx.colorlut_set_mode(mode)
+    sstride, dstride = 4 * w + spad, 4 * w + dpad
+    raw = np.full(h * sstride + 8, 0xA5, np.uint8)
+    src = raw[off:off + h * sstride].reshape(h, sstride)
+    src[:, :4 * w] = synth.frame_noise("RGBA", w, h, 99)[:, :4 * w]
+    exp = orc.colorlut_apply(cube, "RGBA", w, h, np.ascontiguousarray(src), dst_stride=dstride)
+    rawd = np.full(h * dstride + 8, 0x5A, np.uint8)
+    dst = rawd[off:off + h * dstride].reshape(h, dstride)
+    ctx.colorlut_process("RGBA", w, h, src.ctypes.data, sstride, dst.ctypes.data, dstride)
+    ctx.colorlut_set_mode(0)
+    assert (dst == exp).all()          # includes untouched row padding (0x5A)
+    assert (rawd[:off] == 0x5A).all() and (rawd[off + h * dstride:] == 0x5A).all()
+
+
+@pytest.mark.parametrize("fmt", ["RGBA64_LE", "RGBA64_BE"])
+@pytest.mark.parametrize("lut", ["3d33", "3d5dom", "1d"])
+def test_colorlut_rgba64(ctx, fmt, lut):
+    if lut == "3d33":
+        cube = orc.cube_parse(synth.cube_text_3d(33, "mix"))
+    elif lut == "3d5dom":
+        cube = orc.cube_parse(synth.cube_text_3d(5, "mix", domain=((0.0, 0.1, 0.0), (1.0, 0.9, 2.0))))
+    else:
+        cube = orc.cube_parse(synth.cube_text_1d(4096, 2.2, domain=((0.0, 0.0, 0.0), (0.5, 1.0, 2.0))))
+    set_cube(ctx, cube)
+    w, h = 1031, 64
+    for frame, sstride, dstride in ((synth.frame_noise(fmt, w, h, 77, stride=8 * w + 16), 8 * w + 16, 8 * w + 8),
+                                    (synth.frame_ramps(fmt, w, h), 8 * w, 8 * w),
+                                    (synth.frame_noise(fmt, w, h, 78, stride=8 * w + 2), 8 * w + 2, 8 * w + 6)):
+        exp = orc.colorlut_apply(cube, fmt, w, h, frame, dst_stride=dstride, threads=NT)
+        got = gpu_colorlut(ctx, fmt, w, h, frame, dstride)
+        assert (got == exp).all()
+    # boundary values incl. 0/1/max in every channel
+    vals = np.array([0, 1, 2, 255, 256, 32767, 32768, 65534, 65535], np.uint16)
+    grid = np.stack(np.meshgrid(vals, vals, vals, vals[:3], indexing="ij"), -1).reshape(1, -1, 4)
+    dt = "<u2" if fmt.endswith("LE") else ">u2"
+    frame = grid.astype(dt).view(np.uint8).reshape(1, -1)
+    wpx = frame.shape[1] // 8
+    exp = orc.colorlut_apply(cube, fmt, wpx, 1, frame)
+    assert (gpu_colorlut(ctx, fmt, wpx, 1, frame) == exp).all()
+
+
+def test_colorlut_nan_inf_entries(ctx):
+    v = synth.lut_values_3d(5, "mix")
+    v[7] = [np.nan, np.inf, -np.inf]
+    v[60] = [1e30, -1e30, np.nan]
+    cube = orc.cube_from_values(3, 5, v)
+    set_cube(ctx, cube)
+    frame = all_colors_frame("RGBA")[:1024]
+    exp = orc.colorlut_apply(cube, "RGBA", 4096, 1024, frame, threads=NT)
+    for mode in (0, 1):
+        ctx.colorlut_set_mode(mode)
+        assert (gpu_colorlut(ctx, "RGBA", 4096, 1024, frame) == exp).all()
+    ctx.colorlut_set_mode(0)
+    f16 = synth.frame_noise("RGBA64_LE", 512, 64, 5)
+    assert (gpu_colorlut(ctx, "RGBA64_LE", 512, 64, f16) == orc.colorlut_apply(cube, "RGBA64_LE", 512, 64, f16)).all()
+
+
+def test_colorlut_errors_and_lifecycle(ctx, tmp_path):
+    ctx.colorlut_clear()
+    src = np.zeros((2, 8), np.uint8)
+    with pytest.raises(b200vfx.B200VfxError) as e:
+        ctx.colorlut_process("RGBA", 2, 2, src, 8, src.copy(), 8)
+    assert e.value.code == b200vfx.ERR_NOT_NEGOTIATED and "No LUT configured" in e.value.msg
+    with pytest.raises(b200vfx.B200VfxError) as e:
+        ctx.colorlut_load_file(str(tmp_path / "nope.cube"))
+    assert e.value.code == b200vfx.ERR_IO
+    bad = tmp_path / "bad.cube"
+    bad.write_text("LUT_3D_SIZE 2\n0 0 0\n")
+    with pytest.raises(b200vfx.B200VfxError) as e:
+        ctx.colorlut_load_file(str(bad))
+    assert e.value.code == b200vfx.ERR_PARSE and "Failed to parse LUT file" in e.value.msg
+    good = tmp_path / "good.cube"
+    good.write_text(synth.cube_text_3d(4, "invert"))
+    ctx.colorlut_load_file(str(good))
+    with pytest.raises(b200vfx.B200VfxError) as e:
+        ctx.colorlut_process("BGRA", 2, 2, src, 8, src.copy(), 8)
+    assert e.value.code == b200vfx.ERR_UNSUPPORTED
+    with pytest.raises(b200vfx.B200VfxError):
+        ctx.colorlut_process("RGBA", 4, 2, src, 8, src.copy(), 8)   # stride < row bytes
+    ctx.colorlut_process("RGBA", 0, 0, None, 0, None, 0)            # empty frame is a no-op
+    px = np.array([[10, 20, 30, 40, 250, 128, 0, 7]], np.uint8)
+    out = gpu_colorlut(ctx, "RGBA", 2, 1, px)
+    assert out[0].tolist() == [245, 235, 225, 40, 5, 127, 255, 7]
+
+
+def test_colorlut_device_pointers_and_full_size(ctx):
+    torch = pytest.importorskip("torch")
+    cube = orc.cube_parse(synth.cube_text_3d(33, "mix"))
+    set_cube(ctx, cube)
+    w, h = 3840, 2160
+    for frame in (synth.frame_ramps("RGBA", w, h), synth.frame_noise("RGBA", w, h, 0x5EED0002)):
+        exp = orc.colorlut_apply(cube, "RGBA", w, h, frame, threads=NT)
+        d_src = torch.from_numpy(frame).cuda()
+        d_dst = torch.zeros_like(d_src)
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        for mode in (0, 1):
+            ctx.colorlut_set_mode(mode)
+            d_dst.zero_()
+            ctx.colorlut_process("RGBA", w, h, d_src, 4 * w, d_dst, 4 * w)
+            torch.cuda.synchronize()
+            assert (d_dst.cpu().numpy() == exp).all()
+        ctx.colorlut_set_mode(0)
+        # host path (chunked H2D/kernel/D2H pipeline) with a pinned source and pageable destination
+        pin = torch.from_numpy(frame).pin_memory()
+        assert (gpu_colorlut(ctx, "RGBA", w, h, pin.numpy()) == exp).all()
+        # properties at full size: alpha untouched, idempotent under the identity LUT
+        assert (exp.reshape(-1, 4)[:, 3] == frame.reshape(-1, 4)[:, 3]).all()
+    ident = orc.cube_from_values(3, 33, synth.lut_values_3d(33, "identity"))
+    set_cube(ctx, ident)
+    frame = synth.frame_noise("RGBA", w, h, 11)
+    assert (gpu_colorlut(ctx, "RGBA", w, h, frame) == frame).all()
+
+
+# ---- hsvfilter -----------------------------------------------------------------------------------
+def gpu_hsvfilter(ctx, fmt, w, h, frame, **kw):
+    out = frame.copy()
+    ctx.hsvfilter_process(fmt, w, h, out, out.shape[1], **kw)
+    return out
+
+
+HSVF = [dict(), dict(hue_shift=90.0), dict(hue_shift=-270.25, saturation_mul=1.7, saturation_off=-0.2, value_mul=0.8, value_off=0.15),
+        dict(hue_shift=1e9), dict(saturation_mul=float("nan")), dict(value_off=float("inf"), hue_shift=float("-inf")),
+        dict(hue_shift=359.9), dict(hue_shift=-1e-30)]
+
+
+def _orc_kw(kw):
+    m = {"saturation_mul": "sat_mul", "saturation_off": "sat_off", "value_mul": "val_mul", "value_off": "val_off"}
+    return {m.get(k, k): v for k, v in kw.items()}
+
+
+@pytest.mark.parametrize("i", range(len(HSVF)))
+def test_hsvfilter_all_colors(ctx, i):
+    kw = HSVF[i]
+    fmt = ["RGBA", "xBGR", "BGRx", "ARGB"][i % 4]
+    frame = all_colors_frame(fmt)
+    exp = orc.hsvfilter(fmt, 4096, 4096, frame, threads=NT, **_orc_kw(kw))
+    assert (gpu_hsvfilter(ctx, fmt, 4096, 4096, frame, **kw) == exp).all()
+
+
+def test_hsvfilter_default_is_not_identity(ctx):
+    frame = all_colors_frame("RGBA")
+    out = gpu_hsvfilter(ctx, "RGBA", 4096, 4096, frame)
+    d = out.reshape(-1, 4).astype(np.int16) - frame.reshape(-1, 4).astype(np.int16)
+    assert int((d[:, :3] != 0).any(axis=1).sum()) == 11093274 and (d[:, 3] == 0).all()
+
+
+@pytest.mark.parametrize("fmt", ["RGBx", "xRGB", "BGRx", "xBGR", "RGBA", "ARGB", "BGRA", "ABGR", "RGB", "BGR"])
+def test_hsvfilter_formats_strides(ctx, fmt):
+    kw = dict(hue_shift=123.5, saturation_mul=0.9, saturation_off=0.05, value_mul=1.1, value_off=-0.02)
+    for (w, h, pad, off) in ((1, 1, 0, 0), (37, 5, 8, 0), (640, 48, 0, 0), (255, 3, 3, 1)):
+        bpp = 3 if fmt in ("RGB", "BGR") else 4
+        stride = synth.default_stride(fmt, w) + pad
+        raw = np.full(h * stride + 8, 0xA5, np.uint8)
+        fr = raw[off:off + h * stride].reshape(h, stride)
+        fr[:, :bpp * w] = synth.frame_noise(fmt, w, h, 7)[:, :bpp * w]
+        exp = orc.hsvfilter(fmt, w, h, np.ascontiguousarray(fr), **_orc_kw(kw))
+        ctx.hsvfilter_process(fmt, w, h, fr.ctypes.data, stride, **kw)
+        assert (fr == exp).all()
+        assert (raw[:off] == 0xA5).all() and (raw[off + h * stride:] == 0xA5).all()
+
+
+def test_hsvfilter_config1_and_device(ctx):
+    torch = pytest.importorskip("torch")
+    w, h = 640, 480
+    for frame in (synth.frame_ramps("RGBA", w, h), synth.frame_noise("RGBA", w, h, 0x5EED0001)):
+        exp = orc.hsvfilter("RGBA", w, h, frame, hue_shift=90.0)
+        assert (gpu_hsvfilter(ctx, "RGBA", w, h, frame, hue_shift=90.0) == exp).all()
+        d = torch.from_numpy(frame).cuda()
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.hsvfilter_process("RGBA", w, h, d, 4 * w, hue_shift=90.0)
+        torch.cuda.synchronize()
+        assert (d.cpu().numpy() == exp).all()
+
+
+# ---- hsvdetector ---------------------------------------------------------------------------------
+def gpu_hsvdetector(ctx, ifmt, ofmt, w, h, src, dstride=None, **kw):
+    dstride = dstride or 4 * w
+    dst = np.full((h, dstride), 0x5A, np.uint8)
+    ctx.hsvdetector_process(ifmt, ofmt, w, h, src, src.shape[1], dst, dstride, **kw)
+    return dst
+
+
+def _orc_dkw(kw):
+    m = {"saturation_ref": "sat_ref", "saturation_var": "sat_var", "value_ref": "val_ref", "value_var": "val_var"}
+    return {m.get(k, k): v for k, v in kw.items()}
+
+
+HSVD = [dict(), dict(hue_ref=120.0, hue_var=30.0, saturation_ref=0.8, saturation_var=0.2, value_ref=0.8, value_var=0.2),
+        dict(hue_ref=-700.0, hue_var=180.0, saturation_ref=0.5, saturation_var=0.5, value_ref=0.5, value_var=0.5),
+        dict(hue_ref=359.99, hue_var=0.5, saturation_var=1.0, value_var=1.0), dict(hue_ref=float("nan"))]
+
+
+@pytest.mark.parametrize("i", range(len(HSVD)))
+def test_hsvdetector_all_colors(ctx, i):
+    kw = HSVD[i]
+    ifmt, ofmt = [("RGBx", "RGBA"), ("BGRx", "ARGB"), ("xRGB", "BGRA"), ("xBGR", "ABGR"), ("RGBx", "ABGR")][i]
+    frame = all_colors_frame(ifmt.replace("x", "A"))
+    exp = orc.hsvdetector(ifmt, ofmt, 4096, 4096, frame, threads=NT, **_orc_dkw(kw))
+    got = gpu_hsvdetector(ctx, ifmt, ofmt, 4096, 4096, frame, **kw)
+    assert (got == exp).all()
+    if i == 0:
+        assert int((got.reshape(-1, 4)[:, 3] == 255).sum()) == 719
+    if i == 1:
+        assert int((got.reshape(-1, 4)[:, 0] == 255).sum()) == 1415062
+
+
+@pytest.mark.parametrize("ifmt", ["RGBx", "xRGB", "BGRx", "xBGR", "RGB", "BGR"])
+@pytest.mark.parametrize("ofmt", ["RGBA", "ARGB", "BGRA", "ABGR"])
+def test_hsvdetector_format_matrix(ctx, ifmt, ofmt):
+    kw = dict(hue_ref=200.0, hue_var=90.0, saturation_ref=0.5, saturation_var=0.5, value_ref=0.5, value_var=0.5)
+    for (w, h, spad, dpad) in ((1, 1, 0, 0), (37, 5, 8, 12), (1920, 8, 0, 0), (333, 3, 4, 4)):
+        src = synth.frame_noise(ifmt, w, h, 0x5EED0003, stride=synth.default_stride(ifmt, w) + spad)
+        exp = orc.hsvdetector(ifmt, ofmt, w, h, src, dst_stride=4 * w + dpad, **_orc_dkw(kw))
+        assert (gpu_hsvdetector(ctx, ifmt, ofmt, w, h, src, 4 * w + dpad, **kw) == exp).all()
+
+
+def test_hsvdetector_rejects_formats_outside_caps(ctx):
+    src = np.zeros((1, 8), np.uint8)
+    for ifmt, ofmt in (("RGBA", "RGBA"), ("RGBx", "RGBx"), ("RGBA64_LE", "RGBA"), ("RGB", "BGR")):
+        with pytest.raises(b200vfx.B200VfxError) as e:
+            ctx.hsvdetector_process(ifmt, ofmt, 1, 1, src, 8, src.copy(), 8)
+        assert e.value.code == b200vfx.ERR_UNSUPPORTED
+
+
+def test_hsvdetector_config3_full_size(ctx):
+    w, h = 1920, 1080
+    kw = HSVD[1]
+    for frame in (synth.frame_ramps("BGRx", w, h), synth.frame_noise("BGRx", w, h, 0x5EED0003)):
+        exp = orc.hsvdetector("BGRx", "RGBA", w, h, frame, threads=NT, **_orc_dkw(kw))
+        assert (gpu_hsvdetector(ctx, "BGRx", "RGBA", w, h, frame, **kw) == exp).all()
+
+
+# ---- videocompare / blockhash ----------------------------------------------------------------------
+@pytest.mark.parametrize("fmt,w,h,pad", [("RGBA", 64, 48, 0), ("RGBA", 3840, 2160, 0), ("RGBA", 72, 40, 12), ("RGBA", 24, 16, 4),
+                                         ("RGB", 64, 48, 0), ("RGB", 1920, 1080, 0), ("RGB", 40, 24, 4), ("RGBA", 8, 8, 0)])
+def test_blockhash_sums(ctx, fmt, w, h, pad):
+    frame = synth.frame_noise(fmt, w, h, 0x5EED0004, stride=synth.default_stride(fmt, w) + pad)
+    if fmt == "RGBA":
+        frame[::3, 3:4 * w:16] = 0  # some fully transparent pixels -> counted as 765
+    exp = orc.blockhash_sums(fmt, w, h, frame)
+    sums = np.full(64, 0xDEADBEEF, np.uint32)
+    ctx.blockhash_sums(fmt, w, h, frame, frame.shape[1], sums)
+    assert (sums == exp).all()
+
+
+def test_blockhash_device_and_videocompare_semantics(ctx):
+    torch = pytest.importorskip("torch")
+    w, h = 3840, 2160
+    a = synth.frame_ramps("RGBA", w, h)
+    pert = a.copy()
+    idx = synth.pcg32(w * h // 100, 0x5EED0004) % np.uint32(w * h)
+    pert.reshape(-1, 4)[idx, :3] ^= 0xFF
+    red = synth.frame_solid("RGBA", w, h)
+    snow = synth.frame_noise("RGBA", w, h, 1)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def bits(frame):
+        d = torch.from_numpy(frame).cuda()
+        s = torch.zeros(64, dtype=torch.int32, device="cuda")
+        ctx.blockhash_sums("RGBA", w, h, d, 4 * w, s)
+        torch.cuda.synchronize()
+        sums = s.cpu().numpy().view(np.uint32)
+        assert (sums == orc.blockhash_sums("RGBA", w, h, frame)).all()
+        return b200vfx.blockhash_bits(sums, w, h)
+
+    ba, bp, br, bs = bits(a), bits(pert), bits(red), bits(snow)
+    assert b200vfx.hash_distance(ba, ba) == 0
+    assert b200vfx.hash_distance(br, bits(red.copy())) == 0       # red vs red -> distance 0 (tests/videocompare.rs:57-103)
+    assert b200vfx.hash_distance(br, bs) > 0                      # snow vs red -> no match (:105-139)
+    assert b200vfx.hash_distance(ba, bp) <= 8                     # 1 % perturbation stays close
+    with pytest.raises(b200vfx.B200VfxError) as e:
+        ctx.blockhash_sums("RGBA", 30, 16, a, 4 * w, np.zeros(64, np.uint32))
+    assert e.value.code == b200vfx.ERR_UNSUPPORTED
+
+
+# ---- roundedcorners --------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h,stride,r", [(64, 50, 64, 12), (1920, 1080, 1920, 64), (33, 17, 36, 5), (10, 9, 12, 100),
+                                          (64, 51, 68, 0), (1, 1, 4, 3), (640, 480, 640, 1)])
+def test_roundmask(ctx, w, h, stride, r):
+    exp = orc.roundmask(w, h, stride, r)
+    got = np.full(exp.shape, 0x77, np.uint8)
+    ctx.roundmask_generate(w, h, stride, r, got)
+    assert (got == exp).all()

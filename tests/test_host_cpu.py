@@ -1,0 +1,115 @@
+"""CPU tests of the product's host side: the C-ABI library loads, exports every symbol the header
+declares, its .cube parser agrees with the reference KATs and with the oracle parser, and it
+fails loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import b200vfx
+import oracle_binding as orc
+from b200vfx import synth
+
+
+def test_library_exports_every_declared_symbol():
+    names = b200vfx.exported_symbols_in_header()
+    assert len(names) >= 20
+    L = C.CDLL(b200vfx.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), "libb200vfx.so does not export %s" % n
+    assert b200vfx.lib().b200vfx_abi_version() == 1
+
+
+def test_no_gpu_fails_loudly():
+    if b200vfx.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(b200vfx.B200VfxError) as e:
+        b200vfx.Context()
+    assert e.value.code == b200vfx.ERR_CUDA and "no CPU fallback" in e.value.msg
+
+
+# the reference's parser unit tests (video/colorlut/src/parser.rs:382-473) against the PRODUCT parser
+def test_product_parser_reference_kats():
+    k, s, v, sc, of = b200vfx.cube_parse("\n LUT_3D_SIZE 2\n\n 0.0 0.0 0.0\n 1.0 0.0 0.0\n 0.0 1.0 0.0\n 1.0 1.0 0.0\n"
+                                         " 0.0 0.0 1.0\n 1.0 0.0 1.0\n 0.0 1.0 1.0\n 1.0 1.0 1.0\n ")
+    assert (k, s) == (3, 2) and v.shape == (8, 3) and v[0].tolist() == [0, 0, 0] and v[7].tolist() == [1, 1, 1]
+    k, s, v, sc, of = b200vfx.cube_parse('LUT_1D_SIZE 2\n\nTITLE "test"\nDOMAIN_MIN 0.0 0.0 0.0\nDOMAIN_MAX 1.0 1.0 1.0\n\n'
+                                         "0.0 0.0 0.0\n1.0 0.5 0.7\n")
+    assert (k, s) == (1, 2) and v[:, 0].tolist() == [0, 1] and v[:, 1].tolist() == [0, 0.5]
+    assert v[:, 2].tolist() == [0, np.float32(0.7)]
+    for bad in ['LUT_1D_SIZE 2\n0.0 0.0 0.0\n1.0 0.0 0.0\nTITLE "invalid"\n',
+                'LUT_1D_SIZE 2\n0.0 0.0 0.0\nTITLE "invalid"\n1.0 0.0 0.0\n',
+                "LUT_1D_SIZE 2\nLUT_3D_SIZE 2\n0.0 0.0 0.0\n1.0 1.0 1.0\n"]:
+        with pytest.raises(b200vfx.B200VfxError) as e:
+            b200vfx.cube_parse(bad)
+        assert e.value.code == b200vfx.ERR_PARSE
+
+
+CASES_OK = [
+    synth.cube_text_3d(3, "mix", domain=((-0.5, 0.0, 0.25), (1.0, 2.0, 0.75)), title="t"),
+    synth.cube_text_1d(7, 2.2),
+    "# c\r\nTITLE \"x y z\"\r\nLUT_1D_SIZE +3\r\nDOMAIN_MIN -1 0 .5\nDOMAIN_MAX 1 2 1.\n1e-1 +.5 5.E-1\n inf -Infinity NaN \n\t0.1 0.2　0.3",
+    "LUT_1D_SIZE 2\n0 0 0\n1 1 1\r",
+    "LUT_1D_SIZE 2\n\n#x\n   \n1e400 -1e400 1e-60\n0 0 4.9e-324\n",
+]
+CASES_BAD = [
+    "0 0 0\nLUT_1D_SIZE 2\n", "LUT_1D_SIZE 2\n0 0 0\n", "LUT_3D_SIZE 2\n" + "0 0 0\n" * 7, "LUT_1D_SIZE 1\n0 0 0\n",
+    "LUT_3D_SIZE 257\n", "LUT_1D_SIZE 65537\n", "LUT_1D_SIZE 2\n0 0\n1 1 1\n", "LUT_1D_SIZE 2\n0 0 0 0\n1 1 1\n",
+    "LUT_1D_SIZE 2\n0 0 0x1p0\n1 1 1\n", "LUT_1D_SIZE 2\n0 0 1f\n1 1 1\n", "LUT_1D_SIZE -2\n", "LUT_1D_SIZE 2 3\n",
+    "LUT_1D_SIZE\n", "LUT_1D_SIZE 2\nDOMAIN_MIN 1 0 0\nDOMAIN_MAX 1 1 1\n0 0 0\n1 1 1\n",
+    "LUT_1D_SIZE 2\nDOMAIN_MIN 0 0\n0 0 0\n1 1 1\n", "LUT_1D_SIZE 2\nDOMAIN_MAX 1 1 1 1\n0 0 0\n1 1 1\n",
+    "LUT_1D_SIZE 2\nLUT_3D_INPUT_RANGE 0 1\n0 0 0\n1 1 1\n", "﻿LUT_1D_SIZE 2\n0 0 0\n1 1 1\n", "", "# only\n",
+    "LUT_1D_SIZE 2\n0 0 .\n1 1 1\n", "LUT_1D_SIZE 2\n0 0 1e\n1 1 1\n", "LUT_1D_SIZE 2\n0 0 +\n1 1 1\n",
+    "LUT_1D_SIZE 99999999999999999999999\n", "title x\nLUT_1D_SIZE 2\n0 0 0\n1 1 1\n",
+]
+
+
+@pytest.mark.parametrize("i", range(len(CASES_OK)))
+def test_product_parser_matches_oracle_parser(i):
+    text = CASES_OK[i]
+    k, s, v, sc, of = b200vfx.cube_parse(text)
+    o = orc.cube_parse(text)
+    assert (k, s) == (o.kind, o.size)
+    assert v.tobytes() == o.values.tobytes() and sc.tobytes() == o.scale.tobytes() and of.tobytes() == o.offset.tobytes()
+
+
+@pytest.mark.parametrize("i", range(len(CASES_BAD)))
+def test_product_parser_rejects_what_oracle_rejects(i):
+    with pytest.raises(orc.CubeError):
+        orc.cube_parse(CASES_BAD[i])
+    with pytest.raises(b200vfx.B200VfxError) as e:
+        b200vfx.cube_parse(CASES_BAD[i])
+    assert e.value.code == b200vfx.ERR_PARSE
+
+
+def test_product_parser_invalid_utf8_and_missing_file(tmp_path):
+    with pytest.raises(b200vfx.B200VfxError) as e:
+        b200vfx.cube_parse(b"LUT_1D_SIZE 2\n0 0 0\n1 1 \xff1\n")
+    assert e.value.code == b200vfx.ERR_IO
+    L = b200vfx.lib()
+    kind, size = C.c_int(), C.c_int()
+    vals = C.POINTER(C.c_float)()
+    sc = (C.c_float * 3)()
+    of = (C.c_float * 3)()
+    err = C.create_string_buffer(256)
+    rc = L.b200vfx_cube_parse_file(str(tmp_path / "missing.cube").encode(), C.byref(kind), C.byref(size),
+                                   C.byref(vals), sc, of, err, 256)
+    assert rc == b200vfx.ERR_IO and b"IO error" in err.value
+    p = tmp_path / "ok.cube"
+    p.write_text(synth.cube_text_3d(2, "identity"))
+    rc = L.b200vfx_cube_parse_file(str(p).encode(), C.byref(kind), C.byref(size), C.byref(vals), sc, of, err, 256)
+    assert rc == 0 and kind.value == 3 and size.value == 2
+    L.b200vfx_cube_free(vals)
+
+
+def test_blockhash_bits_and_distance_host_side():
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        sums = rng.integers(0, 2 ** 31, 64, dtype=np.uint32)
+        sums[rng.integers(0, 64, 8)] = sums[0]
+        assert (b200vfx.blockhash_bits(sums, 3840, 2160) == orc.blockhash_bits(sums, 3840, 2160)).all()
+    solid = np.full(64, 255 * 480 * 270, np.uint32)  # solid red frame: every block sum equal
+    assert b200vfx.blockhash_bits(solid, 3840, 2160).sum() == 0
+    a = b200vfx.blockhash_bits(rng.integers(0, 2 ** 31, 64, dtype=np.uint32), 3840, 2160)
+    assert b200vfx.hash_distance(a, a) == 0 and b200vfx.hash_distance(a, 1 - a) == 64
