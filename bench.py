@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- 4K RGBA frames/s through `colorlut` (33^3 .cube) on N B200s, HBM roofline beside it.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`; for N>1 it is
+launched under torchrun, one rank per GPU.  Rank 0 prints ONE JSON line.
+
+Workload = BASELINE.json configs[1]: colorlut, generated "mix" 33^3 .cube, 3840x2160 RGBA frames,
+synthetic frames A ("ramps", coherent) and B ("noise", PCG32) of SURVEY Appendix F, alternating.
+A STEP = one GOP of `--gop` (default 64) frames through the element; the inputs of a step are a ring
+of 8 distinct frames and 8 distinct outputs (531 MB > the 126 MB L2), so no frame is L2-resident when
+it is processed ("inputs larger than L2"; no explicit flush: the memo LUT is *meant* to live in L2).
+  value : device-resident frames/s (frames already in HBM), CUDA events on the launching stream.
+  e2e   : the same GOPs through the same C-ABI call with HOST (pinned) buffers, H2D and D2H inside.
+Multi-GPU (weak scaling, no data-path collective): every frame is row-tiled N ways, rank r owns tile r;
+a rank's tiles of N consecutive frames are stacked in its buffer, so its per-step work is the same
+number of rows as at N=1.  value = all frames finished by all ranks / max-over-ranks time.
+`--impl reference`: the CPU oracle (C restatement of the reference loop; the Rust reference cannot be
+built in this image) on all host threads, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "gst-plugin-rs_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W4K, H4K = 3840, 2160
+FRAME_BYTES = W4K * H4K * 4
+ALGO_BYTES_PER_FRAME = 2 * FRAME_BYTES  # 33 177 600 read + 33 177 600 written
+RING = 8
+METRIC = "colorlut_4k_rgba_frames_per_sec"
+WORKLOAD = "colorlut 33^3 .cube on 3840x2160 RGBA synthetic stream (frames A ramps / B noise alternating)"
+
+
+def hbm_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_frames(np, synth):
+    """ring of 8 distinct 4K frames: A (ramps, rolled so each is distinct) and B (noise, 4 seeds) alternating"""
+    base = synth.frame_ramps("RGBA", W4K, H4K)
+    frames, kinds = [], []
+    for i in range(RING):
+        if i % 2 == 0:
+            frames.append(np.ascontiguousarray(np.roll(base, 4 * 97 * (i // 2), axis=1)))
+            kinds.append("ramps")
+        else:
+            frames.append(synth.frame_noise("RGBA", W4K, H4K, 0x5EED0002 + i // 2))
+            kinds.append("noise")
+    return frames, kinds
+
+
+class ClockSampler(threading.Thread):
+    """polls SM clock / throttle reasons of one GPU through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.ok = index, [], set(), False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {getattr(nv, k): k[len("nvmlClocksEventReason"):] for k in dir(nv) if k.startswith("nvmlClocksEventReason") and isinstance(getattr(nv, k), int)}
+        if not names:
+            names = {getattr(nv, k): k[len("nvmlClocksThrottleReason"):] for k in dir(nv) if k.startswith("nvmlClocksThrottleReason") and isinstance(getattr(nv, k), int)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if bit and (mask & bit) and name not in ("None", "GpuIdle", "All"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle on all host threads, 1 full 4K frame per step (alternating A/B)."""
+    import numpy as np
+    import oracle_binding as orc
+    from b200vfx import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    cube = orc.cube_parse(synth.cube_text_3d(33, "mix"))
+    frames = [synth.frame_ramps("RGBA", W4K, H4K), synth.frame_noise("RGBA", W4K, H4K, 0x5EED0002)]
+    out = np.zeros_like(frames[0])
+    for i in range(max(args.warmup, 1)):
+        orc.colorlut_apply(cube, "RGBA", W4K, H4K, frames[i % 2], threads=threads, out=out)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        orc.colorlut_apply(cube, "RGBA", W4K, H4K, frames[i % 2], threads=threads, out=out)
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "lut": "33^3 mix .cube", "frame": "3840x2160 RGBA", "step": "1 frame per step"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": "%d full 4K frames, C restatement of colorlut/imp.rs:267-294 row-parallel over %d threads "
+                                       "(the Rust reference cannot be built here)" % (args.steps, threads)},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(np, synth, budget_s=12.0):
+    import oracle_binding as orc
+    cube = orc.cube_parse(synth.cube_text_3d(33, "mix"))
+    frames = [synth.frame_ramps("RGBA", W4K, H4K), synth.frame_noise("RGBA", W4K, H4K, 0x5EED0002)]
+    threads = os.cpu_count() or 1
+    out = np.zeros_like(frames[0])
+    orc.colorlut_apply(cube, "RGBA", W4K, H4K, frames[0], threads=threads, out=out)  # warm-up
+    t0 = time.perf_counter()
+    orc.colorlut_apply(cube, "RGBA", W4K, H4K, frames[0], threads=1, out=out)
+    orc.colorlut_apply(cube, "RGBA", W4K, H4K, frames[1], threads=1, out=out)
+    t1 = (time.perf_counter() - t0) / 2
+    n, t0 = 0, time.perf_counter()
+    while True:
+        orc.colorlut_apply(cube, "RGBA", W4K, H4K, frames[n % 2], threads=threads, out=out)
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 200:
+            break
+    tn = (time.perf_counter() - t0) / n
+    return {"value": 1.0 / tn, "unit": "frames/s", "cores": threads, "kind": "port",
+            "single_thread_value": 1.0 / t1,
+            "sample": "%d full 4K frames (A/B alternating) on %d threads + 2 frames on 1 thread; C restatement of the "
+                      "reference loop colorlut/imp.rs:267-294 (Rust toolchain absent)" % (n, threads)}
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--gop", type=int, default=64, help="frames per step")
+    ap.add_argument("--mode", type=int, default=0, help="colorlut mode: 0 memo (default), 1 direct trilinear")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps for the e2e leg (default: min(steps, 6))")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import b200vfx
+    from b200vfx import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or b200vfx.device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device -- the b200vfx path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N = world
+
+    frames, kinds = make_frames(np, synth)
+    # rank r owns row tile r of every frame; the tiles of N consecutive frames are stacked -> H rows per launch
+    rows = H4K // N
+    assert rows * N == H4K
+    def my_stack(i):
+        tiles = [frames[(i + j) % RING][rank * rows:(rank + 1) * rows] for j in range(N)]
+        return np.ascontiguousarray(np.concatenate(tiles, axis=0))
+    stacks = [my_stack(i) for i in range(RING)]
+    d_in = [torch.from_numpy(s).cuda() for s in stacks]
+    d_out = [torch.empty_like(t) for t in d_in]
+
+    ctx = b200vfx.Context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    k, s, v, sc, of = b200vfx.cube_parse(synth.cube_text_3d(33, "mix"))
+    ctx.colorlut_set_lut(k, s, v, sc, of)
+    ctx.colorlut_set_mode(args.mode)
+
+    def gop_device():
+        for i in range(args.gop):
+            ctx.colorlut_process("RGBA", W4K, H4K, d_in[i % RING], 4 * W4K, d_out[i % RING], 4 * W4K)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        gop_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        gop_device()
+    e1.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    dev_ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - l0
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    lt = torch.tensor([launches], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    dev_ms_max = float(t.item())
+    total_launches = int(lt.item())
+    frames_total = args.gop * args.steps * N          # every rank finished gop*steps frame-equivalents
+    value = frames_total / (dev_ms_max * 1e-3)
+    # roofline of the dominant kernel: one launch = one 4K frame-equivalent on this GPU
+    per_launch_s = dev_ms * 1e-3 / max(launches, 1)
+    achieved = ALGO_BYTES_PER_FRAME / per_launch_s / 1e9
+    peak, peak_src = hbm_peak_gbs()
+
+    # per-content breakdown (rank 0, N=1 only): ramps-only / noise-only GOPs
+    breakdown = {}
+    if N == 1:
+        for name in ("ramps", "noise"):
+            idx = [i for i in range(RING) if kinds[i] == name]
+            def run_kind():
+                for i in range(args.gop):
+                    j = idx[i % len(idx)]
+                    ctx.colorlut_process("RGBA", W4K, H4K, d_in[j], 4 * W4K, d_out[j], 4 * W4K)
+            for _ in range(3):
+                run_kind()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(max(args.steps // 2, 3)):
+                run_kind()
+            b.record()
+            torch.cuda.synchronize()
+            per = a.elapsed_time(b) * 1e-3 / (max(args.steps // 2, 3) * args.gop)
+            breakdown[name] = {"us_per_frame": per * 1e6, "frames_per_s": 1.0 / per,
+                               "achieved_gbs": ALGO_BYTES_PER_FRAME / per / 1e9, "frac": ALGO_BYTES_PER_FRAME / per / 1e9 / peak}
+
+    # ---- end-to-end leg: same call, HOST pinned buffers, copies inside the timed region ----------
+    e2e = None
+    if not args.no_e2e:
+        h_in = [torch.from_numpy(s).pin_memory() for s in stacks[:4]]
+        h_out = [torch.empty_like(tt).pin_memory() for tt in h_in]
+        e2e_gop = max(1, args.gop // 4)
+        e2e_steps = args.e2e_steps or min(args.steps, 6)
+        def gop_host():
+            for i in range(e2e_gop):
+                ctx.colorlut_process("RGBA", W4K, H4K, h_in[i % 4].numpy(), 4 * W4K, h_out[i % 4].numpy(), 4 * W4K)
+        gop_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            gop_host()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        chk = int(h_out[0].view(torch.int32)[::4096].sum().item())  # device->host result is really read
+        e2e = {"value": e2e_gop * e2e_steps * N / dt, "unit": "frames/s",
+               "h2d_bytes_per_step": FRAME_BYTES * e2e_gop, "d2h_bytes_per_step": FRAME_BYTES * e2e_gop,
+               "frames_per_step": e2e_gop, "steps": e2e_steps, "ms_per_frame": 1e3 * dt / (e2e_gop * e2e_steps),
+               "host_buffers": "pinned", "checksum": chk}
+
+    # ---- optional all-gather reassembly (config 5 style), reported separately ---------------------
+    allgather = None
+    if dist is not None:
+        tile = d_out[0][:rows].contiguous().view(-1)
+        full = torch.empty(N * tile.numel(), dtype=tile.dtype, device="cuda")
+        for _ in range(3):
+            dist.all_gather_into_tensor(full, tile)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            dist.all_gather_into_tensor(full, tile)
+        b.record()
+        torch.cuda.synchronize()
+        ag = torch.tensor([a.elapsed_time(b) / 20], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ag, op=dist.ReduceOp.MAX)
+        allgather = {"ms_per_frame": float(ag.item()), "bytes_per_rank": int(tile.numel()), "note": "ncclAllGather of one 4K frame's row tiles; not part of value"}
+
+    cpu = None
+    if rank == 0 and N == 1 and not args.no_cpu:
+        cpu = cpu_baseline_sample(np, synth)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 (f32 LUT arithmetic)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "lut": "33^3 mix .cube", "frame": "3840x2160 RGBA stride 15360",
+                       "frames_per_step": args.gop * N, "ring_frames": RING, "l2": "inputs larger than L2 (8 in + 8 out frames = 531 MB ring, no flush)",
+                       "colorlut_mode": "memo" if args.mode == 0 else "direct",
+                       "sharding": "row tiles, rank r owns rows [r*H/N,(r+1)*H/N) of every frame; no data-path collective"},
+            "gpu_launches": total_launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "colorlut_memo_apply_kernel<4>" if args.mode == 0 else "colorlut_direct_kernel<0,true>",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME,
+                         "us_per_launch": per_launch_s * 1e6, "by_content": breakdown},
+            "clocks": sampler.summary(),
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if allgather is not None:
+            line["allgather"] = allgather
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

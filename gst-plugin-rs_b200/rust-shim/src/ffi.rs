@@ -1,0 +1,150 @@
+// ffi.rs -- the `extern "C"` binding of include/b200vfx.h that the gstreamer-rs elements use.
+//
+// NOTE: this image has no cargo/rustc/GStreamer, so this crate is written but was never compiled
+// here.  The C ABI it binds is exercised by tests/ through ctypes and by the C++ element
+// emulator (csrc/elements.cpp), which mirrors these elements one-to-one.
+#![allow(non_camel_case_types, dead_code)]
+
+use std::ffi::{c_char, c_float, c_int, c_uint, c_void, CStr};
+
+#[repr(C)]
+pub struct b200vfx_ctx {
+    _private: [u8; 0],
+}
+
+pub const B200VFX_OK: c_int = 0;
+pub const B200VFX_ERR_NOT_NEGOTIATED: c_int = -3;
+
+// GstVideoFormat -> b200vfx_format
+pub fn format_code(f: gst_video::VideoFormat) -> Option<c_int> {
+    use gst_video::VideoFormat::*;
+    Some(match f {
+        Rgbx => 0,
+        Xrgb => 1,
+        Bgrx => 2,
+        Xbgr => 3,
+        Rgba => 4,
+        Argb => 5,
+        Bgra => 6,
+        Abgr => 7,
+        Rgb => 8,
+        Bgr => 9,
+        Rgba64Le => 10,
+        Rgba64Be => 11,
+        I420 => 12,
+        A420 => 13,
+        _ => return None,
+    })
+}
+
+#[link(name = "b200vfx")]
+extern "C" {
+    pub fn b200vfx_ctx_create(out: *mut *mut b200vfx_ctx, device: c_int) -> c_int;
+    pub fn b200vfx_ctx_destroy(ctx: *mut b200vfx_ctx);
+    pub fn b200vfx_last_error(ctx: *const b200vfx_ctx) -> *const c_char;
+    pub fn b200vfx_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn b200vfx_host_free(p: *mut c_void);
+
+    pub fn b200vfx_colorlut_load_file(ctx: *mut b200vfx_ctx, location: *const c_char) -> c_int;
+    pub fn b200vfx_colorlut_clear(ctx: *mut b200vfx_ctx) -> c_int;
+    pub fn b200vfx_colorlut_process(
+        ctx: *mut b200vfx_ctx,
+        fmt: c_int,
+        width: c_int,
+        height: c_int,
+        src: *const c_void,
+        src_stride: c_int,
+        dst: *mut c_void,
+        dst_stride: c_int,
+    ) -> c_int;
+
+    pub fn b200vfx_hsvfilter_process(
+        ctx: *mut b200vfx_ctx,
+        fmt: c_int,
+        width: c_int,
+        height: c_int,
+        data: *mut c_void,
+        stride: c_int,
+        hue_shift: c_float,
+        saturation_mul: c_float,
+        saturation_off: c_float,
+        value_mul: c_float,
+        value_off: c_float,
+    ) -> c_int;
+
+    pub fn b200vfx_hsvdetector_process(
+        ctx: *mut b200vfx_ctx,
+        in_fmt: c_int,
+        out_fmt: c_int,
+        width: c_int,
+        height: c_int,
+        src: *const c_void,
+        src_stride: c_int,
+        dst: *mut c_void,
+        dst_stride: c_int,
+        hue_ref: c_float,
+        hue_var: c_float,
+        saturation_ref: c_float,
+        saturation_var: c_float,
+        value_ref: c_float,
+        value_var: c_float,
+    ) -> c_int;
+
+    pub fn b200vfx_roundmask_generate(
+        ctx: *mut b200vfx_ctx,
+        width: c_int,
+        height: c_int,
+        stride: c_int,
+        border_radius_px: c_uint,
+        a8_out: *mut c_void,
+    ) -> c_int;
+
+    pub fn b200vfx_blockhash_sums(
+        ctx: *mut b200vfx_ctx,
+        fmt: c_int,
+        width: c_int,
+        height: c_int,
+        src: *const c_void,
+        stride: c_int,
+        hw: c_int,
+        hh: c_int,
+        sums: *mut u32,
+    ) -> c_int;
+    pub fn b200vfx_blockhash_bits(sums: *const u32, hw: c_int, hh: c_int, width: c_int, height: c_int, bits_out: *mut u8);
+    pub fn b200vfx_hash_distance(a: *const u8, b: *const u8, nbits: c_int) -> c_int;
+}
+
+/// Owning wrapper: one context per element instance, created in `start()`, dropped in `stop()`.
+pub struct Ctx(pub *mut b200vfx_ctx);
+unsafe impl Send for Ctx {}
+
+impl Ctx {
+    pub fn new() -> Result<Self, String> {
+        let mut p = std::ptr::null_mut();
+        let rc = unsafe { b200vfx_ctx_create(&mut p, -1) };
+        if rc != B200VFX_OK {
+            return Err(last_error(std::ptr::null()));
+        }
+        Ok(Ctx(p))
+    }
+    pub fn error(&self) -> String {
+        last_error(self.0)
+    }
+}
+
+impl Drop for Ctx {
+    fn drop(&mut self) {
+        unsafe { b200vfx_ctx_destroy(self.0) }
+    }
+}
+
+pub fn last_error(ctx: *const b200vfx_ctx) -> String {
+    unsafe {
+        let p = b200vfx_last_error(ctx);
+        if p.is_null() {
+            String::new()
+        } else {
+            CStr::from_ptr(p).to_string_lossy().into_owned()
+        }
+    }
+}

@@ -1,0 +1,103 @@
+/*
+ * b200gst.h -- host-side element layer (C++ in gst-plugin-rs_b200/csrc/elements.cpp) mirroring the
+ * reference's GStreamer element surface for the hot path, without GStreamer/GLib (absent from this
+ * image).  It exists so that the parity tests can read like the reference's own tests:
+ * make an element by factory name, set GObject-style properties from strings, negotiate formats,
+ * start, push frames, read bus messages.
+ *
+ *   factory           type name            parent               reference
+ *   colorlut          GstColorLut          GstVideoFilter       video/colorlut/src/colorlut/imp.rs
+ *   hsvfilter         GstHsvFilter         GstVideoFilter       video/hsv/src/hsvfilter/imp.rs
+ *   hsvdetector       GstHsvDetector       GstVideoFilter       video/hsv/src/hsvdetector/imp.rs
+ *   roundedcorners    GstRoundedCorners    GstBaseTransform     video/videofx/src/border/imp.rs
+ *   videocompare      GstVideoCompare      GstVideoAggregator   video/videofx/src/videocompare/imp.rs
+ *
+ * Every element owns one b200vfx_ctx (created in start(), destroyed in stop()) and calls the
+ * C ABI of b200vfx.h for all pixel work -- the same calls the Rust shim makes.
+ * Frames are borrowed, already "mapped" {format,width,height,data[],stride[]} descriptors, like
+ * GstVideoFrame.  Return codes follow GstFlowReturn where the reference returns a flow:
+ *   0 = Ok, -1 = NotNegotiated-style error, -2 = Error, -3 = Eos; other calls: 0 ok / <0 error.
+ */
+#ifndef B200GST_H
+#define B200GST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GST_FLOW_OK 0
+#define B200GST_FLOW_NOT_NEGOTIATED (-1)
+#define B200GST_FLOW_ERROR (-2)
+#define B200GST_FLOW_EOS (-3)
+
+#define B200GST_PAD_SINK 0
+#define B200GST_PAD_SRC 1
+
+typedef struct b200gst_element b200gst_element;
+
+typedef struct {
+  int format; /* b200vfx_format */
+  int width, height;
+  int n_planes;
+  void *data[4];
+  int stride[4];
+} b200gst_video_frame;
+
+/* gst_element_factory_make(): NULL for an unknown factory name */
+b200gst_element *b200gst_element_factory_make(const char *factory_name);
+void b200gst_element_unref(b200gst_element *el);
+const char *b200gst_element_factory_name(const b200gst_element *el);
+const char *b200gst_element_type_name(const b200gst_element *el);   /* "GstColorLut", ... */
+const char *b200gst_element_plugin_name(const b200gst_element *el); /* "colorlut", "hsv", "rsvideofx" */
+const char *b200gst_element_last_error(const b200gst_element *el);
+
+/* GObject properties, gst-launch style (value given as a string and converted to the property's type;
+ * numeric values are clamped/rejected against the ParamSpec range like g_object_set would).
+ * list: one line per property "name|type|default|min|max|mutability". */
+int b200gst_element_set_property(b200gst_element *el, const char *name, const char *value);
+int b200gst_element_get_property(const b200gst_element *el, const char *name, char *buf, size_t buflen);
+int b200gst_element_list_properties(const b200gst_element *el, char *buf, size_t buflen);
+
+/* pad templates / caps: format lists only (all other caps fields pass through unchanged in the reference) */
+int b200gst_element_pad_template_formats(const b200gst_element *el, int direction, int *formats, int cap);
+/* BaseTransformImpl::transform_caps: given the formats on the `direction` pad, the formats on the other pad */
+int b200gst_element_transform_caps(b200gst_element *el, int direction, const int *formats, int n, int *out, int cap);
+
+/* state: start() = READY->PAUSED, stop() = PAUSED->READY */
+int b200gst_element_start(b200gst_element *el);
+int b200gst_element_stop(b200gst_element *el);
+/* set_caps(incaps, outcaps) reduced to what the hot path needs */
+int b200gst_element_set_caps(b200gst_element *el, int in_format, int out_format, int width, int height);
+int b200gst_element_is_passthrough(const b200gst_element *el);
+
+/* VideoFilterImpl::transform_frame / transform_frame_ip */
+int b200gst_element_transform_frame(b200gst_element *el, const b200gst_video_frame *in, b200gst_video_frame *out);
+int b200gst_element_transform_frame_ip(b200gst_element *el, b200gst_video_frame *frame);
+
+/* roundedcorners: prepare_output_buffer() appends the shared alpha memory as plane 3 of the I420
+ * buffer and rewrites the video meta; here the frame descriptor gets plane 3 (A420). */
+int b200gst_roundedcorners_prepare_output(b200gst_element *el, const b200gst_video_frame *in_i420,
+                                          b200gst_video_frame *out_a420);
+
+/* videocompare: request pads sink_%u (first requested = reference pad), aggregate_frames() */
+int b200gst_videocompare_request_pad(b200gst_element *el);            /* returns pad id >= 0 */
+int b200gst_videocompare_release_pad(b200gst_element *el, int pad_id);
+int b200gst_videocompare_reference_pad(const b200gst_element *el);    /* -1 if none */
+/* frames[i] belongs to pad_ids[i]; a missing pad (no prepared frame) is simply not listed.
+ * running_time_ns < 0 = none.  out (may be NULL) receives a copy of the reference frame. */
+int b200gst_videocompare_aggregate_frames(b200gst_element *el, const b200gst_video_frame *frames,
+                                          const int *pad_ids, int n, int64_t running_time_ns,
+                                          b200gst_video_frame *out);
+
+/* bus: pops the oldest posted element message serialised like gst_structure_to_string(), e.g.
+ * "videocompare, pad-distances=(structure)< \"pad-distance\\,\\ pad\\=sink_1\\,\\ distance\\=0\\;\" >, running-time=(guint64)0;"
+ * returns 1 if a message was written, 0 if the bus is empty. */
+int b200gst_element_pop_message(b200gst_element *el, char *buf, size_t buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -102,11 +102,11 @@ def cube_from_values(kind, size, values, scale=(1, 1, 1), offset=(-0.0, -0.0, -0
 
 
 def colorlut_apply(cube: Cube, fmt: str, width: int, height: int, src: np.ndarray, dst_stride=None,
-                   threads: int = 1, dst_fill: int = 0x5A) -> np.ndarray:
+                   threads: int = 1, dst_fill: int = 0x5A, out: np.ndarray | None = None) -> np.ndarray:
     src = np.ascontiguousarray(src, np.uint8)
     sstride = src.shape[1]
     dstride = dst_stride or sstride
-    dst = np.full((height, dstride), dst_fill, np.uint8)
+    dst = out if out is not None else np.full((height, dstride), dst_fill, np.uint8)
     rc = lib().orc_colorlut_apply(cube.kind, cube.size, _f32p(cube.values), _f32p(cube.scale), _f32p(cube.offset),
                                   FMT[fmt], width, height, src.ctypes.data, sstride, dst.ctypes.data, dstride,
                                   threads)
