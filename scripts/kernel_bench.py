@@ -1,0 +1,161 @@
+#!/usr/bin/env python
+"""Per-kernel device-resident timings (CUDA events) for every element of the hot path, with the
+algorithmic-byte roofline of SURVEY 8(d) next to each.  Development tool: the numbers that are
+judged come from bench.py; this prints one JSON object per line so a gpurun call can collect the
+whole matrix at once.  Usage: python scripts/kernel_bench.py [--only colorlut,hsv,...] [--iters 50]"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gst-plugin-rs_b200"))
+
+import numpy as np
+import torch
+
+import b200vfx
+from b200vfx import synth
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+PEAK = peak()
+RING = 6  # distinct in/out buffers so consecutive launches do not hit L2-resident frames
+
+
+def timeit(fn, iters, warm=5):
+    for _ in range(warm):
+        fn(0)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3 / iters
+
+
+def report(name, seconds, algo_bytes, **extra):
+    gbs = algo_bytes / seconds / 1e9
+    print(json.dumps({"kernel": name, "us": round(seconds * 1e6, 3), "algo_GBps": round(gbs, 1), "frac_of_measured_peak": round(gbs / PEAK, 4),
+                      **extra}), flush=True)
+
+
+def ring_of(frame_fn, n=RING):
+    frames = [torch.from_numpy(frame_fn(i)).cuda() for i in range(n)]
+    outs = [torch.empty_like(f) for f in frames]
+    return frames, outs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--iters", type=int, default=60)
+    args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
+    want = lambda k: not only or k in only
+    ctx = b200vfx.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    W, H = 3840, 2160
+    contents = {
+        "ramps": lambda i: np.ascontiguousarray(np.roll(synth.frame_ramps("RGBA", W, H), 4 * 131 * i, axis=1)),
+        "noise": lambda i: synth.frame_noise("RGBA", W, H, 100 + i),
+        "natural": lambda i: synth.frame_natural("RGBA", W, H, 200 + i, amp=3),
+    }
+    if want("colorlut"):
+        for n in (33, 65):
+            k, s, v, sc, of = b200vfx.cube_parse(synth.cube_text_3d(n, "mix"))
+            ctx.colorlut_set_lut(k, s, v, sc, of)
+            for cname, fn in contents.items():
+                frames, outs = ring_of(fn)
+                for mode in (0, 1):
+                    ctx.colorlut_set_mode(mode)
+                    t = timeit(lambda i: ctx.colorlut_process("RGBA", W, H, frames[i % RING], 4 * W, outs[i % RING], 4 * W), args.iters)
+                    report("colorlut3d_%s_rgba8" % ("memo" if mode == 0 else "direct"), t, 2 * W * H * 4, lut=n, content=cname, frame="3840x2160")
+                del frames, outs
+            ctx.colorlut_set_mode(0)
+        # 1D LUT
+        k, s, v, sc, of = b200vfx.cube_parse(synth.cube_text_1d(1024, 2.2))
+        ctx.colorlut_set_lut(k, s, v, sc, of)
+        for cname in ("ramps", "noise"):
+            frames, outs = ring_of(contents[cname])
+            for mode in (0, 1):
+                ctx.colorlut_set_mode(mode)
+                t = timeit(lambda i: ctx.colorlut_process("RGBA", W, H, frames[i % RING], 4 * W, outs[i % RING], 4 * W), args.iters)
+                report("colorlut1d_%s_rgba8" % ("memo" if mode == 0 else "direct"), t, 2 * W * H * 4, lut=1024, content=cname, frame="3840x2160")
+        ctx.colorlut_set_mode(0)
+    if want("colorlut64"):
+        k, s, v, sc, of = b200vfx.cube_parse(synth.cube_text_3d(33, "mix"))
+        ctx.colorlut_set_lut(k, s, v, sc, of)
+        for fmt in ("RGBA64_LE", "RGBA64_BE"):
+            for cname, fn in (("ramps", lambda i: np.ascontiguousarray(np.roll(synth.frame_ramps(fmt, W, H), 8 * 131 * i, axis=1))),
+                              ("noise", lambda i: synth.frame_noise(fmt, W, H, 300 + i))):
+                frames, outs = ring_of(fn, 4)
+                t = timeit(lambda i: ctx.colorlut_process(fmt, W, H, frames[i % 4], 8 * W, outs[i % 4], 8 * W), max(args.iters // 3, 5))
+                report("colorlut3d_direct_%s" % fmt.lower(), t, 2 * W * H * 8, lut=33, content=cname, frame="3840x2160")
+                del frames, outs
+    if want("hsv"):
+        for (w, h, tag) in ((640, 480, "640x480"), (3840, 2160, "3840x2160")):
+            for cname in ("ramps", "noise"):
+                fr = [torch.from_numpy(synth.frame_ramps("RGBA", w, h) if cname == "ramps" else synth.frame_noise("RGBA", w, h, 0x5EED0001 + i)).cuda() for i in range(RING)]
+                t = timeit(lambda i: ctx.hsvfilter_process("RGBA", w, h, fr[i % RING], 4 * w, hue_shift=90.0), args.iters)
+                report("hsvfilter_rgba", t, 2 * w * h * 4, content=cname, frame=tag)
+        w, h = 1920, 1080
+        kw = dict(hue_ref=120.0, hue_var=30.0, saturation_ref=0.8, saturation_var=0.2, value_ref=0.8, value_var=0.2)
+        for cname in ("ramps", "noise"):
+            fr = [torch.from_numpy(synth.frame_ramps("BGRx", w, h) if cname == "ramps" else synth.frame_noise("BGRx", w, h, 0x5EED0003 + i)).cuda() for i in range(RING)]
+            out = [torch.empty_like(f) for f in fr]
+            t = timeit(lambda i: ctx.hsvdetector_process("BGRx", "RGBA", w, h, fr[i % RING], 4 * w, out[i % RING], 4 * w, **kw), args.iters)
+            report("hsvdetector_bgrx_rgba", t, 2 * w * h * 4, content=cname, frame="1920x1080")
+        for (w, h) in ((1920, 1080), (3840, 2160)):
+            fr = [torch.from_numpy(synth.frame_noise("RGB", w, h, 9 + i)).cuda() for i in range(4)]
+            out = [torch.empty((h, 4 * w), dtype=torch.uint8, device="cuda") for _ in range(4)]
+            t = timeit(lambda i: ctx.hsvdetector_process("RGB", "ARGB", w, h, fr[i % 4], 3 * w, out[i % 4], 4 * w, **kw), max(args.iters // 3, 5))
+            report("hsvdetector_rgb_argb", t, w * h * 7, content="noise", frame="%dx%d" % (w, h))
+    if want("videofx"):
+        frames, _ = ring_of(contents["noise"])
+        sums = torch.zeros(64, dtype=torch.int32, device="cuda")
+        t = timeit(lambda i: ctx.blockhash_sums("RGBA", W, H, frames[i % RING], 4 * W, sums), args.iters)
+        report("blockhash_sums_rgba", t, W * H * 4, content="noise", frame="3840x2160", note="one stream; config 4 = two streams")
+        m = torch.empty((1080, 1920), dtype=torch.uint8, device="cuda")
+        t = timeit(lambda i: ctx.roundmask_generate(1920, 1080, 1920, 64, m), 20)
+        report("roundmask_a8", t, 1920 * 1080, frame="1920x1080", radius=64, note="once per caps/radius change")
+    if want("e2e"):
+        k, s, v, sc, of = b200vfx.cube_parse(synth.cube_text_3d(33, "mix"))
+        ctx.colorlut_set_lut(k, s, v, sc, of)
+        src = torch.from_numpy(contents["noise"](0)).pin_memory()
+        dst = torch.empty_like(src).pin_memory()
+        pag_src = contents["noise"](1)
+        pag_dst = np.empty_like(pag_src)
+        for rows in (0, 34, 68, 136, 270, 540, 2160):
+            ctx.set_chunk_rows(rows)
+            ctx.colorlut_process("RGBA", W, H, src.numpy(), 4 * W, dst.numpy(), 4 * W)
+            t0 = time.perf_counter()
+            n = 12
+            for _ in range(n):
+                ctx.colorlut_process("RGBA", W, H, src.numpy(), 4 * W, dst.numpy(), 4 * W)
+            t = (time.perf_counter() - t0) / n
+            print(json.dumps({"kernel": "e2e_colorlut_pinned", "chunk_rows": rows, "ms": round(t * 1e3, 4), "fps": round(1 / t, 1),
+                              "pcie_GBps_each_way": round(W * H * 4 / t / 1e9, 2)}), flush=True)
+        ctx.set_chunk_rows(0)
+        ctx.colorlut_process("RGBA", W, H, pag_src, 4 * W, pag_dst, 4 * W)
+        t0 = time.perf_counter()
+        for _ in range(6):
+            ctx.colorlut_process("RGBA", W, H, pag_src, 4 * W, pag_dst, 4 * W)
+        t = (time.perf_counter() - t0) / 6
+        print(json.dumps({"kernel": "e2e_colorlut_pageable", "ms": round(t * 1e3, 4), "fps": round(1 / t, 1)}), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Tiny launcher for `ncu --set full`: runs a handful of launches of ONE kernel on ONE content."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gst-plugin-rs_b200"))
+import numpy as np
+import torch
+
+import b200vfx
+from b200vfx import synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--kernel", default="memo", choices=["memo", "direct", "direct64", "hsvfilter", "hsvdetector", "blockhash"])
+ap.add_argument("--content", default="ramps", choices=["ramps", "noise", "natural"])
+ap.add_argument("--lut", type=int, default=33)
+ap.add_argument("--launches", type=int, default=6)
+a = ap.parse_args()
+W, H = 3840, 2160
+ctx = b200vfx.Context(0)
+ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+
+def frame(fmt, w, h, i):
+    if a.content == "ramps":
+        return np.ascontiguousarray(np.roll(synth.frame_ramps(fmt, w, h), 8 * 131 * i, axis=1))
+    if a.content == "natural":
+        return synth.frame_natural(fmt, w, h, 200 + i)
+    return synth.frame_noise(fmt, w, h, 100 + i)
+
+
+if a.kernel in ("memo", "direct", "direct64"):
+    k, s, v, sc, of = b200vfx.cube_parse(synth.cube_text_3d(a.lut, "mix"))
+    ctx.colorlut_set_lut(k, s, v, sc, of)
+    ctx.colorlut_set_mode(0 if a.kernel == "memo" else 1)
+    fmt = "RGBA64_LE" if a.kernel == "direct64" else "RGBA"
+    bpp = 8 if a.kernel == "direct64" else 4
+    fr = [torch.from_numpy(frame(fmt, W, H, i)).cuda() for i in range(4)]
+    out = [torch.empty_like(f) for f in fr]
+    for i in range(a.launches):
+        ctx.colorlut_process(fmt, W, H, fr[i % 4], bpp * W, out[i % 4], bpp * W)
+elif a.kernel == "hsvfilter":
+    fr = [torch.from_numpy(frame("RGBA", W, H, i)).cuda() for i in range(4)]
+    for i in range(a.launches):
+        ctx.hsvfilter_process("RGBA", W, H, fr[i % 4], 4 * W, hue_shift=90.0)
+elif a.kernel == "hsvdetector":
+    w, h = 1920, 1080
+    fr = [torch.from_numpy(frame("BGRx", w, h, i)).cuda() for i in range(4)]
+    out = [torch.empty_like(f) for f in fr]
+    for i in range(a.launches):
+        ctx.hsvdetector_process("BGRx", "RGBA", w, h, fr[i % 4], 4 * w, out[i % 4], 4 * w, hue_ref=120.0, hue_var=30.0,
+                                saturation_ref=0.8, saturation_var=0.2, value_ref=0.8, value_var=0.2)
+else:
+    fr = [torch.from_numpy(frame("RGBA", W, H, i)).cuda() for i in range(4)]
+    sums = torch.zeros(64, dtype=torch.int32, device="cuda")
+    for i in range(a.launches):
+        ctx.blockhash_sums("RGBA", W, H, fr[i % 4], 4 * W, sums)
+torch.cuda.synchronize()
+ctx.close()
