@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -48,6 +49,8 @@ struct b200vfx_ctx {
   std::vector<cudaEvent_t> ev_in, ev_k;
   DevBuf stage_in, stage_out, stage_sums;
   int chunk_rows = 0;
+  int sm_count = 148;
+  bool stream_attr_set = false;
   uint64_t launches = 0;
   std::string err;
 
@@ -55,6 +58,7 @@ struct b200vfx_ctx {
   bool have_lut = false;
   int lut_kind = 0, lut_size = 0;
   int mode = 0;  // 0 auto (memo for u8), 1 direct
+  bool stream_path = true;  // TMA-pipelined streaming kernels (off = plain LDG/STG kernels, for A/B measurements)
   float scale[3] = {1, 1, 1}, offset[3] = {0, 0, 0};
   float4 *d_lut3d = nullptr;
   float *d_lut1d = nullptr;
@@ -145,8 +149,22 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
     const bool al = aligned(f.src, f.sstride, 4) && aligned(f.dst, f.dstride, 4);
     int w = f.width, h = f.height;
     long ss = f.sstride, ds = f.dstride;
-    if (al && ss == 4L * w && ds == 4L * w && (long long)w * h < (1LL << 30)) { w = w * h; h = 1; }  // packed: 1-D
-    if (al) {
+    if (al && ss == 4L * w && ds == 4L * w && (long long)w * h < (1LL << 28)) { w = w * h; h = 1; }  // packed: 1-D
+    const bool al16 = aligned(f.src, ss, 16) && aligned(f.dst, ds, 16) && (w % 4) == 0;
+    if (al16 && c->stream_path) {  // TMA-pipelined streaming kernel (the normal case for GStreamer buffers)
+      if (!c->stream_attr_set) {
+        CU(c, cudaFuncSetAttribute(colorlut_memo_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
+        CU(c, cudaFuncSetAttribute(colorlut_memo1d_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
+        c->stream_attr_set = true;
+      }
+      const int row_bytes = 4 * w;
+      const long long ntiles = (long long)ceil_div(row_bytes, kStreamTileBytes) * h;
+      const unsigned grid = (unsigned)std::min<long long>(ntiles, (long long)c->sm_count * 3);
+      if (c->lut_kind == 3)
+        colorlut_memo_stream_kernel<<<grid, kStreamThreads, kStreamSmemBytes, st>>>(c->d_memo, f.src, ss, f.dst, ds, row_bytes, h);
+      else
+        colorlut_memo1d_stream_kernel<<<grid, kStreamThreads, kStreamSmemBytes, st>>>(c->d_memo1d, f.src, ss, f.dst, ds, row_bytes, h);
+    } else if (al) {
       constexpr int PX = 4;
       dim3 grid((unsigned)ceil_div(w, 8 * 32 * PX), grid_rows(h));
       if (c->lut_kind == 3)
@@ -260,8 +278,13 @@ int run_staged(b200vfx_ctx *c, const Staged &s, LaunchFn launch) {
   const bool need_d2h = s.in_place ? true : !dst_dev;
   int rows = c->chunk_rows;
   if (rows <= 0) {
-    const size_t per_row = std::max(s.in_row_bytes, s.out_row_bytes);
-    rows = (int)std::max<size_t>(1, ((size_t)2 << 20) / std::max<size_t>(per_row, 1));
+    // measured on B200/PCIe5 (profiles/r01_e2e_chunks.md): ~8 MB chunks win for 4K frames (4 chunks);
+    // never fewer than 4 chunks (so the two PCIe directions overlap) and never more than 16
+    const size_t per_row = std::max<size_t>(std::max(s.in_row_bytes, s.out_row_bytes), 1);
+    const size_t total = per_row * (size_t)s.height;
+    size_t nch = std::min<size_t>(16, std::max<size_t>(4, total / ((size_t)8 << 20)));
+    if (total / nch < ((size_t)256 << 10)) nch = std::max<size_t>(1, total / ((size_t)256 << 10));
+    rows = (int)std::max<size_t>(1, ((size_t)s.height + nch - 1) / nch);
   }
   const int nchunks = ceil_div(s.height, rows);
   while ((int)c->ev_in.size() < nchunks) {
@@ -351,6 +374,9 @@ int b200vfx_ctx_create(b200vfx_ctx **out, int device) {
   DeviceGuard g(device);
   b200vfx_ctx *c = new b200vfx_ctx();
   c->device = device;
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (c->sm_count <= 0) c->sm_count = 148;
+  if (const char *e = getenv("B200VFX_NO_TMA")) c->stream_path = !(e[0] == '1');
   cudaError_t err = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking);

@@ -6,6 +6,7 @@
 // under the issue budget that the HBM roofline leaves (~55 thread-instr per 8 B pixel).
 #pragma once
 #include "pixel_math.cuh"
+#include "tma_pipe.cuh"
 
 namespace b200vfx {
 
@@ -157,6 +158,121 @@ __global__ void __launch_bounds__(256) colorlut_memo1d_apply_kernel(const uint8_
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// Streaming skeleton for 4-byte -> 4-byte pixel maps (colorlut memo, 4-bpp hsv kernels).
+// Persistent CTAs; the frame moves HBM -> smem -> HBM through the TMA engine in TILE_BYTES bulk
+// copies (cp.async.bulk + mbarrier, STAGES deep), issued by thread 0.  All threads transform the
+// tile IN PLACE in shared memory (lane-consecutive 32-bit accesses: conflict free, and every table
+// gather instruction covers 32 consecutive pixels), then thread 0 bulk-stores it.
+// Requirements (checked by the launcher): rows 16-byte aligned, row_bytes % 16 == 0.
+// --------------------------------------------------------------------------------------------
+constexpr int kStreamTileBytes = 16384;
+constexpr int kStreamStages = 4;
+constexpr int kStreamThreads = 256;
+constexpr int kStreamSmemBytes = kStreamStages * kStreamTileBytes + 64;
+
+template <typename PixelOp>
+__device__ __forceinline__ void stream_map_u32(const PixelOp &op, const uint8_t *__restrict__ src, long sstride,
+                                               uint8_t *__restrict__ dst, long dstride, int row_bytes, int height) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + kStreamStages * kStreamTileBytes);
+  const int tid = threadIdx.x;
+  const int tiles_per_row = (row_bytes + kStreamTileBytes - 1) / kStreamTileBytes;
+  const long long ntiles = (long long)tiles_per_row * height;
+  const long long first = blockIdx.x, step = gridDim.x;
+  const long long mine = first < ntiles ? (ntiles - first + step - 1) / step : 0;  // tiles this CTA owns
+  uint64_t pol_stream = 0;
+  if (tid == 0) {
+    for (int s = 0; s < kStreamStages; s++) tma::mbar_init(&bars[s], 1);
+    tma::fence_barrier_init();
+    pol_stream = tma::policy_evict_first();
+  }
+  __syncthreads();
+  auto tile_geom = [&](long long i, size_t &soff, size_t &doff, uint32_t &nbytes) {
+    const long long t = first + i * step;
+    const int row = (int)(t / tiles_per_row), c = (int)(t % tiles_per_row);
+    const int off = c * kStreamTileBytes;
+    nbytes = (uint32_t)min(kStreamTileBytes, row_bytes - off);
+    soff = (size_t)row * sstride + off;
+    doff = (size_t)row * dstride + off;
+  };
+  auto issue_load = [&](long long i) {  // thread 0 only
+    size_t soff, doff; uint32_t nbytes;
+    tile_geom(i, soff, doff, nbytes);
+    const int s = (int)(i % kStreamStages);
+    tma::mbar_expect_tx(&bars[s], nbytes);
+    tma::bulk_load(smem_raw + s * kStreamTileBytes, src + soff, nbytes, &bars[s], pol_stream);
+  };
+  if (tid == 0)
+    for (long long i = 0; i < mine && i < kStreamStages - 1; i++) issue_load(i);
+  for (long long i = 0; i < mine; i++) {
+    const int s = (int)(i % kStreamStages);
+    size_t soff, doff; uint32_t nbytes;
+    tile_geom(i, soff, doff, nbytes);
+    tma::mbar_wait(&bars[s], (uint32_t)((i / kStreamStages) & 1));
+    uint32_t *tile = reinterpret_cast<uint32_t *>(smem_raw + s * kStreamTileBytes);
+    const int npx = (int)(nbytes >> 2);
+    constexpr int B = 8;  // pixels per thread per batch: 8 independent gathers in flight
+    for (int j0 = tid; j0 < npx; j0 += B * kStreamThreads) {
+      uint32_t px[B], o[B];
+#pragma unroll
+      for (int k = 0; k < B; k++) px[k] = (j0 + k * kStreamThreads < npx) ? tile[j0 + k * kStreamThreads] : 0u;
+#pragma unroll
+      for (int k = 0; k < B; k++) o[k] = op(px[k]);
+#pragma unroll
+      for (int k = 0; k < B; k++)
+        if (j0 + k * kStreamThreads < npx) tile[j0 + k * kStreamThreads] = o[k];
+    }
+    tma::fence_proxy_async();  // my smem writes -> visible to the bulk store
+    __syncthreads();
+    if (tid == 0) {
+      tma::bulk_store(dst + doff, tile, nbytes, pol_stream);
+      tma::bulk_commit();
+      // the stage used one iteration ago is free once its store has finished reading shared memory
+      tma::bulk_wait_read<1>();
+      const long long nxt = i + kStreamStages - 1;
+      if (nxt < mine) issue_load(nxt);
+    }
+  }
+  if (tid == 0) tma::bulk_wait_all<0>();
+}
+
+struct MemoGatherOp {  // out = memo[px & 0xFFFFFF] | alpha
+  const uint32_t *memo;
+  uint64_t policy;
+  __device__ __forceinline__ uint32_t operator()(uint32_t px) const {
+    return tma::ldg_hint_u32(memo + (px & 0x00FFFFFFu), policy) | (px & 0xFF000000u);
+  }
+};
+
+__global__ void __launch_bounds__(kStreamThreads) colorlut_memo_stream_kernel(const uint32_t *__restrict__ memo,
+                                                                             const uint8_t *__restrict__ src, long sstride,
+                                                                             uint8_t *__restrict__ dst, long dstride,
+                                                                             int row_bytes, int height) {
+  MemoGatherOp op{memo, tma::policy_evict_last()};
+  stream_map_u32(op, src, sstride, dst, dstride, row_bytes, height);
+}
+
+struct Memo1dOp {  // three 256-byte tables staged in shared memory
+  const uint8_t *tab;
+  __device__ __forceinline__ uint32_t operator()(uint32_t px) const {
+    const uint32_t r = tab[px & 255u], g = tab[256 + ((px >> 8) & 255u)], b = tab[512 + ((px >> 16) & 255u)];
+    return r | (g << 8) | (b << 16) | (px & 0xFF000000u);
+  }
+};
+
+__global__ void __launch_bounds__(kStreamThreads) colorlut_memo1d_stream_kernel(const uint8_t *__restrict__ memo1d,
+                                                                               const uint8_t *__restrict__ src, long sstride,
+                                                                               uint8_t *__restrict__ dst, long dstride,
+                                                                               int row_bytes, int height) {
+  __shared__ uint8_t tab[768];
+  for (int i = threadIdx.x; i < 768 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t *>(tab)[i] = __ldg(reinterpret_cast<const uint32_t *>(memo1d) + i);
+  __syncthreads();
+  Memo1dOp op{tab};
+  stream_map_u32(op, src, sstride, dst, dstride, row_bytes, height);
+}
+
 // generic byte-addressed fallback for rows that are not 4-byte aligned
 __global__ void colorlut_memo_apply_bytes_kernel(const uint32_t *__restrict__ memo, const uint8_t *__restrict__ memo1d,
                                                  const uint8_t *__restrict__ src, long sstride,
@@ -185,6 +301,8 @@ __global__ void colorlut_memo_apply_bytes_kernel(const uint32_t *__restrict__ me
 template <int BPP, int COFF, bool BGR, bool ALIGNED>
 __global__ void __launch_bounds__(256) hsvfilter_kernel(HsvFilterSettings st, uint8_t *__restrict__ data,
                                                         long stride, int width, int height) {
+  __shared__ float d255[256];
+  fill_d255(d255);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= width) return;
   for (int row = blockIdx.y; row < height; row += gridDim.y) {
@@ -193,14 +311,14 @@ __global__ void __launch_bounds__(256) hsvfilter_kernel(HsvFilterSettings st, ui
       const uint32_t px = *reinterpret_cast<const uint32_t *>(p);
       unsigned c0 = (px >> (8 * COFF)) & 255u, c1 = (px >> (8 * COFF + 8)) & 255u, c2 = (px >> (8 * COFF + 16)) & 255u;
       unsigned r = BGR ? c2 : c0, g = c1, b = BGR ? c0 : c2;
-      hsvfilter_px(st, r, g, b);
+      hsvfilter_px(st, d255, r, g, b);
       c0 = BGR ? b : r; c1 = g; c2 = BGR ? r : b;
       const uint32_t keep = COFF ? (px & 0x000000FFu) : (px & 0xFF000000u);
       *reinterpret_cast<uint32_t *>(p) = keep | (c0 << (8 * COFF)) | (c1 << (8 * COFF + 8)) | (c2 << (8 * COFF + 16));
     } else {
       unsigned c0 = p[COFF], c1 = p[COFF + 1], c2 = p[COFF + 2];
       unsigned r = BGR ? c2 : c0, g = c1, b = BGR ? c0 : c2;
-      hsvfilter_px(st, r, g, b);
+      hsvfilter_px(st, d255, r, g, b);
       p[COFF] = (uint8_t)(BGR ? b : r); p[COFF + 1] = (uint8_t)g; p[COFF + 2] = (uint8_t)(BGR ? r : b);
     }
   }
@@ -211,6 +329,8 @@ template <int IBPP, int ICOFF, bool IBGR, int OCOFF, bool OBGR, bool ALIGNED>
 __global__ void __launch_bounds__(256) hsvdetector_kernel(HsvDetectSettings st, const uint8_t *__restrict__ src,
                                                           long sstride, uint8_t *__restrict__ dst, long dstride,
                                                           int width, int height) {
+  __shared__ float d255[256];
+  fill_d255(d255);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= width) return;
   for (int row = blockIdx.y; row < height; row += gridDim.y) {
@@ -224,7 +344,7 @@ __global__ void __launch_bounds__(256) hsvdetector_kernel(HsvDetectSettings st, 
       c0 = ip[ICOFF]; c1 = ip[ICOFF + 1]; c2 = ip[ICOFF + 2];
     }
     const unsigned r = IBGR ? c2 : c0, g = c1, b = IBGR ? c0 : c2;
-    const unsigned a = hsvdetect_px(st, r, g, b) ? 255u : 0u;
+    const unsigned a = hsvdetect_px(st, d255, r, g, b) ? 255u : 0u;
     const unsigned o0 = OBGR ? b : r, o1 = g, o2 = OBGR ? r : b;
     const uint32_t out = (o0 << (8 * OCOFF)) | (o1 << (8 * OCOFF + 8)) | (o2 << (8 * OCOFF + 16)) | (OCOFF ? a : (a << 24));
     if (ALIGNED) st_stream_u32(reinterpret_cast<uint32_t *>(op), out);
@@ -250,14 +370,21 @@ __global__ void __launch_bounds__(128) blockhash_sums_kernel(const uint8_t *__re
   uint32_t acc = 0;
   if (VEC) {  // BPP == 4
     const int n4 = bw >> 2;
-    for (int y = y0; y < y1; y++) {
-      const uint4 *row = reinterpret_cast<const uint4 *>(src + (size_t)y * stride + (size_t)bx * bw * 4);
-      for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-        const uint4 q = __ldcs(row + i);
-        acc += (q.x >> 24) ? __dp4a(q.x, 0x00010101u, 0u) : 765u;   // A==0 counts as white (765)
-        acc += (q.y >> 24) ? __dp4a(q.y, 0x00010101u, 0u) : 765u;
-        acc += (q.z >> 24) ? __dp4a(q.z, 0x00010101u, 0u) : 765u;
-        acc += (q.w >> 24) ? __dp4a(q.w, 0x00010101u, 0u) : 765u;
+    constexpr int U = 8;  // rows in flight per thread: 8 independent 16-byte loads (latency hiding)
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const uint8_t *col = src + (size_t)bx * bw * 4 + (size_t)i * 16;
+      for (int y = y0; y < y1; y += U) {
+        uint4 q[U];
+#pragma unroll
+        for (int r = 0; r < U; r++)
+          q[r] = (y + r < y1) ? __ldcs(reinterpret_cast<const uint4 *>(col + (size_t)(y + r) * stride)) : make_uint4(0xFF000000u, 0xFF000000u, 0xFF000000u, 0xFF000000u);
+#pragma unroll
+        for (int r = 0; r < U; r++) {  // out-of-range rows load an opaque black pixel: contributes 0
+          acc += (q[r].x >> 24) ? __dp4a(q[r].x, 0x00010101u, 0u) : 765u;   // A==0 counts as white (765)
+          acc += (q[r].y >> 24) ? __dp4a(q[r].y, 0x00010101u, 0u) : 765u;
+          acc += (q[r].z >> 24) ? __dp4a(q[r].z, 0x00010101u, 0u) : 765u;
+          acc += (q[r].w >> 24) ? __dp4a(q[r].w, 0x00010101u, 0u) : 765u;
+        }
       }
     }
   } else {
