@@ -367,3 +367,24 @@ def test_roundmask(ctx, w, h, stride, r):
     got = np.full(exp.shape, 0x77, np.uint8)
     ctx.roundmask_generate(w, h, stride, r, got)
     assert (got == exp).all()
+
+
+# ---- row tiles (the multi-GPU sharding unit) -------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_row_tiles_match_full_frame(ctx, world):
+    """rank r calls the C ABI on (data + r0*stride, rows): tiles + seams must equal the single-call result"""
+    from b200vfx import sharding
+    w, h = 1280, 723
+    cube = orc.cube_parse(synth.cube_text_3d(17, "mix"))
+    set_cube(ctx, cube)
+    frame = synth.frame_natural("RGBA", w, h, 5)
+    full = gpu_colorlut(ctx, "RGBA", w, h, frame)
+    tiled = np.zeros_like(frame)
+    hs = frame.copy()
+    for r in range(world):
+        r0, r1 = sharding.row_range(h, world, r)
+        if r1 > r0:
+            ctx.colorlut_process("RGBA", w, r1 - r0, frame[r0:].ctypes.data, 4 * w, tiled[r0:].ctypes.data, 4 * w)
+            ctx.hsvfilter_process("RGBA", w, r1 - r0, hs[r0:].ctypes.data, 4 * w, hue_shift=33.0)
+    assert (tiled == full).all() and (full == orc.colorlut_apply(cube, "RGBA", w, h, frame)).all()
+    assert (hs == orc.hsvfilter("RGBA", w, h, frame, hue_shift=33.0)).all()
