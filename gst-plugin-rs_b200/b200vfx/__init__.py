@@ -69,6 +69,7 @@ def lib() -> C.CDLL:
         "b200vfx_ctx_synchronize": ([vp], ci),
         "b200vfx_ctx_set_chunk_rows": ([vp, ci], ci),
         "b200vfx_ctx_kernel_launches": ([vp], C.c_uint64),
+        "b200vfx_ctx_set_option": ([vp, C.c_char_p, ci], ci),
         "b200vfx_host_alloc": ([C.c_size_t], vp),
         "b200vfx_host_free": ([vp], None),
         "b200vfx_cube_parse": ([C.c_char_p, C.c_size_t, C.POINTER(ci), C.POINTER(ci), C.POINTER(f32p), f32p, f32p,
@@ -180,6 +181,9 @@ class Context:
 
     def set_chunk_rows(self, rows: int):
         self._chk(lib().b200vfx_ctx_set_chunk_rows(self._h, rows))
+
+    def set_option(self, name: str, value: int):
+        self._chk(lib().b200vfx_ctx_set_option(self._h, name.encode(), int(value)))
 
     @property
     def kernel_launches(self) -> int:

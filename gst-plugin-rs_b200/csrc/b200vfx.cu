@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "stream_map.cuh"
 
 using namespace b200vfx;
 
@@ -50,7 +51,7 @@ struct b200vfx_ctx {
   DevBuf stage_in, stage_out, stage_sums;
   int chunk_rows = 0;
   int sm_count = 148;
-  bool stream_attr_set = false;
+  int stream_cfg = 0, stream_ctas = 0, stream_hint = 1, memo_px = 4;  // tuning knobs (env overrides, see ctx_create)
   uint64_t launches = 0;
   std::string err;
 
@@ -118,6 +119,13 @@ inline bool aligned(const void *p, long stride, int a) {
 }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline unsigned grid_rows(int height) { return (unsigned)std::min(height, 65535); }
+// compute-heavy 1-pixel-per-thread kernels loop over rows: size grid.y so that ~12 CTAs per SM exist and every
+// thread amortises its per-CTA prologue (shared-memory tables) over many pixels
+inline unsigned grid_rows_persistent(int grid_x, int height, int sm_count) {
+  const long target = (long)sm_count * 12;
+  long gy = std::max<long>(1, target / std::max(grid_x, 1));
+  return (unsigned)std::min<long>(std::min<long>(gy, height), 65535);
+}
 
 LutParams lut_params(const b200vfx_ctx *c) {
   LutParams p;
@@ -129,6 +137,45 @@ LutParams lut_params(const b200vfx_ctx *c) {
 
 // ---- per-element kernel launchers on DEVICE frames ------------------------------------------
 struct Frame { const uint8_t *src; long sstride; uint8_t *dst; long dstride; int width, height; };
+
+// TMA streaming kernel variants (tile bytes, stages, threads, gathers in flight per thread); the
+// default was picked from the sweep in profiles/ (B200VFX_STREAM_CFG / _CTAS / _HINT override it for A/B runs)
+template <int TILE, int STAGES, int THREADS, int B>
+int launch_memo_stream_t(b200vfx_ctx *c, const uint8_t *src, long ss, uint8_t *dst, long ds, int row_bytes, int h,
+                         cudaStream_t st) {
+  constexpr int smem = stream_smem_bytes<TILE, STAGES>();
+  auto k3 = colorlut_memo_stream_kernel<TILE, STAGES, THREADS, B>;
+  auto k1 = colorlut_memo1d_stream_kernel<TILE, STAGES, THREADS, B>;
+  static thread_local bool attr_done = false;
+  if (!attr_done) {
+    CU(c, cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(c, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  int per_sm = 0;
+  CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3, THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  if (c->stream_ctas > 0) per_sm = std::min(per_sm, c->stream_ctas);
+  const long long ntiles = (long long)ceil_div(row_bytes, TILE) * h;
+  const unsigned grid = (unsigned)std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
+  if (c->lut_kind == 3) k3<<<grid, THREADS, smem, st>>>(c->d_memo, c->stream_hint, src, ss, dst, ds, row_bytes, h);
+  else k1<<<grid, THREADS, smem, st>>>(c->d_memo1d, src, ss, dst, ds, row_bytes, h);
+  return 0;
+}
+
+int launch_memo_stream(b200vfx_ctx *c, const uint8_t *src, long ss, uint8_t *dst, long ds, int row_bytes, int h,
+                       cudaStream_t st) {
+  switch (c->stream_cfg) {
+    case 1: return launch_memo_stream_t<8192, 4, 256, 8>(c, src, ss, dst, ds, row_bytes, h, st);
+    case 2: return launch_memo_stream_t<4096, 4, 256, 4>(c, src, ss, dst, ds, row_bytes, h, st);
+    case 3: return launch_memo_stream_t<4096, 8, 128, 8>(c, src, ss, dst, ds, row_bytes, h, st);
+    case 4: return launch_memo_stream_t<2048, 8, 128, 4>(c, src, ss, dst, ds, row_bytes, h, st);
+    case 5: return launch_memo_stream_t<8192, 6, 512, 4>(c, src, ss, dst, ds, row_bytes, h, st);
+    case 6: return launch_memo_stream_t<4096, 6, 512, 2>(c, src, ss, dst, ds, row_bytes, h, st);
+    case 7: return launch_memo_stream_t<2048, 6, 256, 2>(c, src, ss, dst, ds, row_bytes, h, st);
+    default: return launch_memo_stream_t<16384, 4, 256, 8>(c, src, ss, dst, ds, row_bytes, h, st);
+  }
+}
 
 int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
   if (f.width == 0 || f.height == 0) return 0;
@@ -152,25 +199,17 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
     if (al && ss == 4L * w && ds == 4L * w && (long long)w * h < (1LL << 28)) { w = w * h; h = 1; }  // packed: 1-D
     const bool al16 = aligned(f.src, ss, 16) && aligned(f.dst, ds, 16) && (w % 4) == 0;
     if (al16 && c->stream_path) {  // TMA-pipelined streaming kernel (the normal case for GStreamer buffers)
-      if (!c->stream_attr_set) {
-        CU(c, cudaFuncSetAttribute(colorlut_memo_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
-        CU(c, cudaFuncSetAttribute(colorlut_memo1d_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
-        c->stream_attr_set = true;
-      }
-      const int row_bytes = 4 * w;
-      const long long ntiles = (long long)ceil_div(row_bytes, kStreamTileBytes) * h;
-      const unsigned grid = (unsigned)std::min<long long>(ntiles, (long long)c->sm_count * 3);
-      if (c->lut_kind == 3)
-        colorlut_memo_stream_kernel<<<grid, kStreamThreads, kStreamSmemBytes, st>>>(c->d_memo, f.src, ss, f.dst, ds, row_bytes, h);
-      else
-        colorlut_memo1d_stream_kernel<<<grid, kStreamThreads, kStreamSmemBytes, st>>>(c->d_memo1d, f.src, ss, f.dst, ds, row_bytes, h);
+      if (int rc = launch_memo_stream(c, f.src, ss, f.dst, ds, 4 * w, h, st)) return rc;
     } else if (al) {
-      constexpr int PX = 4;
+      const int PX = c->memo_px;
       dim3 grid((unsigned)ceil_div(w, 8 * 32 * PX), grid_rows(h));
-      if (c->lut_kind == 3)
-        colorlut_memo_apply_kernel<PX><<<grid, 256, 0, st>>>(c->d_memo, f.src, ss, f.dst, ds, w, h);
-      else
-        colorlut_memo1d_apply_kernel<PX><<<grid, 256, 0, st>>>(c->d_memo1d, f.src, ss, f.dst, ds, w, h);
+#define LAUNCH_PLAIN(P)                                                                                               \
+  do {                                                                                                                \
+    if (c->lut_kind == 3) colorlut_memo_apply_kernel<P><<<grid, 256, 0, st>>>(c->d_memo, f.src, ss, f.dst, ds, w, h);  \
+    else colorlut_memo1d_apply_kernel<P><<<grid, 256, 0, st>>>(c->d_memo1d, f.src, ss, f.dst, ds, w, h);              \
+  } while (0)
+      if (PX == 16) LAUNCH_PLAIN(16); else if (PX == 8) LAUNCH_PLAIN(8); else LAUNCH_PLAIN(4);
+#undef LAUNCH_PLAIN
     } else {
       dim3 grid((unsigned)ceil_div(w, 256), grid_rows(h));
       colorlut_memo_apply_bytes_kernel<<<grid, 256, 0, st>>>(c->lut_kind == 3 ? c->d_memo : nullptr, c->d_memo1d,
@@ -180,7 +219,7 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
     CU(c, cudaGetLastError());
     return 0;
   }
-  dim3 grid((unsigned)ceil_div(f.width, 256), grid_rows(f.height));
+  dim3 grid((unsigned)ceil_div(f.width, 256), grid_rows_persistent(ceil_div(f.width, 256), f.height, c->sm_count));
   const bool al4 = aligned(f.src, f.sstride, 4) && aligned(f.dst, f.dstride, 4);
   const bool al8 = aligned(f.src, f.sstride, 8) && aligned(f.dst, f.dstride, 8);
   if (((uintptr_t)f.src | (uintptr_t)f.dst) & 1u && fmt != B200VFX_FORMAT_RGBA)
@@ -199,8 +238,8 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
 }
 
 template <int BPP, int COFF, bool BGR>
-void launch_hsvfilter_t(const HsvFilterSettings &s, uint8_t *data, long stride, int w, int h, cudaStream_t st) {
-  dim3 grid((unsigned)ceil_div(w, 256), grid_rows(h));
+void launch_hsvfilter_t(const HsvFilterSettings &s, uint8_t *data, long stride, int w, int h, cudaStream_t st, int sm_count) {
+  dim3 grid((unsigned)ceil_div(w, 256), grid_rows_persistent(ceil_div(w, 256), h, sm_count));
   if (BPP == 4 && aligned(data, stride, 4)) hsvfilter_kernel<BPP, COFF, BGR, true><<<grid, 256, 0, st>>>(s, data, stride, w, h);
   else hsvfilter_kernel<BPP, COFF, BGR, false><<<grid, 256, 0, st>>>(s, data, stride, w, h);
 }
@@ -208,17 +247,17 @@ void launch_hsvfilter_t(const HsvFilterSettings &s, uint8_t *data, long stride, 
 int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings &s, uint8_t *data, long stride,
                      int w, int h, cudaStream_t st) {
   if (w == 0 || h == 0) return 0;
-  if (fi.bpp == 3) { if (fi.bgr) launch_hsvfilter_t<3, 0, true>(s, data, stride, w, h, st); else launch_hsvfilter_t<3, 0, false>(s, data, stride, w, h, st); }
-  else if (fi.coff == 0) { if (fi.bgr) launch_hsvfilter_t<4, 0, true>(s, data, stride, w, h, st); else launch_hsvfilter_t<4, 0, false>(s, data, stride, w, h, st); }
-  else { if (fi.bgr) launch_hsvfilter_t<4, 1, true>(s, data, stride, w, h, st); else launch_hsvfilter_t<4, 1, false>(s, data, stride, w, h, st); }
+  if (fi.bpp == 3) { if (fi.bgr) launch_hsvfilter_t<3, 0, true>(s, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<3, 0, false>(s, data, stride, w, h, st, c->sm_count); }
+  else if (fi.coff == 0) { if (fi.bgr) launch_hsvfilter_t<4, 0, true>(s, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<4, 0, false>(s, data, stride, w, h, st, c->sm_count); }
+  else { if (fi.bgr) launch_hsvfilter_t<4, 1, true>(s, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<4, 1, false>(s, data, stride, w, h, st, c->sm_count); }
   c->launches++;
   CU(c, cudaGetLastError());
   return 0;
 }
 
 template <int IBPP, int ICOFF, bool IBGR>
-void launch_hsvdetector_t(const FmtInfo &fo, const HsvDetectSettings &s, const Frame &f, cudaStream_t st) {
-  dim3 grid((unsigned)ceil_div(f.width, 256), grid_rows(f.height));
+void launch_hsvdetector_t(const FmtInfo &fo, const HsvDetectSettings &s, const Frame &f, cudaStream_t st, int sm_count) {
+  dim3 grid((unsigned)ceil_div(f.width, 256), grid_rows_persistent(ceil_div(f.width, 256), f.height, sm_count));
   const bool al = aligned(f.dst, f.dstride, 4) && (IBPP == 3 || aligned(f.src, f.sstride, 4));
 #define L(OC, OB)                                                                                                   \
   do {                                                                                                              \
@@ -233,9 +272,9 @@ void launch_hsvdetector_t(const FmtInfo &fo, const HsvDetectSettings &s, const F
 int launch_hsvdetector(b200vfx_ctx *c, const FmtInfo &fi, const FmtInfo &fo, const HsvDetectSettings &s,
                        const Frame &f, cudaStream_t st) {
   if (f.width == 0 || f.height == 0) return 0;
-  if (fi.bpp == 3) { if (fi.bgr) launch_hsvdetector_t<3, 0, true>(fo, s, f, st); else launch_hsvdetector_t<3, 0, false>(fo, s, f, st); }
-  else if (fi.coff == 0) { if (fi.bgr) launch_hsvdetector_t<4, 0, true>(fo, s, f, st); else launch_hsvdetector_t<4, 0, false>(fo, s, f, st); }
-  else { if (fi.bgr) launch_hsvdetector_t<4, 1, true>(fo, s, f, st); else launch_hsvdetector_t<4, 1, false>(fo, s, f, st); }
+  if (fi.bpp == 3) { if (fi.bgr) launch_hsvdetector_t<3, 0, true>(fo, s, f, st, c->sm_count); else launch_hsvdetector_t<3, 0, false>(fo, s, f, st, c->sm_count); }
+  else if (fi.coff == 0) { if (fi.bgr) launch_hsvdetector_t<4, 0, true>(fo, s, f, st, c->sm_count); else launch_hsvdetector_t<4, 0, false>(fo, s, f, st, c->sm_count); }
+  else { if (fi.bgr) launch_hsvdetector_t<4, 1, true>(fo, s, f, st, c->sm_count); else launch_hsvdetector_t<4, 1, false>(fo, s, f, st, c->sm_count); }
   c->launches++;
   CU(c, cudaGetLastError());
   return 0;
@@ -377,6 +416,10 @@ int b200vfx_ctx_create(b200vfx_ctx **out, int device) {
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (c->sm_count <= 0) c->sm_count = 148;
   if (const char *e = getenv("B200VFX_NO_TMA")) c->stream_path = !(e[0] == '1');
+  if (const char *e = getenv("B200VFX_STREAM_CFG")) c->stream_cfg = atoi(e);
+  if (const char *e = getenv("B200VFX_STREAM_CTAS")) c->stream_ctas = atoi(e);
+  if (const char *e = getenv("B200VFX_STREAM_HINT")) c->stream_hint = atoi(e);
+  if (const char *e = getenv("B200VFX_MEMO_PX")) c->memo_px = atoi(e);
   cudaError_t err = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking);
@@ -426,6 +469,18 @@ int b200vfx_ctx_set_chunk_rows(b200vfx_ctx *c, int rows) {
 }
 
 uint64_t b200vfx_ctx_kernel_launches(const b200vfx_ctx *c) { return c ? c->launches : 0; }
+
+int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
+  if (!c || !name) return fail(c, B200VFX_ERR_INVALID, "null argument");
+  const std::string n(name);
+  if (n == "stream_path") c->stream_path = value != 0;
+  else if (n == "stream_cfg") c->stream_cfg = value;
+  else if (n == "stream_ctas") c->stream_ctas = value;
+  else if (n == "stream_hint") c->stream_hint = value;
+  else if (n == "memo_px") c->memo_px = value;
+  else return fail(c, B200VFX_ERR_INVALID, "unknown option '%s'", name);
+  return 0;
+}
 
 void *b200vfx_host_alloc(size_t bytes) {
   void *p = nullptr;

@@ -158,121 +158,6 @@ __global__ void __launch_bounds__(256) colorlut_memo1d_apply_kernel(const uint8_
   }
 }
 
-// --------------------------------------------------------------------------------------------
-// Streaming skeleton for 4-byte -> 4-byte pixel maps (colorlut memo, 4-bpp hsv kernels).
-// Persistent CTAs; the frame moves HBM -> smem -> HBM through the TMA engine in TILE_BYTES bulk
-// copies (cp.async.bulk + mbarrier, STAGES deep), issued by thread 0.  All threads transform the
-// tile IN PLACE in shared memory (lane-consecutive 32-bit accesses: conflict free, and every table
-// gather instruction covers 32 consecutive pixels), then thread 0 bulk-stores it.
-// Requirements (checked by the launcher): rows 16-byte aligned, row_bytes % 16 == 0.
-// --------------------------------------------------------------------------------------------
-constexpr int kStreamTileBytes = 16384;
-constexpr int kStreamStages = 4;
-constexpr int kStreamThreads = 256;
-constexpr int kStreamSmemBytes = kStreamStages * kStreamTileBytes + 64;
-
-template <typename PixelOp>
-__device__ __forceinline__ void stream_map_u32(const PixelOp &op, const uint8_t *__restrict__ src, long sstride,
-                                               uint8_t *__restrict__ dst, long dstride, int row_bytes, int height) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + kStreamStages * kStreamTileBytes);
-  const int tid = threadIdx.x;
-  const int tiles_per_row = (row_bytes + kStreamTileBytes - 1) / kStreamTileBytes;
-  const long long ntiles = (long long)tiles_per_row * height;
-  const long long first = blockIdx.x, step = gridDim.x;
-  const long long mine = first < ntiles ? (ntiles - first + step - 1) / step : 0;  // tiles this CTA owns
-  uint64_t pol_stream = 0;
-  if (tid == 0) {
-    for (int s = 0; s < kStreamStages; s++) tma::mbar_init(&bars[s], 1);
-    tma::fence_barrier_init();
-    pol_stream = tma::policy_evict_first();
-  }
-  __syncthreads();
-  auto tile_geom = [&](long long i, size_t &soff, size_t &doff, uint32_t &nbytes) {
-    const long long t = first + i * step;
-    const int row = (int)(t / tiles_per_row), c = (int)(t % tiles_per_row);
-    const int off = c * kStreamTileBytes;
-    nbytes = (uint32_t)min(kStreamTileBytes, row_bytes - off);
-    soff = (size_t)row * sstride + off;
-    doff = (size_t)row * dstride + off;
-  };
-  auto issue_load = [&](long long i) {  // thread 0 only
-    size_t soff, doff; uint32_t nbytes;
-    tile_geom(i, soff, doff, nbytes);
-    const int s = (int)(i % kStreamStages);
-    tma::mbar_expect_tx(&bars[s], nbytes);
-    tma::bulk_load(smem_raw + s * kStreamTileBytes, src + soff, nbytes, &bars[s], pol_stream);
-  };
-  if (tid == 0)
-    for (long long i = 0; i < mine && i < kStreamStages - 1; i++) issue_load(i);
-  for (long long i = 0; i < mine; i++) {
-    const int s = (int)(i % kStreamStages);
-    size_t soff, doff; uint32_t nbytes;
-    tile_geom(i, soff, doff, nbytes);
-    tma::mbar_wait(&bars[s], (uint32_t)((i / kStreamStages) & 1));
-    uint32_t *tile = reinterpret_cast<uint32_t *>(smem_raw + s * kStreamTileBytes);
-    const int npx = (int)(nbytes >> 2);
-    constexpr int B = 8;  // pixels per thread per batch: 8 independent gathers in flight
-    for (int j0 = tid; j0 < npx; j0 += B * kStreamThreads) {
-      uint32_t px[B], o[B];
-#pragma unroll
-      for (int k = 0; k < B; k++) px[k] = (j0 + k * kStreamThreads < npx) ? tile[j0 + k * kStreamThreads] : 0u;
-#pragma unroll
-      for (int k = 0; k < B; k++) o[k] = op(px[k]);
-#pragma unroll
-      for (int k = 0; k < B; k++)
-        if (j0 + k * kStreamThreads < npx) tile[j0 + k * kStreamThreads] = o[k];
-    }
-    tma::fence_proxy_async();  // my smem writes -> visible to the bulk store
-    __syncthreads();
-    if (tid == 0) {
-      tma::bulk_store(dst + doff, tile, nbytes, pol_stream);
-      tma::bulk_commit();
-      // the stage used one iteration ago is free once its store has finished reading shared memory
-      tma::bulk_wait_read<1>();
-      const long long nxt = i + kStreamStages - 1;
-      if (nxt < mine) issue_load(nxt);
-    }
-  }
-  if (tid == 0) tma::bulk_wait_all<0>();
-}
-
-struct MemoGatherOp {  // out = memo[px & 0xFFFFFF] | alpha
-  const uint32_t *memo;
-  uint64_t policy;
-  __device__ __forceinline__ uint32_t operator()(uint32_t px) const {
-    return tma::ldg_hint_u32(memo + (px & 0x00FFFFFFu), policy) | (px & 0xFF000000u);
-  }
-};
-
-__global__ void __launch_bounds__(kStreamThreads) colorlut_memo_stream_kernel(const uint32_t *__restrict__ memo,
-                                                                             const uint8_t *__restrict__ src, long sstride,
-                                                                             uint8_t *__restrict__ dst, long dstride,
-                                                                             int row_bytes, int height) {
-  MemoGatherOp op{memo, tma::policy_evict_last()};
-  stream_map_u32(op, src, sstride, dst, dstride, row_bytes, height);
-}
-
-struct Memo1dOp {  // three 256-byte tables staged in shared memory
-  const uint8_t *tab;
-  __device__ __forceinline__ uint32_t operator()(uint32_t px) const {
-    const uint32_t r = tab[px & 255u], g = tab[256 + ((px >> 8) & 255u)], b = tab[512 + ((px >> 16) & 255u)];
-    return r | (g << 8) | (b << 16) | (px & 0xFF000000u);
-  }
-};
-
-__global__ void __launch_bounds__(kStreamThreads) colorlut_memo1d_stream_kernel(const uint8_t *__restrict__ memo1d,
-                                                                               const uint8_t *__restrict__ src, long sstride,
-                                                                               uint8_t *__restrict__ dst, long dstride,
-                                                                               int row_bytes, int height) {
-  __shared__ uint8_t tab[768];
-  for (int i = threadIdx.x; i < 768 / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t *>(tab)[i] = __ldg(reinterpret_cast<const uint32_t *>(memo1d) + i);
-  __syncthreads();
-  Memo1dOp op{tab};
-  stream_map_u32(op, src, sstride, dst, dstride, row_bytes, height);
-}
-
 // generic byte-addressed fallback for rows that are not 4-byte aligned
 __global__ void colorlut_memo_apply_bytes_kernel(const uint32_t *__restrict__ memo, const uint8_t *__restrict__ memo1d,
                                                  const uint8_t *__restrict__ src, long sstride,
