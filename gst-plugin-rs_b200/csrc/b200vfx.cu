@@ -13,6 +13,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -51,6 +54,8 @@ struct b200vfx_ctx {
   DevBuf stage_in, stage_out, stage_sums;
   int chunk_rows = 0;
   int sm_count = 148;
+  bool pdl = true;       // programmatic dependent launch for out-of-place frame kernels
+  bool pdl_now = false;  // per launch: false when this call (re)built a table the kernel reads
   int stream_cfg = 0, stream_ctas = 0, stream_hint = 1, memo_px = 4;  // tuning knobs (env overrides, see ctx_create)
   uint64_t launches = 0;
   std::string err;
@@ -59,11 +64,13 @@ struct b200vfx_ctx {
   bool have_lut = false;
   int lut_kind = 0, lut_size = 0;
   int mode = 0;  // 0 auto (memo for u8), 1 direct
-  bool stream_path = true;  // TMA-pipelined streaming kernels (off = plain LDG/STG kernels, for A/B measurements)
+  int stream_path = -1;  // TMA-pipelined streaming kernels: -1 auto (1D memo: on; 3D memo: off, the gathers dominate and the
+                         // plain LDG kernel measured faster, profiles/r01_sweep_memo.md), 0 off, 1 on
   float scale[3] = {1, 1, 1}, offset[3] = {0, 0, 0};
-  float4 *d_lut3d = nullptr;
+  LutPair *d_pair = nullptr;     // x-pair table (3D)
   float *d_lut1d = nullptr;
-  float2 *d_axis = nullptr;
+  uint4 *d_axis8 = nullptr;      // [3][256]   axis table for RGBA
+  uint4 *d_axis16 = nullptr;     // [3][65536] axis table for RGBA64 (built on the first RGBA64 frame)
   uint32_t *d_memo = nullptr;   // 2^24 x u32 (3D)
   uint8_t *d_memo1d = nullptr;  // 768 bytes (1D)
   bool memo_ready = false;
@@ -127,12 +134,75 @@ inline unsigned grid_rows_persistent(int grid_x, int height, int sm_count) {
   return (unsigned)std::min<long>(std::min<long>(gy, height), 65535);
 }
 
-LutParams lut_params(const b200vfx_ctx *c) {
-  LutParams p;
-  p.lut3d = c->d_lut3d; p.lut1d = c->d_lut1d; p.axis = c->d_axis;
-  p.size = c->lut_size; p.kind = c->lut_kind;
+LutDev lut_dev(const b200vfx_ctx *c, bool wide) {
+  LutDev L;
+  L.pair = c->d_pair; L.lut1d = c->d_lut1d;
+  L.axis = wide ? c->d_axis16 : c->d_axis8;
+  L.axis_len = wide ? 65536 : 256;
+  L.size = c->lut_size; L.kind = c->lut_kind;
+  return L;
+}
+
+int build_axis(b200vfx_ctx *c, bool wide, cudaStream_t st) {
+  uint4 **slot = wide ? &c->d_axis16 : &c->d_axis8;
+  if (*slot) return 0;
+  AxisBuildParams p;
+  p.size = c->lut_size; p.kind = c->lut_kind; p.axis_len = wide ? 65536 : 256;
+  p.denom = wide ? 65535.0f : 255.0f;   // norm_comp_u16 / norm_comp (imp.rs:471-479)
   for (int i = 0; i < 3; i++) { p.scale[i] = c->scale[i]; p.offset[i] = c->offset[i]; }
-  return p;
+  CU(c, cudaMalloc(slot, (size_t)3 * p.axis_len * sizeof(uint4)));
+  colorlut_axis_table_kernel<<<ceil_div(3 * p.axis_len, 256), 256, 0, st>>>(*slot, p);
+  c->launches++;
+  CU(c, cudaGetLastError());
+  return 0;
+}
+
+// Programmatic dependent launch (PDL): our out-of-place frame kernels do not depend on the previous frame's kernel,
+// so they are launched with programmaticStreamSerialization and trigger `griddepcontrol.launch_dependents` at
+// entry: the next frame's CTAs fill the SMs while this frame's tail drains (same stream, no extra streams).
+// Foreign kernels (which never trigger early) and plain launches/copies still wait for full completion.
+// PDL overlap is only used when the new kernel cannot conflict with any of OUR recent (possibly still running)
+// kernels on the same stream: its output must not touch their inputs/outputs and its input must not be one of
+// their outputs.  The tracker is process-wide (elements chained on one stream use different contexts).
+struct Span { uintptr_t lo, hi; };
+struct RecentLaunch { Span src, dst; };
+std::mutex g_recent_mu;
+std::map<cudaStream_t, std::deque<RecentLaunch>> g_recent;
+
+inline Span span_of(const void *p, long stride, size_t row_bytes, int rows) {
+  if (!p || rows <= 0) return Span{0, 0};
+  const uintptr_t lo = (uintptr_t)p;
+  return Span{lo, lo + (size_t)(rows - 1) * (size_t)stride + row_bytes};
+}
+inline bool overlap(Span a, Span b) { return a.lo < b.hi && b.lo < a.hi; }
+
+// returns whether the launch may use PDL, and records it
+bool pdl_admit(bool want, cudaStream_t st, Span src, Span dst) {
+  std::lock_guard<std::mutex> g(g_recent_mu);
+  std::deque<RecentLaunch> &q = g_recent[st];
+  bool ok = want;
+  if (ok)
+    for (const RecentLaunch &r : q)
+      if (overlap(dst, r.src) || overlap(dst, r.dst) || overlap(src, r.dst)) { ok = false; break; }
+  if (!ok) q.clear();  // a normal launch starts only after everything before it has completed
+  q.push_back(RecentLaunch{src, dst});
+  if (q.size() > 4) q.pop_front();
+  return ok;
+}
+void pdl_forget(cudaStream_t st) {  // after a stream synchronisation nothing of ours is in flight
+  std::lock_guard<std::mutex> g(g_recent_mu);
+  g_recent.erase(st);
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ---- per-element kernel launchers on DEVICE frames ------------------------------------------
@@ -158,8 +228,8 @@ int launch_memo_stream_t(b200vfx_ctx *c, const uint8_t *src, long ss, uint8_t *d
   if (c->stream_ctas > 0) per_sm = std::min(per_sm, c->stream_ctas);
   const long long ntiles = (long long)ceil_div(row_bytes, TILE) * h;
   const unsigned grid = (unsigned)std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
-  if (c->lut_kind == 3) k3<<<grid, THREADS, smem, st>>>(c->d_memo, c->stream_hint, src, ss, dst, ds, row_bytes, h);
-  else k1<<<grid, THREADS, smem, st>>>(c->d_memo1d, src, ss, dst, ds, row_bytes, h);
+  if (c->lut_kind == 3) CU(c, launch_k(c->pdl_now, k3, dim3(grid), dim3(THREADS), smem, st, c->d_memo, c->stream_hint, src, ss, dst, ds, row_bytes, h));
+  else CU(c, launch_k(c->pdl_now, k1, dim3(grid), dim3(THREADS), smem, st, c->d_memo1d, src, ss, dst, ds, row_bytes, h));
   return 0;
 }
 
@@ -179,7 +249,15 @@ int launch_memo_stream(b200vfx_ctx *c, const uint8_t *src, long ss, uint8_t *dst
 
 int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
   if (f.width == 0 || f.height == 0) return 0;
-  const LutParams p = lut_params(c);
+  const bool wide = fmt != B200VFX_FORMAT_RGBA;
+  {
+    const size_t rb = (size_t)f.width * (wide ? 8 : 4);
+    const bool tables_ready = (wide ? c->d_axis16 != nullptr : c->d_axis8 != nullptr) &&
+                              (fmt != B200VFX_FORMAT_RGBA || c->mode != 0 || c->memo_ready);
+    c->pdl_now = pdl_admit(c->pdl && tables_ready, st, span_of(f.src, f.sstride, rb, f.height), span_of(f.dst, f.dstride, rb, f.height));
+  }
+  if (int rc = build_axis(c, wide, st)) return rc;
+  const LutDev p = lut_dev(c, wide);
   if (fmt == B200VFX_FORMAT_RGBA && c->mode == 0) {
     if (!c->memo_ready) {  // once per LUT: evaluate all 2^24 colours with the exact direct evaluator
       if (c->lut_kind == 3) {
@@ -198,15 +276,16 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
     long ss = f.sstride, ds = f.dstride;
     if (al && ss == 4L * w && ds == 4L * w && (long long)w * h < (1LL << 28)) { w = w * h; h = 1; }  // packed: 1-D
     const bool al16 = aligned(f.src, ss, 16) && aligned(f.dst, ds, 16) && (w % 4) == 0;
-    if (al16 && c->stream_path) {  // TMA-pipelined streaming kernel (the normal case for GStreamer buffers)
+    const bool use_stream = c->stream_path == 1 || (c->stream_path < 0 && c->lut_kind == 1);
+    if (al16 && use_stream) {  // TMA-pipelined streaming kernel (the normal case for GStreamer buffers)
       if (int rc = launch_memo_stream(c, f.src, ss, f.dst, ds, 4 * w, h, st)) return rc;
     } else if (al) {
       const int PX = c->memo_px;
       dim3 grid((unsigned)ceil_div(w, 8 * 32 * PX), grid_rows(h));
 #define LAUNCH_PLAIN(P)                                                                                               \
   do {                                                                                                                \
-    if (c->lut_kind == 3) colorlut_memo_apply_kernel<P><<<grid, 256, 0, st>>>(c->d_memo, f.src, ss, f.dst, ds, w, h);  \
-    else colorlut_memo1d_apply_kernel<P><<<grid, 256, 0, st>>>(c->d_memo1d, f.src, ss, f.dst, ds, w, h);              \
+    if (c->lut_kind == 3) CU(c, launch_k(c->pdl_now, colorlut_memo_apply_kernel<P>, grid, dim3(256), 0, st, c->d_memo, f.src, ss, f.dst, ds, w, h));  \
+    else CU(c, launch_k(c->pdl_now, colorlut_memo1d_apply_kernel<P>, grid, dim3(256), 0, st, c->d_memo1d, f.src, ss, f.dst, ds, w, h));              \
   } while (0)
       if (PX == 16) LAUNCH_PLAIN(16); else if (PX == 8) LAUNCH_PLAIN(8); else LAUNCH_PLAIN(4);
 #undef LAUNCH_PLAIN
@@ -224,7 +303,7 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
   const bool al8 = aligned(f.src, f.sstride, 8) && aligned(f.dst, f.dstride, 8);
   if (((uintptr_t)f.src | (uintptr_t)f.dst) & 1u && fmt != B200VFX_FORMAT_RGBA)
     return fail(c, B200VFX_ERR_INVALID, "RGBA64 planes must be 2-byte aligned (as_slice_of::<u16>, imp.rs:323-324)");
-#define LAUNCH_DIRECT(F, A) colorlut_direct_kernel<F, A><<<grid, 256, 0, st>>>(p, f.src, f.sstride, f.dst, f.dstride, f.width, f.height)
+#define LAUNCH_DIRECT(F, A) CU(c, launch_k(c->pdl_now, colorlut_direct_kernel<F, A>, grid, dim3(256), 0, st, p, f.src, f.sstride, f.dst, f.dstride, f.width, f.height))
   switch (fmt) {
     case B200VFX_FORMAT_RGBA: if (al4) LAUNCH_DIRECT(0, true); else LAUNCH_DIRECT(0, false); break;
     case B200VFX_FORMAT_RGBA64_LE: if (al8) LAUNCH_DIRECT(1, true); else LAUNCH_DIRECT(1, false); break;
@@ -247,6 +326,7 @@ void launch_hsvfilter_t(const HsvFilterSettings &s, uint8_t *data, long stride, 
 int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings &s, uint8_t *data, long stride,
                      int w, int h, cudaStream_t st) {
   if (w == 0 || h == 0) return 0;
+  pdl_admit(false, st, Span{0, 0}, Span{0, 0});  // plain launch: waits for, and is waited on by, everything around it
   if (fi.bpp == 3) { if (fi.bgr) launch_hsvfilter_t<3, 0, true>(s, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<3, 0, false>(s, data, stride, w, h, st, c->sm_count); }
   else if (fi.coff == 0) { if (fi.bgr) launch_hsvfilter_t<4, 0, true>(s, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<4, 0, false>(s, data, stride, w, h, st, c->sm_count); }
   else { if (fi.bgr) launch_hsvfilter_t<4, 1, true>(s, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<4, 1, false>(s, data, stride, w, h, st, c->sm_count); }
@@ -272,6 +352,7 @@ void launch_hsvdetector_t(const FmtInfo &fo, const HsvDetectSettings &s, const F
 int launch_hsvdetector(b200vfx_ctx *c, const FmtInfo &fi, const FmtInfo &fo, const HsvDetectSettings &s,
                        const Frame &f, cudaStream_t st) {
   if (f.width == 0 || f.height == 0) return 0;
+  pdl_admit(false, st, Span{0, 0}, Span{0, 0});
   if (fi.bpp == 3) { if (fi.bgr) launch_hsvdetector_t<3, 0, true>(fo, s, f, st, c->sm_count); else launch_hsvdetector_t<3, 0, false>(fo, s, f, st, c->sm_count); }
   else if (fi.coff == 0) { if (fi.bgr) launch_hsvdetector_t<4, 0, true>(fo, s, f, st, c->sm_count); else launch_hsvdetector_t<4, 0, false>(fo, s, f, st, c->sm_count); }
   else { if (fi.bgr) launch_hsvdetector_t<4, 1, true>(fo, s, f, st, c->sm_count); else launch_hsvdetector_t<4, 1, false>(fo, s, f, st, c->sm_count); }
@@ -362,6 +443,7 @@ int run_staged(b200vfx_ctx *c, const Staged &s, LaunchFn launch) {
   }
   if (need_d2h) CU(c, cudaStreamSynchronize(c->s_d2h));
   else CU(c, cudaStreamSynchronize(c->s_k));
+  pdl_forget(c->s_k);
   return 0;
 }
 
@@ -415,7 +497,7 @@ int b200vfx_ctx_create(b200vfx_ctx **out, int device) {
   c->device = device;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (c->sm_count <= 0) c->sm_count = 148;
-  if (const char *e = getenv("B200VFX_NO_TMA")) c->stream_path = !(e[0] == '1');
+  if (const char *e = getenv("B200VFX_STREAM_PATH")) c->stream_path = atoi(e);
   if (const char *e = getenv("B200VFX_STREAM_CFG")) c->stream_cfg = atoi(e);
   if (const char *e = getenv("B200VFX_STREAM_CTAS")) c->stream_ctas = atoi(e);
   if (const char *e = getenv("B200VFX_STREAM_HINT")) c->stream_hint = atoi(e);
@@ -473,11 +555,12 @@ uint64_t b200vfx_ctx_kernel_launches(const b200vfx_ctx *c) { return c ? c->launc
 int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   if (!c || !name) return fail(c, B200VFX_ERR_INVALID, "null argument");
   const std::string n(name);
-  if (n == "stream_path") c->stream_path = value != 0;
+  if (n == "stream_path") c->stream_path = value;
   else if (n == "stream_cfg") c->stream_cfg = value;
   else if (n == "stream_ctas") c->stream_ctas = value;
   else if (n == "stream_hint") c->stream_hint = value;
   else if (n == "memo_px") c->memo_px = value;
+  else if (n == "pdl") c->pdl = value != 0;
   else return fail(c, B200VFX_ERR_INVALID, "unknown option '%s'", name);
   return 0;
 }
@@ -493,12 +576,13 @@ void b200vfx_host_free(void *p) { if (p) cudaFreeHost(p); }
 int b200vfx_colorlut_clear(b200vfx_ctx *c) {
   if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
   DeviceGuard g(c->device);
-  if (c->d_lut3d) cudaFree(c->d_lut3d);
+  if (c->d_pair) cudaFree(c->d_pair);
   if (c->d_lut1d) cudaFree(c->d_lut1d);
-  if (c->d_axis) cudaFree(c->d_axis);
+  if (c->d_axis8) cudaFree(c->d_axis8);
+  if (c->d_axis16) cudaFree(c->d_axis16);
   if (c->d_memo) cudaFree(c->d_memo);
   if (c->d_memo1d) cudaFree(c->d_memo1d);
-  c->d_lut3d = nullptr; c->d_lut1d = nullptr; c->d_axis = nullptr; c->d_memo = nullptr; c->d_memo1d = nullptr;
+  c->d_pair = nullptr; c->d_lut1d = nullptr; c->d_axis8 = nullptr; c->d_axis16 = nullptr; c->d_memo = nullptr; c->d_memo1d = nullptr;
   c->have_lut = false; c->memo_ready = false; c->lut_kind = 0; c->lut_size = 0;
   return 0;
 }
@@ -522,10 +606,22 @@ int b200vfx_colorlut_set_lut(b200vfx_ctx *c, int kind, int size, const float *va
   b200vfx_colorlut_clear(c);
   const size_t n = kind == 1 ? (size_t)size : (size_t)size * size * size;
   if (kind == 3) {
-    std::vector<float4> h(n);
-    for (size_t i = 0; i < n; i++) h[i] = make_float4(values[3 * i], values[3 * i + 1], values[3 * i + 2], 1.0f);  // parser.rs:253-256
-    CU(c, cudaMalloc(&c->d_lut3d, n * sizeof(float4)));
-    CU(c, cudaMemcpyAsync(c->d_lut3d, h.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
+    // x-pair layout: {lut[x], lut[min(x+1,max)] - lut[x]} per entry; the difference is the same single f32
+    // rounding lerp4's `b - a` performs per pixel (imp.rs:528-535).  The alpha lane (1.0, parser.rs:253-256) is
+    // never consumed (imp.rs:444-448) and is not stored.
+    std::vector<LutPair> h(n);
+    const size_t N = (size_t)size;
+    for (size_t i = 0; i < n; i++) {
+      const size_t x = i % N, i1 = (x + 1 < N) ? i + 1 : i;
+      for (int k = 0; k < 3; k++) {
+        const volatile float a = values[3 * i + k], b = values[3 * i1 + k];
+        const volatile float d = b - a;  // volatile: one IEEE binary32 subtraction, no extended precision / fusion
+        h[i].a[k] = a; h[i].d[k] = d;
+      }
+      h[i].pad[0] = h[i].pad[1] = 0.0f;
+    }
+    CU(c, cudaMalloc(&c->d_pair, n * sizeof(LutPair)));
+    CU(c, cudaMemcpyAsync(c->d_pair, h.data(), n * sizeof(LutPair), cudaMemcpyHostToDevice, st));
     CU(c, cudaStreamSynchronize(st));
   } else {
     std::vector<float> h(3 * n);
@@ -536,10 +632,7 @@ int b200vfx_colorlut_set_lut(b200vfx_ctx *c, int kind, int size, const float *va
   }
   for (int i = 0; i < 3; i++) { c->scale[i] = scale[i]; c->offset[i] = offset[i]; }
   c->lut_kind = kind; c->lut_size = size;
-  CU(c, cudaMalloc(&c->d_axis, 768 * sizeof(float2)));
-  colorlut_axis_table_kernel<<<3, 256, 0, st>>>(c->d_axis, lut_params(c));
-  c->launches++;
-  CU(c, cudaGetLastError());
+  if (int rc = build_axis(c, false, st)) return rc;
   CU(c, cudaStreamSynchronize(st));
   c->have_lut = true;
   return 0;
@@ -668,6 +761,7 @@ int b200vfx_blockhash_sums(b200vfx_ctx *c, int fmt, int width, int height, const
   uint32_t *d_sums = sums;
   const size_t nb = sizeof(uint32_t) * (size_t)hw * hh;
   if (!sums_dev) { CU(c, c->stage_sums.reserve(nb)); d_sums = (uint32_t *)c->stage_sums.p; }
+  pdl_admit(false, st, Span{0, 0}, Span{0, 0});
   CU(c, cudaMemsetAsync(d_sums, 0, nb, st));
   // rows per CTA: aim for >= ~8 CTAs per SM
   int rows_per_cta = bh;

@@ -15,28 +15,32 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) { return __
 __device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v) { __stcs(p, v); }
 __device__ __forceinline__ uint2 ld_stream_u2(const uint2 *p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream_u2(uint2 *p, uint2 v) { __stcs(p, v); }
+// PDL: let the next (independent) frame's kernel start as soon as every CTA of this one has been scheduled
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // --------------------------------------------------------------------------------------------
-// colorlut: per-axis coefficient table for 8-bit input (exact partial evaluation of norm_comp:
-// only 256 inputs exist per channel, so the IEEE division leaves the pixel loop)
+// colorlut table builders (once per LUT): axis tables and, on the host, the x-pair table
 // --------------------------------------------------------------------------------------------
-__global__ void colorlut_axis_table_kernel(float2 *axis, LutParams p) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..767
-  if (i >= 768) return;
-  const int c = i >> 8, v = i & 255;
-  const float size_m1 = __fsub_rn((float)p.size, 1.0f);
-  axis[i] = make_float2(lut_pos((float)v, 255.0f, p.scale[c], p.offset[c], size_m1), 0.0f);
+struct AxisBuildParams { int size, kind, axis_len; float denom; float scale[3], offset[3]; };
+
+__global__ void colorlut_axis_table_kernel(uint4 *axis, AxisBuildParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 3*axis_len-1
+  if (i >= 3 * p.axis_len) return;
+  const int c = i / p.axis_len, v = i - c * p.axis_len;
+  const int stride = (p.kind == 3) ? (c == 0 ? 1 : (c == 1 ? p.size : p.size * p.size)) : 1;
+  axis[i] = axis_entry((float)v, p.denom, p.scale[c], p.offset[c], p.size, stride);
 }
 
 // --------------------------------------------------------------------------------------------
-// colorlut direct evaluation: one pixel per thread.
-// FMT 0 = RGBA (u8), 1 = RGBA64_LE, 2 = RGBA64_BE.   imp.rs:237-397
-// ALIGNED: rows are 4-byte (u8) / 8-byte (u16) aligned -> one vector load/store per pixel.
+// colorlut direct evaluation (RGBA64 always; RGBA when mode = direct): one pixel per thread,
+// rows looped by a persistent-style grid.   imp.rs:237-397
+// FMT 0 = RGBA (u8), 1 = RGBA64_LE, 2 = RGBA64_BE.  ALIGNED: one 32/64-bit access per pixel.
 // --------------------------------------------------------------------------------------------
 template <int FMT, bool ALIGNED>
-__global__ void __launch_bounds__(256) colorlut_direct_kernel(LutParams p, const uint8_t *__restrict__ src,
+__global__ void __launch_bounds__(256) colorlut_direct_kernel(LutDev L, const uint8_t *__restrict__ src,
                                                               long sstride, uint8_t *__restrict__ dst,
                                                               long dstride, int width, int height) {
+  pdl_trigger();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= width) return;
   for (int row = blockIdx.y; row < height; row += gridDim.y) {
@@ -47,8 +51,7 @@ __global__ void __launch_bounds__(256) colorlut_direct_kernel(LutParams p, const
       if (ALIGNED) px = ld_stream_u32(reinterpret_cast<const uint32_t *>(s));
       else px = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
       unsigned o[3];
-      colorlut_eval<255>(p, __ldg(&p.axis[px & 255u]).x, __ldg(&p.axis[256 + ((px >> 8) & 255u)]).x,
-                         __ldg(&p.axis[512 + ((px >> 16) & 255u)]).x, o);
+      colorlut_eval<255>(L, px & 255u, (px >> 8) & 255u, (px >> 16) & 255u, o);
       const uint32_t out = o[0] | (o[1] << 8) | (o[2] << 16) | (px & 0xFF000000u);  // d[3] = s[3]
       if (ALIGNED) st_stream_u32(reinterpret_cast<uint32_t *>(d), out);
       else { d[0] = (uint8_t)out; d[1] = (uint8_t)(out >> 8); d[2] = (uint8_t)(out >> 16); d[3] = (uint8_t)(out >> 24); }
@@ -65,12 +68,8 @@ __global__ void __launch_bounds__(256) colorlut_direct_kernel(LutParams p, const
       }
       uint32_t w0 = px.x, w1 = px.y;
       if (FMT == 2) { w0 = __byte_perm(w0, 0, 0x2301); w1 = __byte_perm(w1, 0, 0x2301); }  // from_be on an LE device
-      const float size_m1 = __fsub_rn((float)p.size, 1.0f);
-      const float fx = lut_pos((float)(w0 & 0xFFFFu), 65535.0f, p.scale[0], p.offset[0], size_m1);
-      const float fy = lut_pos((float)(w0 >> 16), 65535.0f, p.scale[1], p.offset[1], size_m1);
-      const float fz = lut_pos((float)(w1 & 0xFFFFu), 65535.0f, p.scale[2], p.offset[2], size_m1);
       unsigned o[3];
-      colorlut_eval<65535>(p, fx, fy, fz, o);
+      colorlut_eval<65535>(L, w0 & 0xFFFFu, w0 >> 16, w1 & 0xFFFFu, o);
       uint32_t o0 = o[0] | (o[1] << 16), o1 = o[2];
       if (FMT == 2) { o0 = __byte_perm(o0, 0, 0x2301); o1 = __byte_perm(o1, 0, 0x2301); }
       o1 = (o1 & 0xFFFFu) | (px.y & 0xFFFF0000u);  // alpha word copied raw, never byte-swapped (imp.rs:345,394)
@@ -89,20 +88,21 @@ __global__ void __launch_bounds__(256) colorlut_direct_kernel(LutParams p, const
 // them ONCE per start() for all 2^24 colours with the exact direct evaluator above and keeps
 // the 64 MiB answer table resident in B200's 126 MB L2.  Bit-exact by construction.
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) colorlut_memo_build_kernel(LutParams p, uint32_t *__restrict__ memo) {
+__global__ void __launch_bounds__(256) colorlut_memo_build_kernel(LutDev L, uint32_t *__restrict__ memo) {
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;  // idx = r | g<<8 | b<<16
   unsigned o[3];
-  colorlut_eval<255>(p, __ldg(&p.axis[idx & 255u]).x, __ldg(&p.axis[256 + ((idx >> 8) & 255u)]).x,
-                     __ldg(&p.axis[512 + (idx >> 16)]).x, o);
+  colorlut_eval<255>(L, idx & 255u, (idx >> 8) & 255u, idx >> 16, o);
   memo[idx] = o[0] | (o[1] << 8) | (o[2] << 16);
 }
 
 // per-channel 256-entry answer tables for a 1D LUT (768 bytes, lives in shared memory)
-__global__ void colorlut_memo1d_build_kernel(LutParams p, uint8_t *__restrict__ memo1d) {
+__global__ void colorlut_memo1d_build_kernel(LutDev L, uint8_t *__restrict__ memo1d) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 768) return;
   const int c = i >> 8;
-  memo1d[i] = (uint8_t)quantize_round<255>(sample_1d(p.lut1d + c * p.size, p.size - 1, __ldg(&p.axis[i]).x));
+  const uint4 a = __ldg(L.axis + i);  // axis_len == 256 here
+  const float *tab = L.lut1d + c * L.size;
+  memo1d[i] = (uint8_t)quantize_round<255>(lerp_exact(__ldg(tab + a.x), __ldg(tab + a.y), __uint_as_float(a.z)));
 }
 
 // The pixel loop for RGBA with a memo table: out = memo[px & 0xFFFFFF] | (px & 0xFF000000).
@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256) colorlut_memo_apply_kernel(const uint32_t
                                                                   const uint8_t *__restrict__ src, long sstride,
                                                                   uint8_t *__restrict__ dst, long dstride,
                                                                   int width, int height) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x0 = (blockIdx.x * (blockDim.x >> 5) + warp) * (32 * PX) + lane;
   if (x0 - lane >= width) return;
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(256) colorlut_memo1d_apply_kernel(const uint8_
                                                                     const uint8_t *__restrict__ src, long sstride,
                                                                     uint8_t *__restrict__ dst, long dstride,
                                                                     int width, int height) {
+  pdl_trigger();
   __shared__ uint8_t tab[768];
   for (int i = threadIdx.x; i < 768 / 4; i += blockDim.x)
     reinterpret_cast<uint32_t *>(tab)[i] = __ldg(reinterpret_cast<const uint32_t *>(memo1d) + i);

@@ -1,105 +1,14 @@
-// pixel_math.cuh -- exact (bit-for-bit) device restatement of the reference's per-pixel f32
-// arithmetic.  Every operator is a single IEEE-754 binary32 round-to-nearest-even operation,
+// pixel_math.cuh -- exact (bit-for-bit) device restatement of the reference's per-pixel HSV f32
+// arithmetic (colorlut lives in colorlut_math.cuh).  Every operator is a single IEEE-754 binary32 round-to-nearest-even operation,
 // spelled with __f*_rn intrinsics so ptxas can never contract a mul+add into an FMA (the file
 // is also compiled with -fmad=false).  References are paths inside gst-plugins-rs.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "colorlut_math.cuh"
+
 namespace b200vfx {
-
-// ---------------------------------------------------------------------------------------------
-// colorlut  (video/colorlut/src/colorlut/imp.rs:399-543)
-// ---------------------------------------------------------------------------------------------
-struct LutParams {
-  const float4 *lut3d;   // size^3 entries {r,g,b,1.0}, index x + y*size + z*size^2 (parser.rs:43-53)
-  const float *lut1d;    // 3 planes of `size` floats: r[], g[], b[]
-  const float2 *axis;    // u8 only: 3 x 256 x {pos, unused}  (pos = norm_comp(v) * (size-1), exact)
-  int size;
-  int kind;              // 1 | 3
-  float scale[3];
-  float offset[3];
-};
-
-// f32::clamp(0,1): NaN-preserving (imp.rs:473,478)
-__device__ __forceinline__ float clamp01_nanpass(float x) {
-  x = (x < 0.0f) ? 0.0f : x;
-  x = (x > 1.0f) ? 1.0f : x;
-  return x;
-}
-
-// norm_comp / norm_comp_u16 followed by `* (size as f32 - 1.0)`  (imp.rs:471-479, 411, 439-441)
-__device__ __forceinline__ float lut_pos(float value, float denom, float scale, float offset, float size_m1) {
-  float v = __fdiv_rn(value, denom);
-  float n = __fadd_rn(__fmul_rn(v, scale), offset);
-  return __fmul_rn(clamp01_nanpass(n), size_m1);
-}
-
-// a + (b - a) * t, three roundings (imp.rs:528-535)
-__device__ __forceinline__ float lerp_exact(float a, float b, float t) {
-  return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t));
-}
-
-// (v.clamp(0,1) * MAXV).round() as uN  (imp.rs:537-543).
-// round-half-away for q >= 0 equals floor(q + 0.5) evaluated exactly; FADD.RM never rounds up
-// across an integer, so floor(fadd_rd(q, .5)) is exact (q = 0.49999997 -> 0, q = 0.5 -> 1).
-// NaN: fmaxf(NaN,0) = 0 here, the reference keeps NaN and `as u8` maps it to 0 -- same byte.
-template <int MAXV>
-__device__ __forceinline__ unsigned quantize_round(float v) {
-  float c = fminf(fmaxf(v, 0.0f), 1.0f);
-  float q = __fmul_rn(c, (float)MAXV);
-  return __float2uint_rd(__fadd_rd(q, 0.5f));
-}
-
-// x.floor() as usize).min(max)   (imp.rs:485,496-498); pos in [0,size-1] or NaN (-> 0)
-__device__ __forceinline__ int lut_index(float pos, int max_idx) {
-  int i = (int)__float2uint_rd(pos);
-  return min(i, max_idx);
-}
-
-__device__ __forceinline__ float sample_1d(const float *__restrict__ tab, int max_idx, float x) {
-  int x0 = lut_index(x, max_idx);           // imp.rs:482-490
-  int x1 = min(x0 + 1, max_idx);
-  float t = __fsub_rn(x, (float)x0);
-  return lerp_exact(__ldg(tab + x0), __ldg(tab + x1), t);
-}
-
-__device__ __forceinline__ void sample_3d(const float4 *__restrict__ lut, int size, float x, float y,
-                                          float z, float out[3]) {
-  const int m = size - 1;                   // imp.rs:493-526
-  const int x0 = lut_index(x, m), y0 = lut_index(y, m), z0 = lut_index(z, m);
-  const int x1 = min(x0 + 1, m), y1 = min(y0 + 1, m), z1 = min(z0 + 1, m);
-  const float tx = __fsub_rn(x, (float)x0), ty = __fsub_rn(y, (float)y0), tz = __fsub_rn(z, (float)z0);
-  const int r0 = y0 * size, r1 = y1 * size, p0 = z0 * size * size, p1 = z1 * size * size;
-  const float4 c000 = __ldg(lut + x0 + r0 + p0), c100 = __ldg(lut + x1 + r0 + p0);
-  const float4 c010 = __ldg(lut + x0 + r1 + p0), c110 = __ldg(lut + x1 + r1 + p0);
-  const float4 c001 = __ldg(lut + x0 + r0 + p1), c101 = __ldg(lut + x1 + r0 + p1);
-  const float4 c011 = __ldg(lut + x0 + r1 + p1), c111 = __ldg(lut + x1 + r1 + p1);
-#define B200_TRI(L)                                                      \
-  lerp_exact(lerp_exact(lerp_exact(c000.L, c100.L, tx), lerp_exact(c010.L, c110.L, tx), ty), \
-             lerp_exact(lerp_exact(c001.L, c101.L, tx), lerp_exact(c011.L, c111.L, tx), ty), tz)
-  out[0] = B200_TRI(x);
-  out[1] = B200_TRI(y);
-  out[2] = B200_TRI(z);
-#undef B200_TRI
-}
-
-// apply_1d / apply_3d on already-computed LUT positions; returns quantised channels
-template <int MAXV>
-__device__ __forceinline__ void colorlut_eval(const LutParams &p, float x, float y, float z, unsigned out[3]) {
-  if (p.kind == 3) {
-    float o[3];
-    sample_3d(p.lut3d, p.size, x, y, z, o);
-    out[0] = quantize_round<MAXV>(o[0]);
-    out[1] = quantize_round<MAXV>(o[1]);
-    out[2] = quantize_round<MAXV>(o[2]);
-  } else {
-    const int m = p.size - 1;
-    out[0] = quantize_round<MAXV>(sample_1d(p.lut1d, m, x));
-    out[1] = quantize_round<MAXV>(sample_1d(p.lut1d + p.size, m, y));
-    out[2] = quantize_round<MAXV>(sample_1d(p.lut1d + 2 * p.size, m, z));
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // hsvutils  (video/hsv/src/hsvutils.rs:42-198)

@@ -16,6 +16,7 @@ constexpr int stream_smem_bytes() { return TILE * STAGES + 8 * STAGES + 64; }
 template <int TILE, int STAGES, int THREADS, int B, typename PixelOp>
 __device__ __forceinline__ void stream_map_u32(const PixelOp &op, const uint8_t *__restrict__ src, long sstride,
                                                uint8_t *__restrict__ dst, long dstride, int row_bytes, int height) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: frames are independent (see b200vfx.cu launch_k)
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + STAGES * TILE);
   const int tid = threadIdx.x;

@@ -86,7 +86,8 @@ int b200vfx_ctx_set_chunk_rows(b200vfx_ctx *ctx, int rows);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t b200vfx_ctx_kernel_launches(const b200vfx_ctx *ctx);
 /* kernel-variant knobs for A/B measurements (results are identical for every setting):
- * "stream_path" 0|1 (TMA-pipelined streaming kernels), "stream_cfg" 0..7 (tile/stage/thread variant),
+ * "stream_path" -1 auto | 0 | 1 (TMA-pipelined streaming kernels), "stream_cfg" 0..7 (tile/stage/thread variant),
+ * "pdl" 0|1 (overlap consecutive independent frames by programmatic dependent launch; hazards are detected),
  * "stream_ctas" CTAs per SM (0 = occupancy maximum), "stream_hint" 0|1 (L2 evict_last policy on table gathers),
  * "memo_px" 4|8|16 (pixels per thread of the non-TMA kernel). */
 int b200vfx_ctx_set_option(b200vfx_ctx *ctx, const char *name, int value);

@@ -38,12 +38,10 @@ for name, fn in contents.items():
 fr, out = data["noise"]
 t = timeit(lambda i: out[i % RING].copy_(fr[i % RING]))
 print(json.dumps({"variant": "torch_copy_33MB", "us": round(t * 1e6, 2), "frac": round(2 * W * H * 4 / t / 1e9 / PEAK, 4)}), flush=True)
-variants = [("plain", {"stream_path": 0, "memo_px": px}) for px in (4, 8, 16)]
-for cfg in range(8):
-    for hint in (0, 1):
-        variants.append(("tma", {"stream_path": 1, "stream_cfg": cfg, "stream_ctas": 0, "stream_hint": hint}))
-for cfg, ctas in ((0, 2), (1, 3), (1, 4), (2, 4), (2, 6), (5, 2), (5, 3), (7, 8)):
-    variants.append(("tma", {"stream_path": 1, "stream_cfg": cfg, "stream_ctas": ctas, "stream_hint": 0}))
+variants = [("plain", {"stream_path": 0, "memo_px": px, "pdl": pdl}) for px in (4, 8) for pdl in (0, 1)]
+for cfg in (0, 1, 2, 7):
+    for pdl in (0, 1):
+        variants.append(("tma", {"stream_path": 1, "stream_cfg": cfg, "stream_ctas": 0, "stream_hint": 1, "pdl": pdl}))
 for kind, opts in variants:
     for o, val in opts.items(): ctx.set_option(o, val)
     row = {"variant": kind, **opts}

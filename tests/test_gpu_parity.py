@@ -388,3 +388,74 @@ def test_row_tiles_match_full_frame(ctx, world):
             ctx.hsvfilter_process("RGBA", w, r1 - r0, hs[r0:].ctypes.data, 4 * w, hue_shift=33.0)
     assert (tiled == full).all() and (full == orc.colorlut_apply(cube, "RGBA", w, h, frame)).all()
     assert (hs == orc.hsvfilter("RGBA", w, h, frame, hue_shift=33.0)).all()
+
+
+# ---- kernel variants and PDL overlap ---------------------------------------------------------------
+def test_kernel_variants_give_identical_results(ctx):
+    torch = pytest.importorskip("torch")
+    w, h = 1920, 270
+    cube = orc.cube_parse(synth.cube_text_3d(17, "mix"))
+    cube1 = orc.cube_parse(synth.cube_text_1d(256, 2.0))
+    frame = synth.frame_natural("RGBA", w, h, 9)
+    d_src = torch.from_numpy(frame).cuda()
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        for cb in (cube, cube1):
+            set_cube(ctx, cb)
+            exp = orc.colorlut_apply(cb, "RGBA", w, h, frame, threads=NT)
+            for sp in (0, 1):
+                for cfg in range(8):
+                    for pdl in (0, 1):
+                        for px in (4, 8, 16):
+                            if sp == 1 and px != 4:
+                                continue
+                            if sp == 0 and cfg != 0:
+                                continue
+                            for k, v in (("stream_path", sp), ("stream_cfg", cfg), ("pdl", pdl), ("memo_px", px)):
+                                ctx.set_option(k, v)
+                            d_dst = torch.zeros_like(d_src)
+                            for _ in range(3):
+                                ctx.colorlut_process("RGBA", w, h, d_src, 4 * w, d_dst, 4 * w)
+                            torch.cuda.synchronize()
+                            assert (d_dst.cpu().numpy() == exp).all(), (cb.kind, sp, cfg, pdl, px)
+    finally:
+        for k, v in (("stream_path", -1), ("stream_cfg", 0), ("pdl", 1), ("memo_px", 4)):
+            ctx.set_option(k, v)
+
+
+def test_pdl_overlap_respects_dependencies(ctx):
+    """back-to-back launches with PDL: chains (y = f(x); z = g(y)) across two contexts on one stream, the same
+    destination written twice, and in-place work on a buffer that a previous kernel still reads"""
+    torch = pytest.importorskip("torch")
+    w, h = 3840, 1080
+    cube_a = orc.cube_parse(synth.cube_text_3d(9, "mix"))
+    cube_b = orc.cube_parse(synth.cube_text_3d(5, "invert"))
+    st = torch.cuda.current_stream().cuda_stream
+    ctx_b = b200vfx.Context(0)
+    try:
+        ctx.set_stream(st); ctx_b.set_stream(st)
+        set_cube(ctx, cube_a); set_cube(ctx_b, cube_b)
+        frames = [synth.frame_noise("RGBA", w, h, 40 + i) for i in range(3)]
+        exp_a = [orc.colorlut_apply(cube_a, "RGBA", w, h, f, threads=NT) for f in frames]
+        exp_ab = [orc.colorlut_apply(cube_b, "RGBA", w, h, e, threads=NT) for e in exp_a]
+        d = [torch.from_numpy(f).cuda() for f in frames]
+        y = torch.zeros_like(d[0]); z = torch.zeros_like(d[0])
+        dummy_in = [torch.from_numpy(frames[0]).cuda() for _ in range(2)]
+        dummy_out = [torch.zeros_like(d[0]) for _ in range(2)]
+        for rep in range(3):
+            for i in range(3):
+                ctx.colorlut_process("RGBA", w, h, dummy_in[0], 4 * w, dummy_out[0], 4 * w)   # warm: ours, PDL-able
+                ctx.colorlut_process("RGBA", w, h, dummy_in[1], 4 * w, dummy_out[1], 4 * w)
+                ctx.colorlut_process("RGBA", w, h, d[i], 4 * w, y, 4 * w)                     # y = A(x)
+                ctx_b.colorlut_process("RGBA", w, h, y, 4 * w, z, 4 * w)                      # z = B(y): RAW on y
+                ctx.colorlut_process("RGBA", w, h, d[(i + 1) % 3], 4 * w, y, 4 * w)           # WAR on y (ctx_b still reading)
+                torch.cuda.synchronize()
+                assert (z.cpu().numpy() == exp_ab[i]).all()
+                assert (y.cpu().numpy() == exp_a[(i + 1) % 3]).all()
+        # same destination twice in a row: the second frame must win
+        ctx.colorlut_process("RGBA", w, h, d[0], 4 * w, y, 4 * w)
+        ctx.colorlut_process("RGBA", w, h, d[1], 4 * w, y, 4 * w)
+        torch.cuda.synchronize()
+        assert (y.cpu().numpy() == exp_a[1]).all()
+    finally:
+        ctx_b.close()
