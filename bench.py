@@ -38,6 +38,19 @@ METRIC = "colorlut_4k_rgba_frames_per_sec"
 WORKLOAD = "colorlut 33^3 .cube on 3840x2160 RGBA synthetic stream (frames A ramps / B noise alternating)"
 
 
+def host_threads():
+    """threads the CPU arm may use: the cgroup CPU quota of this container (cpu.max), not the host's core count --
+    oversubscribing the quota makes the OpenMP loop slower (measured: 128 threads 10 fps, 32 threads 47 fps)"""
+    n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(round(2 * int(q) / int(per)))))   # 2 SMT threads per quota core measured best
+    except Exception:
+        pass
+    return n
+
+
 def hbm_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -113,7 +126,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     cube = orc.cube_parse(synth.cube_text_3d(33, "mix"))
     frames = [synth.frame_ramps("RGBA", W4K, H4K), synth.frame_noise("RGBA", W4K, H4K, 0x5EED0002)]
     out = np.zeros_like(frames[0])
@@ -140,7 +153,7 @@ def cpu_baseline_sample(np, synth, budget_s=12.0):
     import oracle_binding as orc
     cube = orc.cube_parse(synth.cube_text_3d(33, "mix"))
     frames = [synth.frame_ramps("RGBA", W4K, H4K), synth.frame_noise("RGBA", W4K, H4K, 0x5EED0002)]
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     out = np.zeros_like(frames[0])
     orc.colorlut_apply(cube, "RGBA", W4K, H4K, frames[0], threads=threads, out=out)  # warm-up
     t0 = time.perf_counter()

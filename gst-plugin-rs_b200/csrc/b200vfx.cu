@@ -54,6 +54,7 @@ struct b200vfx_ctx {
   DevBuf stage_in, stage_out, stage_sums;
   int chunk_rows = 0;
   int sm_count = 148;
+  bool zero_copy = false;  // pinned host frames: TMA kernel reads/writes host memory directly (no staging copies)
   bool pdl = true;       // programmatic dependent launch for out-of-place frame kernels
   bool pdl_now = false;  // per launch: false when this call (re)built a table the kernel reads
   int stream_cfg = 0, stream_ctas = 0, stream_hint = 1, memo_px = 4;  // tuning knobs (env overrides, see ctx_create)
@@ -69,11 +70,15 @@ struct b200vfx_ctx {
   float scale[3] = {1, 1, 1}, offset[3] = {0, 0, 0};
   LutPair *d_pair = nullptr;     // x-pair table (3D)
   float *d_lut1d = nullptr;
-  uint4 *d_axis8 = nullptr;      // [3][256]   axis table for RGBA
-  uint4 *d_axis16 = nullptr;     // [3][65536] axis table for RGBA64 (built on the first RGBA64 frame)
+  uint4 *d_axis8 = nullptr;      // [3][256] axis table for RGBA (RGBA64 evaluates its axis entries per pixel)
   uint32_t *d_memo = nullptr;   // 2^24 x u32 (3D)
   uint8_t *d_memo1d = nullptr;  // 768 bytes (1D)
   bool memo_ready = false;
+
+  // hsvfilter / hsvdetector memoisation (settings-keyed; built after 2^24 pixels with unchanged settings)
+  int hsv_memo = -1;  // -1 auto (rent-or-buy), 0 never, 1 build on first use
+  HsvFilterSettings hf_key{}; bool hf_key_valid = false, hf_ready = false; uint64_t hf_px_seen = 0; uint32_t *d_hf_memo = nullptr;
+  HsvDetectSettings hd_key{}; bool hd_key_valid = false, hd_ready = false; uint64_t hd_px_seen = 0; uint32_t *d_hd_bitmap = nullptr;
 
   cudaStream_t stream() const { return use_user_stream ? user_stream : own_stream; }
 };
@@ -102,6 +107,15 @@ bool is_device_ptr(const void *p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// page-locked host memory that the device can address directly (UVA): returns its device alias
+bool pinned_device_ptr(const void *p, void **dev) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+  *dev = a.devicePointer;
+  return true;
 }
 
 struct FmtInfo { int bpp, coff; bool bgr, alpha; };
@@ -134,21 +148,22 @@ inline unsigned grid_rows_persistent(int grid_x, int height, int sm_count) {
   return (unsigned)std::min<long>(std::min<long>(gy, height), 65535);
 }
 
-LutDev lut_dev(const b200vfx_ctx *c, bool wide) {
+LutDev lut_dev(const b200vfx_ctx *c) {
   LutDev L;
   L.pair = c->d_pair; L.lut1d = c->d_lut1d;
-  L.axis = wide ? c->d_axis16 : c->d_axis8;
-  L.axis_len = wide ? 65536 : 256;
+  L.axis = c->d_axis8;
+  L.axis_len = 256;
   L.size = c->lut_size; L.kind = c->lut_kind;
+  for (int i = 0; i < 3; i++) { L.scale[i] = c->scale[i]; L.offset[i] = c->offset[i]; }
   return L;
 }
 
-int build_axis(b200vfx_ctx *c, bool wide, cudaStream_t st) {
-  uint4 **slot = wide ? &c->d_axis16 : &c->d_axis8;
+int build_axis(b200vfx_ctx *c, cudaStream_t st) {
+  uint4 **slot = &c->d_axis8;
   if (*slot) return 0;
   AxisBuildParams p;
-  p.size = c->lut_size; p.kind = c->lut_kind; p.axis_len = wide ? 65536 : 256;
-  p.denom = wide ? 65535.0f : 255.0f;   // norm_comp_u16 / norm_comp (imp.rs:471-479)
+  p.size = c->lut_size; p.kind = c->lut_kind; p.axis_len = 256;
+  p.denom = 255.0f;   // norm_comp (imp.rs:471-474)
   for (int i = 0; i < 3; i++) { p.scale[i] = c->scale[i]; p.offset[i] = c->offset[i]; }
   CU(c, cudaMalloc(slot, (size_t)3 * p.axis_len * sizeof(uint4)));
   colorlut_axis_table_kernel<<<ceil_div(3 * p.axis_len, 256), 256, 0, st>>>(*slot, p);
@@ -252,12 +267,11 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
   const bool wide = fmt != B200VFX_FORMAT_RGBA;
   {
     const size_t rb = (size_t)f.width * (wide ? 8 : 4);
-    const bool tables_ready = (wide ? c->d_axis16 != nullptr : c->d_axis8 != nullptr) &&
-                              (fmt != B200VFX_FORMAT_RGBA || c->mode != 0 || c->memo_ready);
+    const bool tables_ready = c->d_axis8 != nullptr && (fmt != B200VFX_FORMAT_RGBA || c->mode != 0 || c->memo_ready);
     c->pdl_now = pdl_admit(c->pdl && tables_ready, st, span_of(f.src, f.sstride, rb, f.height), span_of(f.dst, f.dstride, rb, f.height));
   }
-  if (int rc = build_axis(c, wide, st)) return rc;
-  const LutDev p = lut_dev(c, wide);
+  if (int rc = build_axis(c, st)) return rc;
+  const LutDev p = lut_dev(c);
   if (fmt == B200VFX_FORMAT_RGBA && c->mode == 0) {
     if (!c->memo_ready) {  // once per LUT: evaluate all 2^24 colours with the exact direct evaluator
       if (c->lut_kind == 3) {
@@ -316,46 +330,106 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
   return 0;
 }
 
+// rent-or-buy: build the answer table once the current settings have processed as many pixels as the table has entries
+bool hsv_memo_decide(int option, bool key_same, uint64_t &px_seen, uint64_t npx, bool &ready) {
+  if (!key_same) { ready = false; px_seen = 0; }
+  px_seen += npx;
+  if (option == 0) return false;
+  return ready || option == 1 || px_seen >= (1ull << 24);
+}
+
 template <int BPP, int COFF, bool BGR>
-void launch_hsvfilter_t(const HsvFilterSettings &s, uint8_t *data, long stride, int w, int h, cudaStream_t st, int sm_count) {
-  dim3 grid((unsigned)ceil_div(w, 256), grid_rows_persistent(ceil_div(w, 256), h, sm_count));
-  if (BPP == 4 && aligned(data, stride, 4)) hsvfilter_kernel<BPP, COFF, BGR, true><<<grid, 256, 0, st>>>(s, data, stride, w, h);
-  else hsvfilter_kernel<BPP, COFF, BGR, false><<<grid, 256, 0, st>>>(s, data, stride, w, h);
+void launch_hsvfilter_t(const HsvFilterSettings &s, const uint32_t *memo, uint8_t *data, long stride, int w, int h,
+                        cudaStream_t st, int sm_count) {
+  const bool al = BPP == 4 && aligned(data, stride, 4);
+  if (memo) {
+    dim3 grid((unsigned)ceil_div(w, 256), grid_rows(h));
+    if (al) hsvfilter_kernel<BPP, COFF, BGR, true, true><<<grid, 256, 0, st>>>(s, memo, data, stride, w, h);
+    else hsvfilter_kernel<BPP, COFF, BGR, false, true><<<grid, 256, 0, st>>>(s, memo, data, stride, w, h);
+  } else {
+    dim3 grid((unsigned)ceil_div(w, 256), grid_rows_persistent(ceil_div(w, 256), h, sm_count));
+    if (al) hsvfilter_kernel<BPP, COFF, BGR, true, false><<<grid, 256, 0, st>>>(s, nullptr, data, stride, w, h);
+    else hsvfilter_kernel<BPP, COFF, BGR, false, false><<<grid, 256, 0, st>>>(s, nullptr, data, stride, w, h);
+  }
 }
 
 int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings &s, uint8_t *data, long stride,
                      int w, int h, cudaStream_t st) {
   if (w == 0 || h == 0) return 0;
   pdl_admit(false, st, Span{0, 0}, Span{0, 0});  // plain launch: waits for, and is waited on by, everything around it
-  if (fi.bpp == 3) { if (fi.bgr) launch_hsvfilter_t<3, 0, true>(s, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<3, 0, false>(s, data, stride, w, h, st, c->sm_count); }
-  else if (fi.coff == 0) { if (fi.bgr) launch_hsvfilter_t<4, 0, true>(s, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<4, 0, false>(s, data, stride, w, h, st, c->sm_count); }
-  else { if (fi.bgr) launch_hsvfilter_t<4, 1, true>(s, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<4, 1, false>(s, data, stride, w, h, st, c->sm_count); }
+  const bool same = c->hf_key_valid && std::memcmp(&c->hf_key, &s, sizeof s) == 0;
+  const bool use_memo = hsv_memo_decide(c->hsv_memo, same, c->hf_px_seen, (uint64_t)w * h, c->hf_ready);
+  c->hf_key = s; c->hf_key_valid = true;
+  const uint32_t *memo = nullptr;
+  if (use_memo) {
+    if (!c->hf_ready) {
+      if (!c->d_hf_memo) CU(c, cudaMalloc(&c->d_hf_memo, sizeof(uint32_t) << 24));
+      hsvfilter_memo_build_kernel<<<(1u << 24) / 256, 256, 0, st>>>(s, c->d_hf_memo);
+      c->launches++;
+      CU(c, cudaGetLastError());
+      c->hf_ready = true;
+    }
+    memo = c->d_hf_memo;
+  }
+  if (fi.bpp == 3) { if (fi.bgr) launch_hsvfilter_t<3, 0, true>(s, memo, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<3, 0, false>(s, memo, data, stride, w, h, st, c->sm_count); }
+  else if (fi.coff == 0) { if (fi.bgr) launch_hsvfilter_t<4, 0, true>(s, memo, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<4, 0, false>(s, memo, data, stride, w, h, st, c->sm_count); }
+  else { if (fi.bgr) launch_hsvfilter_t<4, 1, true>(s, memo, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<4, 1, false>(s, memo, data, stride, w, h, st, c->sm_count); }
   c->launches++;
   CU(c, cudaGetLastError());
   return 0;
 }
 
 template <int IBPP, int ICOFF, bool IBGR>
-void launch_hsvdetector_t(const FmtInfo &fo, const HsvDetectSettings &s, const Frame &f, cudaStream_t st, int sm_count) {
-  dim3 grid((unsigned)ceil_div(f.width, 256), grid_rows_persistent(ceil_div(f.width, 256), f.height, sm_count));
+int launch_hsvdetector_t(b200vfx_ctx *c, const FmtInfo &fo, const HsvDetectSettings &s, const uint32_t *bitmap, bool pdl,
+                         const Frame &f, cudaStream_t st) {
   const bool al = aligned(f.dst, f.dstride, 4) && (IBPP == 3 || aligned(f.src, f.sstride, 4));
-#define L(OC, OB)                                                                                                   \
-  do {                                                                                                              \
-    if (al) hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, true><<<grid, 256, 0, st>>>(s, f.src, f.sstride, f.dst, f.dstride, f.width, f.height); \
-    else hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, false><<<grid, 256, 0, st>>>(s, f.src, f.sstride, f.dst, f.dstride, f.width, f.height);  \
+  const int gx = ceil_div(f.width, 256);
+  dim3 grid((unsigned)gx, bitmap ? grid_rows(f.height) : grid_rows_persistent(gx, f.height, c->sm_count));
+#define L(OC, OB)                                                                                                          \
+  do {                                                                                                                     \
+    if (bitmap) {                                                                                                          \
+      if (al) CU(c, launch_k(pdl, hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, true, true>, grid, dim3(256), 0, st, s, bitmap, f.src, f.sstride, f.dst, f.dstride, f.width, f.height)); \
+      else CU(c, launch_k(pdl, hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, false, true>, grid, dim3(256), 0, st, s, bitmap, f.src, f.sstride, f.dst, f.dstride, f.width, f.height)); \
+    } else {                                                                                                               \
+      if (al) hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, true, false><<<grid, 256, 0, st>>>(s, nullptr, f.src, f.sstride, f.dst, f.dstride, f.width, f.height); \
+      else hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, false, false><<<grid, 256, 0, st>>>(s, nullptr, f.src, f.sstride, f.dst, f.dstride, f.width, f.height);  \
+    }                                                                                                                      \
   } while (0)
   if (fo.coff == 0) { if (fo.bgr) L(0, true); else L(0, false); }
   else { if (fo.bgr) L(1, true); else L(1, false); }
 #undef L
+  return 0;
 }
 
 int launch_hsvdetector(b200vfx_ctx *c, const FmtInfo &fi, const FmtInfo &fo, const HsvDetectSettings &s,
                        const Frame &f, cudaStream_t st) {
   if (f.width == 0 || f.height == 0) return 0;
-  pdl_admit(false, st, Span{0, 0}, Span{0, 0});
-  if (fi.bpp == 3) { if (fi.bgr) launch_hsvdetector_t<3, 0, true>(fo, s, f, st, c->sm_count); else launch_hsvdetector_t<3, 0, false>(fo, s, f, st, c->sm_count); }
-  else if (fi.coff == 0) { if (fi.bgr) launch_hsvdetector_t<4, 0, true>(fo, s, f, st, c->sm_count); else launch_hsvdetector_t<4, 0, false>(fo, s, f, st, c->sm_count); }
-  else { if (fi.bgr) launch_hsvdetector_t<4, 1, true>(fo, s, f, st, c->sm_count); else launch_hsvdetector_t<4, 1, false>(fo, s, f, st, c->sm_count); }
+  const bool same = c->hd_key_valid && std::memcmp(&c->hd_key, &s, sizeof s) == 0;
+  const bool use_memo = hsv_memo_decide(c->hsv_memo, same, c->hd_px_seen, (uint64_t)f.width * f.height, c->hd_ready);
+  c->hd_key = s; c->hd_key_valid = true;
+  const uint32_t *bitmap = nullptr;
+  bool pdl = false;
+  if (use_memo) {
+    const bool was_ready = c->hd_ready;
+    if (!c->hd_ready) {
+      if (!c->d_hd_bitmap) CU(c, cudaMalloc(&c->d_hd_bitmap, (1u << 24) / 8));
+      pdl_admit(false, st, Span{0, 0}, Span{0, 0});
+      hsvdetector_bitmap_build_kernel<<<(1u << 24) / 256, 256, 0, st>>>(s, c->d_hd_bitmap);
+      c->launches++;
+      CU(c, cudaGetLastError());
+      c->hd_ready = true;
+    }
+    bitmap = c->d_hd_bitmap;
+    pdl = pdl_admit(c->pdl && was_ready, st, span_of(f.src, f.sstride, (size_t)f.width * fi.bpp, f.height),
+                    span_of(f.dst, f.dstride, (size_t)f.width * 4, f.height));
+  } else {
+    pdl_admit(false, st, Span{0, 0}, Span{0, 0});
+  }
+  int rc;
+  if (fi.bpp == 3) rc = fi.bgr ? launch_hsvdetector_t<3, 0, true>(c, fo, s, bitmap, pdl, f, st) : launch_hsvdetector_t<3, 0, false>(c, fo, s, bitmap, pdl, f, st);
+  else if (fi.coff == 0) rc = fi.bgr ? launch_hsvdetector_t<4, 0, true>(c, fo, s, bitmap, pdl, f, st) : launch_hsvdetector_t<4, 0, false>(c, fo, s, bitmap, pdl, f, st);
+  else rc = fi.bgr ? launch_hsvdetector_t<4, 1, true>(c, fo, s, bitmap, pdl, f, st) : launch_hsvdetector_t<4, 1, false>(c, fo, s, bitmap, pdl, f, st);
+  if (rc) return rc;
   c->launches++;
   CU(c, cudaGetLastError());
   return 0;
@@ -520,6 +594,8 @@ void b200vfx_ctx_destroy(b200vfx_ctx *c) {
   DeviceGuard g(c->device);
   cudaDeviceSynchronize();
   b200vfx_colorlut_clear(c);
+  if (c->d_hf_memo) cudaFree(c->d_hf_memo);
+  if (c->d_hd_bitmap) cudaFree(c->d_hd_bitmap);
   for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
   c->stage_in.release(); c->stage_out.release(); c->stage_sums.release();
@@ -561,6 +637,8 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "stream_hint") c->stream_hint = value;
   else if (n == "memo_px") c->memo_px = value;
   else if (n == "pdl") c->pdl = value != 0;
+  else if (n == "zero_copy") c->zero_copy = value != 0;
+  else if (n == "hsv_memo") { c->hsv_memo = value; c->hf_ready = c->hd_ready = false; c->hf_px_seen = c->hd_px_seen = 0; }
   else return fail(c, B200VFX_ERR_INVALID, "unknown option '%s'", name);
   return 0;
 }
@@ -579,10 +657,9 @@ int b200vfx_colorlut_clear(b200vfx_ctx *c) {
   if (c->d_pair) cudaFree(c->d_pair);
   if (c->d_lut1d) cudaFree(c->d_lut1d);
   if (c->d_axis8) cudaFree(c->d_axis8);
-  if (c->d_axis16) cudaFree(c->d_axis16);
   if (c->d_memo) cudaFree(c->d_memo);
   if (c->d_memo1d) cudaFree(c->d_memo1d);
-  c->d_pair = nullptr; c->d_lut1d = nullptr; c->d_axis8 = nullptr; c->d_axis16 = nullptr; c->d_memo = nullptr; c->d_memo1d = nullptr;
+  c->d_pair = nullptr; c->d_lut1d = nullptr; c->d_axis8 = nullptr; c->d_memo = nullptr; c->d_memo1d = nullptr;
   c->have_lut = false; c->memo_ready = false; c->lut_kind = 0; c->lut_size = 0;
   return 0;
 }
@@ -632,7 +709,7 @@ int b200vfx_colorlut_set_lut(b200vfx_ctx *c, int kind, int size, const float *va
   }
   for (int i = 0; i < 3; i++) { c->scale[i] = scale[i]; c->offset[i] = offset[i]; }
   c->lut_kind = kind; c->lut_size = size;
-  if (int rc = build_axis(c, false, st)) return rc;
+  if (int rc = build_axis(c, st)) return rc;
   CU(c, cudaStreamSynchronize(st));
   c->have_lut = true;
   return 0;
@@ -663,6 +740,23 @@ int b200vfx_colorlut_process(b200vfx_ctx *c, int fmt, int width, int height, con
   if (int rc = check_frame(c, width, height, src, src_stride, row, dst, dst_stride, row)) return rc;
   if (width == 0 || height == 0) return 0;
   DeviceGuard g(c->device);
+  // zero-copy variant for PINNED host frames: the TMA streaming kernel bulk-loads tiles straight from host memory
+  // over PCIe and bulk-stores the results straight back -- no staging buffers, both PCIe directions busy for the
+  // whole frame, no chunk pipeline to fill and drain.  (option "zero_copy", RGBA memo path only)
+  if (c->zero_copy && fmt == B200VFX_FORMAT_RGBA && c->mode == 0 && (width % 4) == 0 && aligned(src, src_stride, 16) &&
+      aligned(dst, dst_stride, 16)) {
+    void *dsrc = nullptr, *ddst = nullptr;
+    if (pinned_device_ptr(src, &dsrc) && pinned_device_ptr(dst, &ddst)) {
+      const int saved = c->stream_path;
+      c->stream_path = 1;
+      int rc = launch_colorlut(c, fmt, Frame{(const uint8_t *)dsrc, src_stride, (uint8_t *)ddst, dst_stride, width, height}, c->s_k);
+      c->stream_path = saved;
+      if (rc) return rc;
+      CU(c, cudaStreamSynchronize(c->s_k));
+      pdl_forget(c->s_k);
+      return 0;
+    }
+  }
   Staged s{(const uint8_t *)src, src_stride, row, (uint8_t *)dst, dst_stride, row, height, false};
   return run_staged(c, s, [&](const uint8_t *ds, long dss, uint8_t *dd, long dds, int, int rows, cudaStream_t st) {
     return launch_colorlut(c, fmt, Frame{ds, dss, dd, dds, width, rows}, st);

@@ -23,9 +23,10 @@ struct LutDev {
   const LutPair *pair;   // 3D: size^3 x-pair entries
   const float *lut1d;    // 1D: 3 planes of `size` floats r[], g[], b[]
   const uint4 *axis;     // [3][axis_len] {o0, o1, t (bits), 0}
-  int axis_len;          // 256 (RGBA) or 65536 (RGBA64)
+  int axis_len;          // 256 (RGBA); RGBA64 evaluates the axis entry arithmetically (see axis_entry_u16)
   int size;
   int kind;              // 1 | 3
+  float scale[3], offset[3];
 };
 
 // f32::clamp(0,1): NaN-preserving (imp.rs:473,478)
@@ -45,6 +46,30 @@ __device__ __forceinline__ uint4 axis_entry(float value, float denom, float scal
   const int i1 = min(i0 + 1, m);
   const float t = __fsub_rn(pos, (float)i0);
   return make_uint4((uint32_t)(i0 * stride), (uint32_t)(i1 * stride), __float_as_uint(t), 0u);
+}
+
+// (v as f32) / 65535.0 for an integer v in [0, 65535], correctly rounded, in 3 instructions: reciprocal multiply
+// plus one Newton correction with two FMAs (the same scheme the compiler's IEEE division uses, minus its
+// special-case handling).  Verified against true division for all 65536 inputs with exact rational arithmetic
+//  and on the GPU by tests/test_gpu_parity.py::test_colorlut_rgba64_every_channel_value.
+__device__ __forceinline__ float div65535_exact(float v) {
+  const float c = 1.0f / 65535.0f;
+  const float q0 = __fmul_rn(v, c);
+  const float r = __fmaf_rn(-q0, 65535.0f, v);
+  return __fmaf_rn(r, c, q0);
+}
+
+// RGBA64: a 65536-entry axis table would cost one L1 wavefront per lane (neighbouring 16-bit values are 17 apart
+// on a ramp), so the entry is evaluated per pixel with the reference's operator sequence (norm_comp_u16 and
+// sample_* index logic, imp.rs:476-479, 496-503)
+__device__ __forceinline__ uint4 axis_entry_u16(unsigned v, float scale, float offset, int size, int stride) {
+  const float q = div65535_exact((float)v);
+  const float n = clamp01_nanpass(__fadd_rn(__fmul_rn(q, scale), offset));
+  const float pos = __fmul_rn(n, __fsub_rn((float)size, 1.0f));
+  const int m = size - 1;
+  const int i0 = min((int)__float2uint_rd(pos), m);
+  const int i1 = min(i0 + 1, m);
+  return make_uint4((uint32_t)(i0 * stride), (uint32_t)(i1 * stride), __float_as_uint(__fsub_rn(pos, (float)i0)), 0u);
 }
 
 // a + (b - a) * t, three roundings (imp.rs:528-535)
@@ -71,10 +96,18 @@ __device__ __forceinline__ void ldg256(const LutPair *p, float (&v)[8]) {
       : "l"(p));
 }
 
-// apply_1d / apply_3d for one pixel whose channel values are (vr, vg, vb) in [0, axis_len)
+// apply_1d / apply_3d for one pixel whose channel values are (vr, vg, vb); MAXV = 255 (table axis) or 65535 (inline axis)
 template <int MAXV>
 __device__ __forceinline__ void colorlut_eval(const LutDev &L, unsigned vr, unsigned vg, unsigned vb, unsigned out[3]) {
-  const uint4 ax = __ldg(L.axis + vr), ay = __ldg(L.axis + L.axis_len + vg), az = __ldg(L.axis + 2 * L.axis_len + vb);
+  uint4 ax, ay, az;
+  if (MAXV == 255) {
+    ax = __ldg(L.axis + vr); ay = __ldg(L.axis + L.axis_len + vg); az = __ldg(L.axis + 2 * L.axis_len + vb);
+  } else {
+    const int s1 = (L.kind == 3) ? L.size : 1, s2 = (L.kind == 3) ? L.size * L.size : 1;
+    ax = axis_entry_u16(vr, L.scale[0], L.offset[0], L.size, 1);
+    ay = axis_entry_u16(vg, L.scale[1], L.offset[1], L.size, s1);
+    az = axis_entry_u16(vb, L.scale[2], L.offset[2], L.size, s2);
+  }
   const float tx = __uint_as_float(ax.z), ty = __uint_as_float(ay.z), tz = __uint_as_float(az.z);
   if (L.kind == 3) {
     float e00[8], e10[8], e01[8], e11[8];

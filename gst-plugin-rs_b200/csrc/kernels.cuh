@@ -185,39 +185,71 @@ __global__ void colorlut_memo_apply_bytes_kernel(const uint32_t *__restrict__ me
 // BPP 3|4; COFF = byte offset of the first colour byte (1 for xRGB/ARGB/xBGR/ABGR); BGR = byte order.
 // 4-bpp pixels move as one 32-bit word when the rows are 4-byte aligned.
 // --------------------------------------------------------------------------------------------
-template <int BPP, int COFF, bool BGR, bool ALIGNED>
-__global__ void __launch_bounds__(256) hsvfilter_kernel(HsvFilterSettings st, uint8_t *__restrict__ data,
-                                                        long stride, int width, int height) {
+// Memoised variants (MEMO = true): hsvfilter/hsvdetector are pure functions of (settings, 24-bit colour).  Once the
+// same settings have processed 2^24 pixels (as much arithmetic as evaluating every colour once), the element builds
+//   hsvfilter   : u32[2^24]  answer table  memo[r|g<<8|b<<16] = r'|g'<<8|b'<<16   (64 MiB, L2 resident)
+//   hsvdetector : 2^24-bit hit bitmap (2 MiB)
+// with the exact per-pixel evaluator below and the frame kernel becomes a table lookup (bit-exact by construction).
+__global__ void __launch_bounds__(256) hsvfilter_memo_build_kernel(HsvFilterSettings st, uint32_t *__restrict__ memo) {
   __shared__ float d255[256];
   fill_d255(d255);
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned r = idx & 255u, g = (idx >> 8) & 255u, b = idx >> 16;
+  hsvfilter_px(st, d255, r, g, b);
+  memo[idx] = r | (g << 8) | (b << 16);
+}
+
+__global__ void __launch_bounds__(256) hsvdetector_bitmap_build_kernel(HsvDetectSettings st, uint32_t *__restrict__ bitmap) {
+  __shared__ float d255[256];
+  fill_d255(d255);
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;  // 32 consecutive colours per warp -> one bitmap word
+  const bool hit = hsvdetect_px(st, d255, idx & 255u, (idx >> 8) & 255u, idx >> 16);
+  const unsigned word = __ballot_sync(0xFFFFFFFFu, hit);
+  if ((threadIdx.x & 31) == 0) bitmap[idx >> 5] = word;
+}
+
+template <int BPP, int COFF, bool BGR, bool ALIGNED, bool MEMO>
+__global__ void __launch_bounds__(256) hsvfilter_kernel(HsvFilterSettings st, const uint32_t *__restrict__ memo,
+                                                        uint8_t *__restrict__ data, long stride, int width, int height) {
+  __shared__ float d255[256];
+  if (!MEMO) fill_d255(d255);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= width) return;
   for (int row = blockIdx.y; row < height; row += gridDim.y) {
     uint8_t *p = data + (size_t)row * stride + (size_t)x * BPP;
+    uint32_t px = 0;
+    unsigned c0, c1, c2;
     if (BPP == 4 && ALIGNED) {
-      const uint32_t px = *reinterpret_cast<const uint32_t *>(p);
-      unsigned c0 = (px >> (8 * COFF)) & 255u, c1 = (px >> (8 * COFF + 8)) & 255u, c2 = (px >> (8 * COFF + 16)) & 255u;
-      unsigned r = BGR ? c2 : c0, g = c1, b = BGR ? c0 : c2;
+      px = *reinterpret_cast<const uint32_t *>(p);
+      c0 = (px >> (8 * COFF)) & 255u; c1 = (px >> (8 * COFF + 8)) & 255u; c2 = (px >> (8 * COFF + 16)) & 255u;
+    } else {
+      c0 = p[COFF]; c1 = p[COFF + 1]; c2 = p[COFF + 2];
+    }
+    unsigned r = BGR ? c2 : c0, g = c1, b = BGR ? c0 : c2;
+    if (MEMO) {
+      const uint32_t v = __ldg(memo + (r | (g << 8) | (b << 16)));
+      r = v & 255u; g = (v >> 8) & 255u; b = (v >> 16) & 255u;
+    } else {
       hsvfilter_px(st, d255, r, g, b);
-      c0 = BGR ? b : r; c1 = g; c2 = BGR ? r : b;
+    }
+    c0 = BGR ? b : r; c1 = g; c2 = BGR ? r : b;
+    if (BPP == 4 && ALIGNED) {
       const uint32_t keep = COFF ? (px & 0x000000FFu) : (px & 0xFF000000u);
       *reinterpret_cast<uint32_t *>(p) = keep | (c0 << (8 * COFF)) | (c1 << (8 * COFF + 8)) | (c2 << (8 * COFF + 16));
     } else {
-      unsigned c0 = p[COFF], c1 = p[COFF + 1], c2 = p[COFF + 2];
-      unsigned r = BGR ? c2 : c0, g = c1, b = BGR ? c0 : c2;
-      hsvfilter_px(st, d255, r, g, b);
-      p[COFF] = (uint8_t)(BGR ? b : r); p[COFF + 1] = (uint8_t)g; p[COFF + 2] = (uint8_t)(BGR ? r : b);
+      p[COFF] = (uint8_t)c0; p[COFF + 1] = (uint8_t)c1; p[COFF + 2] = (uint8_t)c2;
     }
   }
 }
 
 // IBPP/ICOFF/IBGR describe the input pixel; OCOFF/OBGR the 4-byte output pixel (alpha at 3 if OCOFF==0 else 0)
-template <int IBPP, int ICOFF, bool IBGR, int OCOFF, bool OBGR, bool ALIGNED>
-__global__ void __launch_bounds__(256) hsvdetector_kernel(HsvDetectSettings st, const uint8_t *__restrict__ src,
-                                                          long sstride, uint8_t *__restrict__ dst, long dstride,
-                                                          int width, int height) {
+template <int IBPP, int ICOFF, bool IBGR, int OCOFF, bool OBGR, bool ALIGNED, bool MEMO>
+__global__ void __launch_bounds__(256) hsvdetector_kernel(HsvDetectSettings st, const uint32_t *__restrict__ bitmap,
+                                                          const uint8_t *__restrict__ src, long sstride,
+                                                          uint8_t *__restrict__ dst, long dstride, int width, int height) {
+  if (MEMO) pdl_trigger();
   __shared__ float d255[256];
-  fill_d255(d255);
+  if (!MEMO) fill_d255(d255);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= width) return;
   for (int row = blockIdx.y; row < height; row += gridDim.y) {
@@ -231,7 +263,14 @@ __global__ void __launch_bounds__(256) hsvdetector_kernel(HsvDetectSettings st, 
       c0 = ip[ICOFF]; c1 = ip[ICOFF + 1]; c2 = ip[ICOFF + 2];
     }
     const unsigned r = IBGR ? c2 : c0, g = c1, b = IBGR ? c0 : c2;
-    const unsigned a = hsvdetect_px(st, d255, r, g, b) ? 255u : 0u;
+    bool hit;
+    if (MEMO) {
+      const uint32_t idx = r | (g << 8) | (b << 16);
+      hit = (__ldg(bitmap + (idx >> 5)) >> (idx & 31u)) & 1u;
+    } else {
+      hit = hsvdetect_px(st, d255, r, g, b);
+    }
+    const unsigned a = hit ? 255u : 0u;
     const unsigned o0 = OBGR ? b : r, o1 = g, o2 = OBGR ? r : b;
     const uint32_t out = (o0 << (8 * OCOFF)) | (o1 << (8 * OCOFF + 8)) | (o2 << (8 * OCOFF + 16)) | (OCOFF ? a : (a << 24));
     if (ALIGNED) st_stream_u32(reinterpret_cast<uint32_t *>(op), out);

@@ -89,7 +89,9 @@ uint64_t b200vfx_ctx_kernel_launches(const b200vfx_ctx *ctx);
  * "stream_path" -1 auto | 0 | 1 (TMA-pipelined streaming kernels), "stream_cfg" 0..7 (tile/stage/thread variant),
  * "pdl" 0|1 (overlap consecutive independent frames by programmatic dependent launch; hazards are detected),
  * "stream_ctas" CTAs per SM (0 = occupancy maximum), "stream_hint" 0|1 (L2 evict_last policy on table gathers),
- * "memo_px" 4|8|16 (pixels per thread of the non-TMA kernel). */
+ * "memo_px" 4|8|16 (pixels per thread of the non-TMA kernel),
+ * "hsv_memo" -1 auto | 0 never | 1 at once (settings-keyed answer tables of hsvfilter / hsvdetector; auto builds
+ * the table after the same settings have processed 2^24 pixels). */
 int b200vfx_ctx_set_option(b200vfx_ctx *ctx, const char *name, int value);
 
 /* Page-locked host memory for a GstAllocator handed out in

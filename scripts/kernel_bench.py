@@ -148,6 +148,20 @@ def main():
             print(json.dumps({"kernel": "e2e_colorlut_pinned", "chunk_rows": rows, "ms": round(t * 1e3, 4), "fps": round(1 / t, 1),
                               "pcie_GBps_each_way": round(W * H * 4 / t / 1e9, 2)}), flush=True)
         ctx.set_chunk_rows(0)
+        ref_out = dst.clone()
+        for cfg in (0, 1, 2):
+            for ctas in (1, 2, 0):
+                ctx.set_option("zero_copy", 1); ctx.set_option("stream_cfg", cfg); ctx.set_option("stream_ctas", ctas)
+                dst.zero_()
+                ctx.colorlut_process("RGBA", W, H, src.numpy(), 4 * W, dst.numpy(), 4 * W)
+                same = bool((dst == ref_out).all())
+                t0 = time.perf_counter()
+                for _ in range(12):
+                    ctx.colorlut_process("RGBA", W, H, src.numpy(), 4 * W, dst.numpy(), 4 * W)
+                t = (time.perf_counter() - t0) / 12
+                print(json.dumps({"kernel": "e2e_colorlut_pinned_zero_copy", "stream_cfg": cfg, "ctas_per_sm": ctas, "ms": round(t * 1e3, 4),
+                                  "fps": round(1 / t, 1), "pcie_GBps_each_way": round(W * H * 4 / t / 1e9, 2), "identical": same}), flush=True)
+        ctx.set_option("zero_copy", 0); ctx.set_option("stream_cfg", 0); ctx.set_option("stream_ctas", 0)
         ctx.colorlut_process("RGBA", W, H, pag_src, 4 * W, pag_dst, 4 * W)
         t0 = time.perf_counter()
         for _ in range(6):

@@ -214,13 +214,18 @@ def _orc_kw(kw):
     return {m.get(k, k): v for k, v in kw.items()}
 
 
+@pytest.mark.parametrize("memo", [0, 1])
 @pytest.mark.parametrize("i", range(len(HSVF)))
-def test_hsvfilter_all_colors(ctx, i):
+def test_hsvfilter_all_colors(ctx, i, memo):
     kw = HSVF[i]
     fmt = ["RGBA", "xBGR", "BGRx", "ARGB"][i % 4]
     frame = all_colors_frame(fmt)
     exp = orc.hsvfilter(fmt, 4096, 4096, frame, threads=NT, **_orc_kw(kw))
-    assert (gpu_hsvfilter(ctx, fmt, 4096, 4096, frame, **kw) == exp).all()
+    ctx.set_option("hsv_memo", memo)
+    try:
+        assert (gpu_hsvfilter(ctx, fmt, 4096, 4096, frame, **kw) == exp).all()
+    finally:
+        ctx.set_option("hsv_memo", -1)
 
 
 def test_hsvfilter_default_is_not_identity(ctx):
@@ -230,9 +235,11 @@ def test_hsvfilter_default_is_not_identity(ctx):
     assert int((d[:, :3] != 0).any(axis=1).sum()) == 11093274 and (d[:, 3] == 0).all()
 
 
+@pytest.mark.parametrize("memo", [0, 1])
 @pytest.mark.parametrize("fmt", ["RGBx", "xRGB", "BGRx", "xBGR", "RGBA", "ARGB", "BGRA", "ABGR", "RGB", "BGR"])
-def test_hsvfilter_formats_strides(ctx, fmt):
+def test_hsvfilter_formats_strides(ctx, fmt, memo):
     kw = dict(hue_shift=123.5, saturation_mul=0.9, saturation_off=0.05, value_mul=1.1, value_off=-0.02)
+    ctx.set_option("hsv_memo", memo)
     for (w, h, pad, off) in ((1, 1, 0, 0), (37, 5, 8, 0), (640, 48, 0, 0), (255, 3, 3, 1)):
         bpp = 3 if fmt in ("RGB", "BGR") else 4
         stride = synth.default_stride(fmt, w) + pad
@@ -243,6 +250,7 @@ def test_hsvfilter_formats_strides(ctx, fmt):
         ctx.hsvfilter_process(fmt, w, h, fr.ctypes.data, stride, **kw)
         assert (fr == exp).all()
         assert (raw[:off] == 0xA5).all() and (raw[off + h * stride:] == 0xA5).all()
+    ctx.set_option("hsv_memo", -1)
 
 
 def test_hsvfilter_config1_and_device(ctx):
@@ -276,8 +284,10 @@ HSVD = [dict(), dict(hue_ref=120.0, hue_var=30.0, saturation_ref=0.8, saturation
         dict(hue_ref=359.99, hue_var=0.5, saturation_var=1.0, value_var=1.0), dict(hue_ref=float("nan"))]
 
 
+@pytest.mark.parametrize("memo", [0, 1])
 @pytest.mark.parametrize("i", range(len(HSVD)))
-def test_hsvdetector_all_colors(ctx, i):
+def test_hsvdetector_all_colors(ctx, i, memo):
+    ctx.set_option("hsv_memo", memo)
     kw = HSVD[i]
     ifmt, ofmt = [("RGBx", "RGBA"), ("BGRx", "ARGB"), ("xRGB", "BGRA"), ("xBGR", "ABGR"), ("RGBx", "ABGR")][i]
     frame = all_colors_frame(ifmt.replace("x", "A"))
@@ -288,16 +298,20 @@ def test_hsvdetector_all_colors(ctx, i):
         assert int((got.reshape(-1, 4)[:, 3] == 255).sum()) == 719
     if i == 1:
         assert int((got.reshape(-1, 4)[:, 0] == 255).sum()) == 1415062
+    ctx.set_option("hsv_memo", -1)
 
 
+@pytest.mark.parametrize("memo", [0, 1])
 @pytest.mark.parametrize("ifmt", ["RGBx", "xRGB", "BGRx", "xBGR", "RGB", "BGR"])
 @pytest.mark.parametrize("ofmt", ["RGBA", "ARGB", "BGRA", "ABGR"])
-def test_hsvdetector_format_matrix(ctx, ifmt, ofmt):
+def test_hsvdetector_format_matrix(ctx, ifmt, ofmt, memo):
     kw = dict(hue_ref=200.0, hue_var=90.0, saturation_ref=0.5, saturation_var=0.5, value_ref=0.5, value_var=0.5)
+    ctx.set_option("hsv_memo", memo)
     for (w, h, spad, dpad) in ((1, 1, 0, 0), (37, 5, 8, 12), (1920, 8, 0, 0), (333, 3, 4, 4)):
         src = synth.frame_noise(ifmt, w, h, 0x5EED0003, stride=synth.default_stride(ifmt, w) + spad)
         exp = orc.hsvdetector(ifmt, ofmt, w, h, src, dst_stride=4 * w + dpad, **_orc_dkw(kw))
         assert (gpu_hsvdetector(ctx, ifmt, ofmt, w, h, src, 4 * w + dpad, **kw) == exp).all()
+    ctx.set_option("hsv_memo", -1)
 
 
 def test_hsvdetector_rejects_formats_outside_caps(ctx):
@@ -459,3 +473,39 @@ def test_pdl_overlap_respects_dependencies(ctx):
         assert (y.cpu().numpy() == exp_a[1]).all()
     finally:
         ctx_b.close()
+
+
+def test_hsv_memo_policy_switches_and_tracks_settings(ctx):
+    """auto policy: direct evaluation until the current settings have seen 2^24 pixels, then the memo table; a
+    settings change (properties are mutable in PLAYING) must never serve stale answers"""
+    ctx.set_option("hsv_memo", -1)
+    w, h = 2048, 1024   # 2^21 pixels per frame: the switch happens at the 8th frame
+    frame = synth.frame_noise("RGBA", w, h, 21)
+    det_in = synth.frame_noise("BGRx", w, h, 22)
+    exp = {hs: orc.hsvfilter("RGBA", w, h, frame, hue_shift=hs, threads=NT) for hs in (10.0, 200.0)}
+    dexp = {hr: orc.hsvdetector("BGRx", "RGBA", w, h, det_in, hue_ref=hr, hue_var=40.0, sat_var=1.0, val_var=1.0, threads=NT) for hr in (30.0, 250.0)}
+    n0 = ctx.kernel_launches
+    for hs, hr in ((10.0, 30.0), (200.0, 250.0), (10.0, 30.0)):
+        for i in range(11):
+            assert (gpu_hsvfilter(ctx, "RGBA", w, h, frame, hue_shift=hs) == exp[hs]).all()
+            assert (gpu_hsvdetector(ctx, "BGRx", "RGBA", w, h, det_in, hue_ref=hr, hue_var=40.0, saturation_var=1.0, value_var=1.0) == dexp[hr]).all()
+    # 3 settings epochs x (11 frames + 1 table build) x 2 elements
+    assert ctx.kernel_launches - n0 == 3 * 2 * 12
+
+
+@pytest.mark.parametrize("fmt", ["RGBA64_LE", "RGBA64_BE"])
+def test_colorlut_rgba64_every_channel_value(ctx, fmt):
+    """all 65536 values in every channel: exhaustively validates the 3-instruction exact x/65535 used by the
+    RGBA64 kernel (and the inline index/weight computation) against the oracle's IEEE division"""
+    i = np.arange(65536, dtype=np.uint32)
+    px = np.stack([i, i ^ 0x5555, 65535 - i, (i * 31) & 0xFFFF], axis=-1)
+    dt = "<u2" if fmt.endswith("LE") else ">u2"
+    frame = px.astype(dt).view(np.uint8).reshape(256, 256 * 8)
+    for cube in (orc.cube_parse(synth.cube_text_3d(33, "mix")),
+                 orc.cube_parse(synth.cube_text_3d(7, "mix", domain=((-0.3, 0.1, 0.0), (1.7, 0.8, 3.0)))),
+                 orc.cube_from_values(3, 256, synth.lut_values_3d(256, "mix")) if fmt.endswith("LE") else orc.cube_parse(synth.cube_text_3d(2, "invert")),
+                 orc.cube_parse(synth.cube_text_1d(65536, 1.7)),
+                 orc.cube_parse(synth.cube_text_1d(3, 2.0, domain=((0.25, 0.0, -1.0), (0.75, 2.0, 1.0))))):
+        set_cube(ctx, cube)
+        exp = orc.colorlut_apply(cube, fmt, 256, 256, frame, threads=NT)
+        assert (gpu_colorlut(ctx, fmt, 256, 256, frame) == exp).all(), (cube.kind, cube.size)
