@@ -311,7 +311,9 @@ def main():
         e2e = {"value": e2e_gop * e2e_steps * N / dt, "unit": "frames/s",
                "h2d_bytes_per_step": FRAME_BYTES * e2e_gop, "d2h_bytes_per_step": FRAME_BYTES * e2e_gop,
                "frames_per_step": e2e_gop, "steps": e2e_steps, "ms_per_frame": 1e3 * dt / (e2e_gop * e2e_steps),
-               "host_buffers": "pinned", "checksum": chk}
+               "host_buffers": "pinned", "checksum": chk,
+               "transfer": "zero-copy: the kernel bulk-loads (cp.async.bulk) the frame from pinned host memory over PCIe and "
+                           "bulk-stores the result back; h2d/d2h bytes cross PCIe inside the timed call"}
 
     # ---- optional all-gather reassembly (config 5 style), reported separately ---------------------
     allgather = None

@@ -54,7 +54,9 @@ struct b200vfx_ctx {
   DevBuf stage_in, stage_out, stage_sums;
   int chunk_rows = 0;
   int sm_count = 148;
-  bool zero_copy = false;  // pinned host frames: TMA kernel reads/writes host memory directly (no staging copies)
+  bool zero_copy = true;   // pinned host frames: TMA kernel reads/writes host memory directly (no staging copies)
+  int zc_cfg = 2, zc_ctas = 1, zc_grid = 0;  // stream-kernel variant / CTAs per SM / absolute grid cap for the zero-copy path
+  int stream_grid = 0;     // absolute cap on the persistent grid of the stream kernels (0 = none)
   bool pdl = true;       // programmatic dependent launch for out-of-place frame kernels
   bool pdl_now = false;  // per launch: false when this call (re)built a table the kernel reads
   int stream_cfg = 0, stream_ctas = 0, stream_hint = 1, memo_px = 4;  // tuning knobs (env overrides, see ctx_create)
@@ -242,7 +244,9 @@ int launch_memo_stream_t(b200vfx_ctx *c, const uint8_t *src, long ss, uint8_t *d
   if (per_sm < 1) per_sm = 1;
   if (c->stream_ctas > 0) per_sm = std::min(per_sm, c->stream_ctas);
   const long long ntiles = (long long)ceil_div(row_bytes, TILE) * h;
-  const unsigned grid = (unsigned)std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
+  long long gmax = (long long)c->sm_count * per_sm;
+  if (c->stream_grid > 0) gmax = std::min<long long>(gmax, c->stream_grid);
+  const unsigned grid = (unsigned)std::min<long long>(ntiles, gmax);
   if (c->lut_kind == 3) CU(c, launch_k(c->pdl_now, k3, dim3(grid), dim3(THREADS), smem, st, c->d_memo, c->stream_hint, src, ss, dst, ds, row_bytes, h));
   else CU(c, launch_k(c->pdl_now, k1, dim3(grid), dim3(THREADS), smem, st, c->d_memo1d, src, ss, dst, ds, row_bytes, h));
   return 0;
@@ -638,6 +642,10 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "memo_px") c->memo_px = value;
   else if (n == "pdl") c->pdl = value != 0;
   else if (n == "zero_copy") c->zero_copy = value != 0;
+  else if (n == "zc_cfg") c->zc_cfg = value;
+  else if (n == "zc_ctas") c->zc_ctas = value;
+  else if (n == "zc_grid") c->zc_grid = value;
+  else if (n == "stream_grid") c->stream_grid = value;
   else if (n == "hsv_memo") { c->hsv_memo = value; c->hf_ready = c->hd_ready = false; c->hf_px_seen = c->hd_px_seen = 0; }
   else return fail(c, B200VFX_ERR_INVALID, "unknown option '%s'", name);
   return 0;
@@ -747,10 +755,11 @@ int b200vfx_colorlut_process(b200vfx_ctx *c, int fmt, int width, int height, con
       aligned(dst, dst_stride, 16)) {
     void *dsrc = nullptr, *ddst = nullptr;
     if (pinned_device_ptr(src, &dsrc) && pinned_device_ptr(dst, &ddst)) {
-      const int saved = c->stream_path;
-      c->stream_path = 1;
+      // PCIe needs far fewer bytes in flight than HBM: a small grid of small tiles measured best (profiles/)
+      const int saved_path = c->stream_path, saved_cfg = c->stream_cfg, saved_ctas = c->stream_ctas, saved_grid = c->stream_grid;
+      c->stream_path = 1; c->stream_cfg = c->zc_cfg; c->stream_ctas = c->zc_ctas; c->stream_grid = c->zc_grid;
       int rc = launch_colorlut(c, fmt, Frame{(const uint8_t *)dsrc, src_stride, (uint8_t *)ddst, dst_stride, width, height}, c->s_k);
-      c->stream_path = saved;
+      c->stream_path = saved_path; c->stream_cfg = saved_cfg; c->stream_ctas = saved_ctas; c->stream_grid = saved_grid;
       if (rc) return rc;
       CU(c, cudaStreamSynchronize(c->s_k));
       pdl_forget(c->s_k);

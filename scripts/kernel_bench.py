@@ -105,23 +105,27 @@ def main():
                 report("colorlut3d_direct_%s" % fmt.lower(), t, 2 * W * H * 8, lut=33, content=cname, frame="3840x2160")
                 del frames, outs
     if want("hsv"):
-        for (w, h, tag) in ((640, 480, "640x480"), (3840, 2160, "3840x2160")):
-            for cname in ("ramps", "noise"):
-                fr = [torch.from_numpy(synth.frame_ramps("RGBA", w, h) if cname == "ramps" else synth.frame_noise("RGBA", w, h, 0x5EED0001 + i)).cuda() for i in range(RING)]
-                t = timeit(lambda i: ctx.hsvfilter_process("RGBA", w, h, fr[i % RING], 4 * w, hue_shift=90.0), args.iters)
-                report("hsvfilter_rgba", t, 2 * w * h * 4, content=cname, frame=tag)
-        w, h = 1920, 1080
         kw = dict(hue_ref=120.0, hue_var=30.0, saturation_ref=0.8, saturation_var=0.2, value_ref=0.8, value_var=0.2)
-        for cname in ("ramps", "noise"):
-            fr = [torch.from_numpy(synth.frame_ramps("BGRx", w, h) if cname == "ramps" else synth.frame_noise("BGRx", w, h, 0x5EED0003 + i)).cuda() for i in range(RING)]
-            out = [torch.empty_like(f) for f in fr]
-            t = timeit(lambda i: ctx.hsvdetector_process("BGRx", "RGBA", w, h, fr[i % RING], 4 * w, out[i % RING], 4 * w, **kw), args.iters)
-            report("hsvdetector_bgrx_rgba", t, 2 * w * h * 4, content=cname, frame="1920x1080")
-        for (w, h) in ((1920, 1080), (3840, 2160)):
-            fr = [torch.from_numpy(synth.frame_noise("RGB", w, h, 9 + i)).cuda() for i in range(4)]
-            out = [torch.empty((h, 4 * w), dtype=torch.uint8, device="cuda") for _ in range(4)]
-            t = timeit(lambda i: ctx.hsvdetector_process("RGB", "ARGB", w, h, fr[i % 4], 3 * w, out[i % 4], 4 * w, **kw), max(args.iters // 3, 5))
-            report("hsvdetector_rgb_argb", t, w * h * 7, content="noise", frame="%dx%d" % (w, h))
+        for memo in (0, 1):
+            ctx.set_option("hsv_memo", memo)
+            tag_m = "memo" if memo else "direct"
+            for (w, h, tag) in ((640, 480, "640x480"), (3840, 2160, "3840x2160")):
+                for cname in ("ramps", "noise"):
+                    fr = [torch.from_numpy(synth.frame_ramps("RGBA", w, h) if cname == "ramps" else synth.frame_noise("RGBA", w, h, 0x5EED0001 + i)).cuda() for i in range(RING)]
+                    t = timeit(lambda i: ctx.hsvfilter_process("RGBA", w, h, fr[i % RING], 4 * w, hue_shift=90.0), args.iters)
+                    report("hsvfilter_rgba_" + tag_m, t, 2 * w * h * 4, content=cname, frame=tag)
+            w, h = 1920, 1080
+            for cname in ("ramps", "noise"):
+                fr = [torch.from_numpy(synth.frame_ramps("BGRx", w, h) if cname == "ramps" else synth.frame_noise("BGRx", w, h, 0x5EED0003 + i)).cuda() for i in range(RING)]
+                out = [torch.empty_like(f) for f in fr]
+                t = timeit(lambda i: ctx.hsvdetector_process("BGRx", "RGBA", w, h, fr[i % RING], 4 * w, out[i % RING], 4 * w, **kw), args.iters)
+                report("hsvdetector_bgrx_rgba_" + tag_m, t, 2 * w * h * 4, content=cname, frame="1920x1080")
+            for (w, h) in ((1920, 1080), (3840, 2160)):
+                fr = [torch.from_numpy(synth.frame_noise("RGB", w, h, 9 + i)).cuda() for i in range(4)]
+                out = [torch.empty((h, 4 * w), dtype=torch.uint8, device="cuda") for _ in range(4)]
+                t = timeit(lambda i: ctx.hsvdetector_process("RGB", "ARGB", w, h, fr[i % 4], 3 * w, out[i % 4], 4 * w, **kw), max(args.iters // 3, 5))
+                report("hsvdetector_rgb_argb_" + tag_m, t, w * h * 7, content="noise", frame="%dx%d" % (w, h))
+        ctx.set_option("hsv_memo", -1)
     if want("videofx"):
         frames, _ = ring_of(contents["noise"])
         sums = torch.zeros(64, dtype=torch.int32, device="cuda")
@@ -137,7 +141,8 @@ def main():
         dst = torch.empty_like(src).pin_memory()
         pag_src = contents["noise"](1)
         pag_dst = np.empty_like(pag_src)
-        for rows in (0, 34, 68, 136, 270, 540, 2160):
+        ctx.set_option("zero_copy", 0)   # first the staged (copy-engine) pipeline, chunk size swept
+        for rows in (0, 136, 270, 540, 2160):
             ctx.set_chunk_rows(rows)
             ctx.colorlut_process("RGBA", W, H, src.numpy(), 4 * W, dst.numpy(), 4 * W)
             t0 = time.perf_counter()
@@ -148,10 +153,14 @@ def main():
             print(json.dumps({"kernel": "e2e_colorlut_pinned", "chunk_rows": rows, "ms": round(t * 1e3, 4), "fps": round(1 / t, 1),
                               "pcie_GBps_each_way": round(W * H * 4 / t / 1e9, 2)}), flush=True)
         ctx.set_chunk_rows(0)
+        ctx.set_option("zero_copy", 0)
+        ctx.set_chunk_rows(540)
+        ctx.colorlut_process("RGBA", W, H, src.numpy(), 4 * W, dst.numpy(), 4 * W)
+        ctx.set_chunk_rows(0)
         ref_out = dst.clone()
-        for cfg in (0, 1, 2):
-            for ctas in (1, 2, 0):
-                ctx.set_option("zero_copy", 1); ctx.set_option("stream_cfg", cfg); ctx.set_option("stream_ctas", ctas)
+        for cfg, ctas, grid in ((2, 1, 0), (2, 1, 64), (2, 1, 32), (2, 1, 16), (2, 2, 0), (7, 1, 0), (7, 2, 0), (7, 1, 64), (4, 1, 0), (4, 2, 0),
+                                (1, 1, 0), (1, 1, 64), (0, 1, 0), (0, 1, 32)):
+                ctx.set_option("zero_copy", 1); ctx.set_option("zc_cfg", cfg); ctx.set_option("zc_ctas", ctas); ctx.set_option("zc_grid", grid)
                 dst.zero_()
                 ctx.colorlut_process("RGBA", W, H, src.numpy(), 4 * W, dst.numpy(), 4 * W)
                 same = bool((dst == ref_out).all())
@@ -159,7 +168,7 @@ def main():
                 for _ in range(12):
                     ctx.colorlut_process("RGBA", W, H, src.numpy(), 4 * W, dst.numpy(), 4 * W)
                 t = (time.perf_counter() - t0) / 12
-                print(json.dumps({"kernel": "e2e_colorlut_pinned_zero_copy", "stream_cfg": cfg, "ctas_per_sm": ctas, "ms": round(t * 1e3, 4),
+                print(json.dumps({"kernel": "e2e_colorlut_pinned_zero_copy", "stream_cfg": cfg, "ctas_per_sm": ctas, "grid_cap": grid, "ms": round(t * 1e3, 4),
                                   "fps": round(1 / t, 1), "pcie_GBps_each_way": round(W * H * 4 / t / 1e9, 2), "identical": same}), flush=True)
         ctx.set_option("zero_copy", 0); ctx.set_option("stream_cfg", 0); ctx.set_option("stream_ctas", 0)
         ctx.colorlut_process("RGBA", W, H, pag_src, 4 * W, pag_dst, 4 * W)
