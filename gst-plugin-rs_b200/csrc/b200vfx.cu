@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -54,8 +55,9 @@ struct b200vfx_ctx {
   DevBuf stage_in, stage_out, stage_sums;
   int chunk_rows = 0;
   int sm_count = 148;
-  bool zero_copy = true;   // pinned host frames: TMA kernel reads/writes host memory directly (no staging copies)
-  int zc_cfg = 2, zc_ctas = 1, zc_grid = 0;  // stream-kernel variant / CTAs per SM / absolute grid cap for the zero-copy path
+  int zero_copy = 2;       // pinned host frames: TMA kernel reads/writes host memory directly; 0 never, 1 always, 2 auto-probe
+  int zc_calls = 0; double zc_best_ms[2] = {1e30, 1e30};   // auto-probe state: [0] zero-copy, [1] staged
+  int zc_cfg = 2, zc_ctas = 1, zc_grid = 64;  // stream-kernel variant / CTAs per SM / absolute grid cap for the zero-copy path
   int stream_grid = 0;     // absolute cap on the persistent grid of the stream kernels (0 = none)
   bool pdl = true;       // programmatic dependent launch for out-of-place frame kernels
   bool pdl_now = false;  // per launch: false when this call (re)built a table the kernel reads
@@ -156,7 +158,11 @@ LutDev lut_dev(const b200vfx_ctx *c) {
   L.axis = c->d_axis8;
   L.axis_len = 256;
   L.size = c->lut_size; L.kind = c->lut_kind;
-  for (int i = 0; i < 3; i++) { L.scale[i] = c->scale[i]; L.offset[i] = c->offset[i]; }
+  L.ident_domain = 1;
+  for (int i = 0; i < 3; i++) {
+    L.scale[i] = c->scale[i]; L.offset[i] = c->offset[i];
+    if (!(c->scale[i] == 1.0f && c->offset[i] == 0.0f)) L.ident_domain = 0;   // -0.0 == 0.0: the default domain yields offset -0.0
+  }
   return L;
 }
 
@@ -360,21 +366,39 @@ void launch_hsvfilter_t(const HsvFilterSettings &s, const uint32_t *memo, uint8_
 int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings &s, uint8_t *data, long stride,
                      int w, int h, cudaStream_t st) {
   if (w == 0 || h == 0) return 0;
-  pdl_admit(false, st, Span{0, 0}, Span{0, 0});  // plain launch: waits for, and is waited on by, everything around it
   const bool same = c->hf_key_valid && std::memcmp(&c->hf_key, &s, sizeof s) == 0;
   const bool use_memo = hsv_memo_decide(c->hsv_memo, same, c->hf_px_seen, (uint64_t)w * h, c->hf_ready);
   c->hf_key = s; c->hf_key_valid = true;
   const uint32_t *memo = nullptr;
+  bool built_now = false;
   if (use_memo) {
     if (!c->hf_ready) {
       if (!c->d_hf_memo) CU(c, cudaMalloc(&c->d_hf_memo, sizeof(uint32_t) << 24));
+      pdl_admit(false, st, Span{0, 0}, Span{0, 0});  // plain launch
       hsvfilter_memo_build_kernel<<<(1u << 24) / 256, 256, 0, st>>>(s, c->d_hf_memo);
       c->launches++;
       CU(c, cudaGetLastError());
       c->hf_ready = true;
+      built_now = true;
     }
     memo = c->d_hf_memo;
   }
+  if (memo && fi.bpp == 4 && aligned(data, stride, 4)) {  // table-lookup map kernel, PDL-overlapped when frames are disjoint
+    int ww = w, hh = h;
+    long ss = stride;
+    if (ss == 4L * w && (long long)w * h < (1LL << 28)) { ww = w * h; hh = 1; }
+    const Span sp = span_of(data, stride, (size_t)w * 4, h);
+    const bool pdl = pdl_admit(c->pdl && !built_now, st, sp, sp);
+    dim3 grid((unsigned)ceil_div(ww, 8 * 32 * 4), grid_rows(hh));
+#define LM(CO, BG) CU(c, launch_k(pdl, map_u32_kernel<HsvFilterMemoOp<CO, BG>, 4>, grid, dim3(256), 0, st, HsvFilterMemoOp<CO, BG>{memo}, (const uint8_t *)data, ss, data, ss, ww, hh))
+    if (fi.coff == 0) { if (fi.bgr) LM(0, true); else LM(0, false); }
+    else { if (fi.bgr) LM(1, true); else LM(1, false); }
+#undef LM
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return 0;
+  }
+  pdl_admit(false, st, Span{0, 0}, Span{0, 0});  // plain launch: waits for, and is waited on by, everything around it
   if (fi.bpp == 3) { if (fi.bgr) launch_hsvfilter_t<3, 0, true>(s, memo, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<3, 0, false>(s, memo, data, stride, w, h, st, c->sm_count); }
   else if (fi.coff == 0) { if (fi.bgr) launch_hsvfilter_t<4, 0, true>(s, memo, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<4, 0, false>(s, memo, data, stride, w, h, st, c->sm_count); }
   else { if (fi.bgr) launch_hsvfilter_t<4, 1, true>(s, memo, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<4, 1, false>(s, memo, data, stride, w, h, st, c->sm_count); }
@@ -414,7 +438,7 @@ int launch_hsvdetector(b200vfx_ctx *c, const FmtInfo &fi, const FmtInfo &fo, con
   const uint32_t *bitmap = nullptr;
   bool pdl = false;
   if (use_memo) {
-    const bool was_ready = c->hd_ready;
+    bool built_now = false;
     if (!c->hd_ready) {
       if (!c->d_hd_bitmap) CU(c, cudaMalloc(&c->d_hd_bitmap, (1u << 24) / 8));
       pdl_admit(false, st, Span{0, 0}, Span{0, 0});
@@ -422,10 +446,25 @@ int launch_hsvdetector(b200vfx_ctx *c, const FmtInfo &fi, const FmtInfo &fo, con
       c->launches++;
       CU(c, cudaGetLastError());
       c->hd_ready = true;
+      built_now = true;
     }
     bitmap = c->d_hd_bitmap;
-    pdl = pdl_admit(c->pdl && was_ready, st, span_of(f.src, f.sstride, (size_t)f.width * fi.bpp, f.height),
+    pdl = pdl_admit(c->pdl && !built_now, st, span_of(f.src, f.sstride, (size_t)f.width * fi.bpp, f.height),
                     span_of(f.dst, f.dstride, (size_t)f.width * 4, f.height));
+    if (fi.bpp == 4 && aligned(f.src, f.sstride, 4) && aligned(f.dst, f.dstride, 4)) {  // table-lookup map kernel
+      int ww = f.width, hh = f.height;
+      if (f.sstride == 4L * ww && f.dstride == 4L * ww && (long long)ww * hh < (1LL << 28)) { ww = ww * hh; hh = 1; }
+      dim3 grid((unsigned)ceil_div(ww, 8 * 32 * 4), grid_rows(hh));
+#define LD(IC, IB, OC, OB) CU(c, launch_k(pdl, map_u32_kernel<HsvDetectBitmapOp<IC, IB, OC, OB>, 4>, grid, dim3(256), 0, st, HsvDetectBitmapOp<IC, IB, OC, OB>{bitmap}, f.src, f.sstride, f.dst, f.dstride, ww, hh))
+#define LD2(IC, IB) do { if (fo.coff == 0) { if (fo.bgr) LD(IC, IB, 0, true); else LD(IC, IB, 0, false); } else { if (fo.bgr) LD(IC, IB, 1, true); else LD(IC, IB, 1, false); } } while (0)
+      if (fi.coff == 0) { if (fi.bgr) LD2(0, true); else LD2(0, false); }
+      else { if (fi.bgr) LD2(1, true); else LD2(1, false); }
+#undef LD2
+#undef LD
+      c->launches++;
+      CU(c, cudaGetLastError());
+      return 0;
+    }
   } else {
     pdl_admit(false, st, Span{0, 0}, Span{0, 0});
   }
@@ -641,7 +680,7 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "stream_hint") c->stream_hint = value;
   else if (n == "memo_px") c->memo_px = value;
   else if (n == "pdl") c->pdl = value != 0;
-  else if (n == "zero_copy") c->zero_copy = value != 0;
+  else if (n == "zero_copy") { c->zero_copy = value; c->zc_calls = 0; c->zc_best_ms[0] = c->zc_best_ms[1] = 1e30; }
   else if (n == "zc_cfg") c->zc_cfg = value;
   else if (n == "zc_ctas") c->zc_ctas = value;
   else if (n == "zc_grid") c->zc_grid = value;
@@ -748,28 +787,43 @@ int b200vfx_colorlut_process(b200vfx_ctx *c, int fmt, int width, int height, con
   if (int rc = check_frame(c, width, height, src, src_stride, row, dst, dst_stride, row)) return rc;
   if (width == 0 || height == 0) return 0;
   DeviceGuard g(c->device);
-  // zero-copy variant for PINNED host frames: the TMA streaming kernel bulk-loads tiles straight from host memory
+  // Zero-copy variant for PINNED host frames: the TMA streaming kernel bulk-loads tiles straight from host memory
   // over PCIe and bulk-stores the results straight back -- no staging buffers, both PCIe directions busy for the
-  // whole frame, no chunk pipeline to fill and drain.  (option "zero_copy", RGBA memo path only)
-  if (c->zero_copy && fmt == B200VFX_FORMAT_RGBA && c->mode == 0 && (width % 4) == 0 && aligned(src, src_stride, 16) &&
-      aligned(dst, dst_stride, 16)) {
-    void *dsrc = nullptr, *ddst = nullptr;
-    if (pinned_device_ptr(src, &dsrc) && pinned_device_ptr(dst, &ddst)) {
-      // PCIe needs far fewer bytes in flight than HBM: a small grid of small tiles measured best (profiles/)
-      const int saved_path = c->stream_path, saved_cfg = c->stream_cfg, saved_ctas = c->stream_ctas, saved_grid = c->stream_grid;
-      c->stream_path = 1; c->stream_cfg = c->zc_cfg; c->stream_ctas = c->zc_ctas; c->stream_grid = c->zc_grid;
-      int rc = launch_colorlut(c, fmt, Frame{(const uint8_t *)dsrc, src_stride, (uint8_t *)ddst, dst_stride, width, height}, c->s_k);
-      c->stream_path = saved_path; c->stream_cfg = saved_cfg; c->stream_ctas = saved_ctas; c->stream_grid = saved_grid;
-      if (rc) return rc;
-      CU(c, cudaStreamSynchronize(c->s_k));
-      pdl_forget(c->s_k);
-      return 0;
-    }
+  // whole frame, no chunk pipeline to fill and drain (RGBA memo path).  Option "zero_copy": 0 never, 1 always,
+  // 2 auto (default): the first eligible calls alternate between this kernel and the staged copy-engine pipeline,
+  // timed with the host clock (both are synchronous), and the faster one is kept -- how well kernel-issued bulk
+  // reads of host memory perform depends on the host's PCIe/IOMMU set-up (profiles/r01_e2e.md).
+  void *dsrc = nullptr, *ddst = nullptr;
+  const bool eligible = c->zero_copy != 0 && fmt == B200VFX_FORMAT_RGBA && c->mode == 0 && (width % 4) == 0 &&
+                        aligned(src, src_stride, 16) && aligned(dst, dst_stride, 16) && pinned_device_ptr(src, &dsrc) &&
+                        pinned_device_ptr(dst, &ddst);
+  const bool probing = eligible && c->zero_copy == 2 && c->zc_calls < 6;
+  const bool use_zc = eligible && (c->zero_copy == 1 || (probing ? (c->zc_calls % 2 == 0) : (c->zc_best_ms[0] <= c->zc_best_ms[1])));
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto probe_done = [&](int which) {
+    if (!probing) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    if (c->zc_calls >= 2) c->zc_best_ms[which] = std::min(c->zc_best_ms[which], ms);   // first call of each kind is a warm-up
+    c->zc_calls++;
+  };
+  if (use_zc) {
+    // PCIe needs far fewer bytes in flight than HBM: a small grid of small tiles measured best (profiles/)
+    const int saved_path = c->stream_path, saved_cfg = c->stream_cfg, saved_ctas = c->stream_ctas, saved_grid = c->stream_grid;
+    c->stream_path = 1; c->stream_cfg = c->zc_cfg; c->stream_ctas = c->zc_ctas; c->stream_grid = c->zc_grid;
+    int rc = launch_colorlut(c, fmt, Frame{(const uint8_t *)dsrc, src_stride, (uint8_t *)ddst, dst_stride, width, height}, c->s_k);
+    c->stream_path = saved_path; c->stream_cfg = saved_cfg; c->stream_ctas = saved_ctas; c->stream_grid = saved_grid;
+    if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->s_k));
+    pdl_forget(c->s_k);
+    probe_done(0);
+    return 0;
   }
   Staged s{(const uint8_t *)src, src_stride, row, (uint8_t *)dst, dst_stride, row, height, false};
-  return run_staged(c, s, [&](const uint8_t *ds, long dss, uint8_t *dd, long dds, int, int rows, cudaStream_t st) {
+  const int rc = run_staged(c, s, [&](const uint8_t *ds, long dss, uint8_t *dd, long dds, int, int rows, cudaStream_t st) {
     return launch_colorlut(c, fmt, Frame{ds, dss, dd, dds, width, rows}, st);
   });
+  if (rc == 0) probe_done(1);
+  return rc;
 }
 
 // ---- hsvfilter / hsvdetector ------------------------------------------------------------------

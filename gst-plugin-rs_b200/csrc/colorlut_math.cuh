@@ -26,6 +26,7 @@ struct LutDev {
   int axis_len;          // 256 (RGBA); RGBA64 evaluates the axis entry arithmetically (see axis_entry_u16)
   int size;
   int kind;              // 1 | 3
+  int ident_domain;      // scale == 1 and offset == +-0 on all channels (no DOMAIN_MIN/MAX in the .cube)
   float scale[3], offset[3];
 };
 
@@ -62,14 +63,27 @@ __device__ __forceinline__ float div65535_exact(float v) {
 // RGBA64: a 65536-entry axis table would cost one L1 wavefront per lane (neighbouring 16-bit values are 17 apart
 // on a ramp), so the entry is evaluated per pixel with the reference's operator sequence (norm_comp_u16 and
 // sample_* index logic, imp.rs:476-479, 496-503)
+//
+// Integer<->float conversions go through the 2^23 "magic number" instead of I2F/F2I (those run on the quarter-rate
+// XU pipe and were the first bottleneck, profiles/r01_ncu_direct64.txt):
+//   u16 -> f32 : bits(0x4B000000 | v) - 2^23                          (exact)
+//   floor(pos) : y = pos +(round-down) 2^23; i0 = bits(y) & 0x7FFFFF; (float)i0 = y - 2^23   (exact, 0 <= pos < 2^23)
+// NaN pos: the reference takes i0 = 0 and t = NaN; here i0 is some in-range index and t = NaN -- every lerp with a
+// NaN weight is NaN, so the quantised output (0) is the same.
+// IDENT: default DOMAIN (scale 1, offset +-0): q*1 + (+-0) == q and clamp(q) == q for q in [0,1] -- both dropped.
+template <bool IDENT>
 __device__ __forceinline__ uint4 axis_entry_u16(unsigned v, float scale, float offset, int size, int stride) {
-  const float q = div65535_exact((float)v);
-  const float n = clamp01_nanpass(__fadd_rn(__fmul_rn(q, scale), offset));
+  const float MAGIC = 8388608.0f;
+  const float vf = __fsub_rn(__uint_as_float(0x4B000000u | v), MAGIC);
+  const float q = div65535_exact(vf);
+  const float n = IDENT ? q : clamp01_nanpass(__fadd_rn(__fmul_rn(q, scale), offset));
   const float pos = __fmul_rn(n, __fsub_rn((float)size, 1.0f));
-  const int m = size - 1;
-  const int i0 = min((int)__float2uint_rd(pos), m);
-  const int i1 = min(i0 + 1, m);
-  return make_uint4((uint32_t)(i0 * stride), (uint32_t)(i1 * stride), __float_as_uint(__fsub_rn(pos, (float)i0)), 0u);
+  const unsigned m = (unsigned)(size - 1);
+  const float y = __fadd_rd(pos, MAGIC);
+  const unsigned i0 = min(__float_as_uint(y) & 0x007FFFFFu, m);
+  const float f0 = __fsub_rn(__uint_as_float(0x4B000000u | i0), MAGIC);   // (float)i0 after the clamp to size-1
+  const unsigned i1 = min(i0 + 1u, m);
+  return make_uint4(i0 * (unsigned)stride, i1 * (unsigned)stride, __float_as_uint(__fsub_rn(pos, f0)), 0u);
 }
 
 // a + (b - a) * t, three roundings (imp.rs:528-535)
@@ -87,7 +101,8 @@ template <int MAXV>
 __device__ __forceinline__ unsigned quantize_round(float v) {
   const float c = fminf(fmaxf(v, 0.0f), 1.0f);
   const float q = __fmul_rn(c, (float)MAXV);
-  return __float2uint_rd(__fadd_rd(q, 0.5f));
+  // floor() via the 2^23 magic number as well (no F2I): two round-down adds, then the low mantissa bits
+  return __float_as_uint(__fadd_rd(__fadd_rd(q, 0.5f), 8388608.0f)) & 0x007FFFFFu;
 }
 
 __device__ __forceinline__ void ldg256(const LutPair *p, float (&v)[8]) {
@@ -104,9 +119,15 @@ __device__ __forceinline__ void colorlut_eval(const LutDev &L, unsigned vr, unsi
     ax = __ldg(L.axis + vr); ay = __ldg(L.axis + L.axis_len + vg); az = __ldg(L.axis + 2 * L.axis_len + vb);
   } else {
     const int s1 = (L.kind == 3) ? L.size : 1, s2 = (L.kind == 3) ? L.size * L.size : 1;
-    ax = axis_entry_u16(vr, L.scale[0], L.offset[0], L.size, 1);
-    ay = axis_entry_u16(vg, L.scale[1], L.offset[1], L.size, s1);
-    az = axis_entry_u16(vb, L.scale[2], L.offset[2], L.size, s2);
+    if (L.ident_domain) {
+      ax = axis_entry_u16<true>(vr, 1.0f, 0.0f, L.size, 1);
+      ay = axis_entry_u16<true>(vg, 1.0f, 0.0f, L.size, s1);
+      az = axis_entry_u16<true>(vb, 1.0f, 0.0f, L.size, s2);
+    } else {
+      ax = axis_entry_u16<false>(vr, L.scale[0], L.offset[0], L.size, 1);
+      ay = axis_entry_u16<false>(vg, L.scale[1], L.offset[1], L.size, s1);
+      az = axis_entry_u16<false>(vb, L.scale[2], L.offset[2], L.size, s2);
+    }
   }
   const float tx = __uint_as_float(ax.z), ty = __uint_as_float(ay.z), tz = __uint_as_float(az.z);
   if (L.kind == 3) {

@@ -279,6 +279,61 @@ __global__ void __launch_bounds__(256) hsvdetector_kernel(HsvDetectSettings st, 
 }
 
 // --------------------------------------------------------------------------------------------
+// Generic 4-byte -> 4-byte table-lookup map (memoised hsvfilter / hsvdetector on 4-bpp formats): same thread
+// mapping as colorlut_memo_apply_kernel -- a warp owns 32*PX consecutive pixels, every gather instruction covers 32
+// consecutive pixels, PX gathers in flight per thread.  In place (src == dst) is fine: a thread only rewrites its
+// own pixels.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t swap_c0_c2(uint32_t c) { return __byte_perm(c, 0u, 0x4012); }  // (c0,c1,c2,_) -> (c2,c1,c0,0)
+
+template <int COFF, bool BGR>
+struct HsvFilterMemoOp {  // memo is keyed and valued in R,G,B byte order
+  const uint32_t *memo;
+  __device__ __forceinline__ uint32_t operator()(uint32_t px) const {
+    uint32_t c = (px >> (8 * COFF)) & 0x00FFFFFFu;
+    if (BGR) c = swap_c0_c2(c);
+    uint32_t v = __ldg(memo + c);
+    if (BGR) v = swap_c0_c2(v);
+    const uint32_t keep = COFF ? (px & 0x000000FFu) : (px & 0xFF000000u);   // x / alpha byte untouched
+    return keep | (v << (8 * COFF));
+  }
+};
+
+template <int ICOFF, bool IBGR, int OCOFF, bool OBGR>
+struct HsvDetectBitmapOp {  // bitmap bit index = r | g<<8 | b<<16
+  const uint32_t *bitmap;
+  __device__ __forceinline__ uint32_t operator()(uint32_t px) const {
+    const uint32_t c = (px >> (8 * ICOFF)) & 0x00FFFFFFu;
+    const uint32_t idx = IBGR ? swap_c0_c2(c) : c;
+    const uint32_t hit = (__ldg(bitmap + (idx >> 5)) >> (idx & 31u)) & 1u;
+    const uint32_t oc = (IBGR == OBGR) ? c : swap_c0_c2(c);
+    const uint32_t a = hit ? (OCOFF ? 0x000000FFu : 0xFF000000u) : 0u;
+    return (oc << (8 * OCOFF)) | a;
+  }
+};
+
+template <typename Op, int PX>
+__global__ void __launch_bounds__(256) map_u32_kernel(Op op, const uint8_t *__restrict__ src, long sstride,
+                                                      uint8_t *__restrict__ dst, long dstride, int width, int height) {
+  pdl_trigger();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x0 = (blockIdx.x * (blockDim.x >> 5) + warp) * (32 * PX) + lane;
+  if (x0 - lane >= width) return;
+  for (int row = blockIdx.y; row < height; row += gridDim.y) {
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)row * sstride);
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst + (size_t)row * dstride);
+    uint32_t px[PX], o[PX];
+#pragma unroll
+    for (int k = 0; k < PX; k++) px[k] = (x0 + 32 * k < width) ? ld_stream_u32(s + x0 + 32 * k) : 0u;
+#pragma unroll
+    for (int k = 0; k < PX; k++) o[k] = op(px[k]);
+#pragma unroll
+    for (int k = 0; k < PX; k++)
+      if (x0 + 32 * k < width) st_stream_u32(d + x0 + 32 * k, o[k]);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
 // videocompare / blockhash block sums.  hashed_image.rs:24-64 -> image_hasher blockhash fast path.
 // One CTA reduces a (bw x rows) tile that lies inside ONE hash block: registers -> warp shuffle
 // -> shared -> a single atomicAdd on the bin.  Integer adds are order independent => exact.

