@@ -22,6 +22,7 @@
 
 #include "kernels.cuh"
 #include "stream_map.cuh"
+#include "blockhash_tma.cuh"
 
 using namespace b200vfx;
 
@@ -55,6 +56,7 @@ struct b200vfx_ctx {
   DevBuf stage_in, stage_out, stage_sums;
   int chunk_rows = 0;
   int sm_count = 148;
+  bool blockhash_tma = true;  // videocompare block sums through the TMA-fed kernel (0 = register-staged LDG kernel)
   int zero_copy = 2;       // pinned host frames: TMA kernel reads/writes host memory directly; 0 never, 1 always, 2 auto-probe
   int zc_calls = 0; double zc_best_ms[2] = {1e30, 1e30};   // auto-probe state: [0] zero-copy, [1] staged
   int zc_cfg = 2, zc_ctas = 1, zc_grid = 64;  // stream-kernel variant / CTAs per SM / absolute grid cap for the zero-copy path
@@ -681,6 +683,7 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "memo_px") c->memo_px = value;
   else if (n == "pdl") c->pdl = value != 0;
   else if (n == "zero_copy") { c->zero_copy = value; c->zc_calls = 0; c->zc_best_ms[0] = c->zc_best_ms[1] = 1e30; }
+  else if (n == "blockhash_tma") c->blockhash_tma = value != 0;
   else if (n == "zc_cfg") c->zc_cfg = value;
   else if (n == "zc_ctas") c->zc_ctas = value;
   else if (n == "zc_grid") c->zc_grid = value;
@@ -926,7 +929,16 @@ int b200vfx_blockhash_sums(b200vfx_ctx *c, int fmt, int width, int height, const
   if ((long)hw * hh < ctas_target) rows_per_cta = std::max(1, (int)((long)bh * hw * hh / ctas_target));
   dim3 grid((unsigned)hw, (unsigned)hh, (unsigned)ceil_div(bh, rows_per_cta));
   const bool vec = bpp == 4 && (bw % 4) == 0 && aligned(d_src, d_stride, 16);
-  if (vec) blockhash_sums_kernel<4, true><<<grid, 128, 0, st>>>(d_src, d_stride, bw, bh, hw, rows_per_cta, d_sums);
+  if (vec && c->blockhash_tma) {  // TMA-fed variant: whole tile in flight through cp.async.bulk, tile <= 32 KB
+    const int rows_tma = std::max(1, std::min(rows_per_cta, kBlockhashTileBytes / (bw * 4)));
+    if (bw * 4 <= kBlockhashTileBytes) {
+      dim3 g2((unsigned)hw, (unsigned)hh, (unsigned)ceil_div(bh, rows_tma));
+      blockhash_sums_tma_kernel<<<g2, 128, (size_t)rows_tma * bw * 4, st>>>(d_src, d_stride, bw, bh, hw, rows_tma, d_sums);
+    } else {
+      blockhash_sums_kernel<4, true><<<grid, 128, 0, st>>>(d_src, d_stride, bw, bh, hw, rows_per_cta, d_sums);
+    }
+  }
+  else if (vec) blockhash_sums_kernel<4, true><<<grid, 128, 0, st>>>(d_src, d_stride, bw, bh, hw, rows_per_cta, d_sums);
   else if (bpp == 4) blockhash_sums_kernel<4, false><<<grid, 128, 0, st>>>(d_src, d_stride, bw, bh, hw, rows_per_cta, d_sums);
   else blockhash_sums_kernel<3, false><<<grid, 128, 0, st>>>(d_src, d_stride, bw, bh, hw, rows_per_cta, d_sums);
   c->launches++;
