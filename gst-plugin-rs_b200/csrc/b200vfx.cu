@@ -56,7 +56,7 @@ struct b200vfx_ctx {
   DevBuf stage_in, stage_out, stage_sums;
   int chunk_rows = 0;
   int sm_count = 148;
-  bool blockhash_tma = true;  // videocompare block sums through the TMA-fed kernel (0 = register-staged LDG kernel)
+  bool blockhash_tma = false; // videocompare block sums through the TMA-fed kernel (measured equal or slightly slower than the register-staged LDG kernel: profiles/r01_kernel_matrix.md)
   int zero_copy = 2;       // pinned host frames: TMA kernel reads/writes host memory directly; 0 never, 1 always, 2 auto-probe
   int zc_calls = 0; double zc_best_ms[2] = {1e30, 1e30};   // auto-probe state: [0] zero-copy, [1] staged
   int zc_cfg = 2, zc_ctas = 1, zc_grid = 64;  // stream-kernel variant / CTAs per SM / absolute grid cap for the zero-copy path
