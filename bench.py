@@ -203,6 +203,8 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's "NCCL version ..." banner goes to stdout; rank 0 must print ONE JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N = world
