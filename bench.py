@@ -51,6 +51,37 @@ def host_threads():
     return n
 
 
+def ncu_traffic_bytes(mode):
+    """dram bytes (read+write) per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_traffic.json): mean of the frame-A and frame-B captures, like the bench's A/B frame mix"""
+    if mode != 0:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return int(json.load(f)["colorlut_memo_apply_kernel<4>"]["mix_ramps_noise_cold"])
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa(index):
+    """best effort: run this rank on the CPUs NVML reports as local to GPU `index`, so page-locked host frames are
+    allocated on that NUMA node and PCIe traffic does not cross the socket interconnect (matters for e2e at N>1)"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        target = cpus & allowed
+        if target:
+            os.sched_setaffinity(0, target)
+            return len(target)
+    except Exception:
+        pass
+    return 0
+
+
 def hbm_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -201,6 +232,7 @@ def main():
     if not torch.cuda.is_available() or b200vfx.device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device -- the b200vfx path has no CPU fallback")
     torch.cuda.set_device(local)
+    bind_to_gpu_numa(local)   # pinned frame buffers and the submitting thread live on the GPU's NUMA node (best effort)
     dist = None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
@@ -350,7 +382,7 @@ def main():
                        "sharding": "row tiles, rank r owns rows [r*H/N,(r+1)*H/N) of every frame; no data-path collective"},
             "gpu_launches": total_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "colorlut_memo_apply_kernel<4>" if args.mode == 0 else "colorlut_direct_kernel<0,true>",
+                         "traffic": ncu_traffic_bytes(args.mode), "kernel": "colorlut_memo_apply_kernel<4>" if args.mode == 0 else "colorlut_direct_kernel<0,true>",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME,
                          "us_per_launch": per_launch_s * 1e6, "by_content": breakdown},
             "clocks": sampler.summary(),

@@ -58,7 +58,7 @@ struct b200vfx_ctx {
   int sm_count = 148;
   bool blockhash_tma = false; // videocompare block sums through the TMA-fed kernel (measured equal or slightly slower than the register-staged LDG kernel: profiles/r01_kernel_matrix.md)
   int zero_copy = 2;       // pinned host frames: TMA kernel reads/writes host memory directly; 0 never, 1 always, 2 auto-probe
-  int zc_calls = 0; double zc_best_ms[2] = {1e30, 1e30};   // auto-probe state: [0] zero-copy, [1] staged
+  int zc_calls = 0, zc_bad_streak = 0; double zc_best_ms[2] = {1e30, 1e30};   // auto-probe state: [0] zero-copy, [1] staged
   int zc_cfg = 2, zc_ctas = 1, zc_grid = 64;  // stream-kernel variant / CTAs per SM / absolute grid cap for the zero-copy path
   int stream_grid = 0;     // absolute cap on the persistent grid of the stream kernels (0 = none)
   bool pdl = true;       // programmatic dependent launch for out-of-place frame kernels
@@ -804,10 +804,17 @@ int b200vfx_colorlut_process(b200vfx_ctx *c, int fmt, int width, int height, con
   const bool use_zc = eligible && (c->zero_copy == 1 || (probing ? (c->zc_calls % 2 == 0) : (c->zc_best_ms[0] <= c->zc_best_ms[1])));
   const auto t_begin = std::chrono::steady_clock::now();
   auto probe_done = [&](int which) {
-    if (!probing) return;
+    if (!eligible || c->zero_copy != 2) return;
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-    if (c->zc_calls >= 2) c->zc_best_ms[which] = std::min(c->zc_best_ms[which], ms);   // first call of each kind is a warm-up
-    c->zc_calls++;
+    if (probing) {
+      if (c->zc_calls >= 2) c->zc_best_ms[which] = std::min(c->zc_best_ms[which], ms);   // first call of each kind is a warm-up
+      c->zc_calls++;
+      return;
+    }
+    // watchdog: the kernel-issued PCIe reads occasionally fall into a slow mode (measured 4x, profiles/r01_e2e.md);
+    // three consecutive calls 1.5x slower than the other path's best trigger a new probe
+    if (ms > 1.5 * c->zc_best_ms[1 - which]) { if (++c->zc_bad_streak >= 3) { c->zc_calls = 0; c->zc_bad_streak = 0; c->zc_best_ms[0] = c->zc_best_ms[1] = 1e30; } }
+    else c->zc_bad_streak = 0;
   };
   if (use_zc) {
     // PCIe needs far fewer bytes in flight than HBM: a small grid of small tiles measured best (profiles/)
