@@ -241,15 +241,23 @@ int launch_memo_stream_t(b200vfx_ctx *c, const uint8_t *src, long ss, uint8_t *d
   constexpr int smem = stream_smem_bytes<TILE, STAGES>();
   auto k3 = colorlut_memo_stream_kernel<TILE, STAGES, THREADS, B>;
   auto k1 = colorlut_memo1d_stream_kernel<TILE, STAGES, THREADS, B>;
-  static thread_local bool attr_done = false;
-  if (!attr_done) {
-    CU(c, cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(c, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
+  // function attributes are per device: remember per (kernel variant, device) whether they are set and what the
+  // occupancy query returned (both are driver calls we do not want on every frame)
+  static std::mutex mu;
+  static int per_sm_cache[64] = {0};
   int per_sm = 0;
-  CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3, THREADS, smem));
-  if (per_sm < 1) per_sm = 1;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    const int dev = (c->device >= 0 && c->device < 64) ? c->device : 0;
+    if (per_sm_cache[dev] == 0) {
+      CU(c, cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CU(c, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      int n = 0;
+      CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k3, THREADS, smem));
+      per_sm_cache[dev] = n < 1 ? 1 : n;
+    }
+    per_sm = per_sm_cache[dev];
+  }
   if (c->stream_ctas > 0) per_sm = std::min(per_sm, c->stream_ctas);
   const long long ntiles = (long long)ceil_div(row_bytes, TILE) * h;
   long long gmax = (long long)c->sm_count * per_sm;
@@ -638,6 +646,8 @@ void b200vfx_ctx_destroy(b200vfx_ctx *c) {
   if (!c) return;
   DeviceGuard g(c->device);
   cudaDeviceSynchronize();
+  pdl_forget(c->own_stream); pdl_forget(c->s_k);
+  if (c->use_user_stream) pdl_forget(c->user_stream);   // everything of ours on it has completed (device synchronised)
   b200vfx_colorlut_clear(c);
   if (c->d_hf_memo) cudaFree(c->d_hf_memo);
   if (c->d_hd_bitmap) cudaFree(c->d_hd_bitmap);

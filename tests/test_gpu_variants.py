@@ -39,6 +39,29 @@ def test_blockhash_tma_and_plain_variants(ctx, tma, w, h, pad):
         ctx.set_option("blockhash_tma", 1)
 
 
+def test_contexts_on_every_visible_device():
+    """one context per GPU in one process (function attributes / streams / tables are per device)"""
+    torch = pytest.importorskip("torch")
+    n = torch.cuda.device_count()
+    cube1 = orc.cube_parse(synth.cube_text_1d(64, 2.0))     # 1D LUT -> TMA streaming kernel (needs the smem attribute)
+    cube3 = orc.cube_parse(synth.cube_text_3d(9, "mix"))
+    w, h = 1024, 96
+    frame = synth.frame_natural("RGBA", w, h, 4)
+    for dev in range(n):
+        with b200vfx.Context(dev) as c:
+            for cube in (cube1, cube3):
+                c.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+                exp = orc.colorlut_apply(cube, "RGBA", w, h, frame)
+                out = np.zeros_like(frame)
+                c.colorlut_process("RGBA", w, h, frame, 4 * w, out, 4 * w)              # host path
+                assert (out == exp).all(), dev
+                d_in = torch.from_numpy(frame).to("cuda:%d" % dev)
+                d_out = torch.zeros_like(d_in)
+                c.colorlut_process("RGBA", w, h, d_in, 4 * w, d_out, 4 * w)             # device path on the ctx's own stream
+                c.synchronize()
+                assert (d_out.cpu().numpy() == exp).all(), dev
+
+
 def test_videocompare_config4_two_4k_streams(ctx):
     """BASELINE config 4: stream 0 = frame A, stream 1 = frame A with 1 % of the pixels perturbed"""
     w, h = 3840, 2160
