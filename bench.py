@@ -235,8 +235,8 @@ def main():
     bind_to_gpu_numa(local)   # pinned frame buffers and the submitting thread live on the GPU's NUMA node (best effort)
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's "NCCL version ..." banner goes to stdout; rank 0 must print ONE JSON line
+        # NCCL writes its banner / debug lines to stdout; rank 0 must print ONE JSON line there -> send them to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N = world

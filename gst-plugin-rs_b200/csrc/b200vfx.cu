@@ -56,6 +56,8 @@ struct b200vfx_ctx {
   DevBuf stage_in, stage_out, stage_sums;
   int chunk_rows = 0;
   int sm_count = 148;
+  int l2_persist = 1;        // mark the 2^24-entry answer tables as L2-persisting (access-policy window per launch)
+  size_t l2_persist_max = 0, l2_window_max = 0, l2_set_aside = 0;
   bool blockhash_tma = false; // videocompare block sums through the TMA-fed kernel (measured equal or slightly slower than the register-staged LDG kernel: profiles/r01_kernel_matrix.md)
   int zero_copy = 2;       // pinned host frames: TMA kernel reads/writes host memory directly; 0 never, 1 always, 2 auto-probe
   int zc_calls = 0, zc_bad_streak = 0; double zc_best_ms[2] = {1e30, 1e30};   // auto-probe state: [0] zero-copy, [1] staged
@@ -182,6 +184,36 @@ int build_axis(b200vfx_ctx *c, cudaStream_t st) {
   return 0;
 }
 
+// L2 residency control for the big answer tables: the launch carries an access-policy window that marks table lines
+// "persisting" (they live in the L2 set-aside reserved with cudaLimitPersistingL2CacheSize) while everything else of
+// the launch (the frame) is "streaming".  thread_local: set around one launch by with_l2_window().
+thread_local cudaAccessPolicyWindow g_l2_window = {};
+struct with_l2_window {
+  with_l2_window(const b200vfx_ctx *c, const void *table, size_t bytes);
+  ~with_l2_window() { g_l2_window = cudaAccessPolicyWindow{}; }
+};
+
+with_l2_window::with_l2_window(const b200vfx_ctx *c, const void *table, size_t bytes) {
+  g_l2_window = cudaAccessPolicyWindow{};
+  if (!c->l2_persist || !table || c->l2_window_max == 0 || c->l2_set_aside == 0) return;
+  g_l2_window.base_ptr = const_cast<void *>(table);
+  g_l2_window.num_bytes = std::min(bytes, c->l2_window_max);
+  g_l2_window.hitRatio = (float)std::min(1.0, (double)c->l2_set_aside / (double)g_l2_window.num_bytes);
+  g_l2_window.hitProp = cudaAccessPropertyPersisting;
+  g_l2_window.missProp = cudaAccessPropertyStreaming;
+}
+
+// reserve L2 set-aside for persisting lines (device-wide limit; only raised, never lowered, by this library)
+int ensure_l2_set_aside(b200vfx_ctx *c, size_t want) {
+  if (!c->l2_persist || c->l2_persist_max == 0) return 0;
+  const size_t target = std::min(c->l2_persist_max, want);
+  size_t cur = 0;
+  CU(c, cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize));
+  if (cur < target) CU(c, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, target));
+  c->l2_set_aside = std::max(cur, target);
+  return 0;
+}
+
 // Programmatic dependent launch (PDL): our out-of-place frame kernels do not depend on the previous frame's kernel,
 // so they are launched with programmaticStreamSerialization and trigger `griddepcontrol.launch_dependents` at
 // entry: the next frame's CTAs fill the SMs while this frame's tail drains (same stream, no extra streams).
@@ -223,10 +255,15 @@ template <typename... KArgs, typename... Args>
 cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (g_l2_window.num_bytes) {  // lookup table of this launch: L2 persisting access window (set by with_l2_window)
+    attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[1].val.accessPolicyWindow = g_l2_window;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -295,6 +332,7 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
   if (fmt == B200VFX_FORMAT_RGBA && c->mode == 0) {
     if (!c->memo_ready) {  // once per LUT: evaluate all 2^24 colours with the exact direct evaluator
       if (c->lut_kind == 3) {
+        if (int rc = ensure_l2_set_aside(c, (size_t)72 << 20)) return rc;
         if (!c->d_memo) CU(c, cudaMalloc(&c->d_memo, sizeof(uint32_t) << 24));
         colorlut_memo_build_kernel<<<(1u << 24) / 256, 256, 0, st>>>(p, c->d_memo);
       } else {
@@ -306,6 +344,7 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
       c->memo_ready = true;
     }
     const bool al = aligned(f.src, f.sstride, 4) && aligned(f.dst, f.dstride, 4);
+    with_l2_window l2w(c, c->lut_kind == 3 ? c->d_memo : nullptr, sizeof(uint32_t) << 24);
     int w = f.width, h = f.height;
     long ss = f.sstride, ds = f.dstride;
     if (al && ss == 4L * w && ds == 4L * w && (long long)w * h < (1LL << 28)) { w = w * h; h = 1; }  // packed: 1-D
@@ -383,6 +422,7 @@ int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings 
   bool built_now = false;
   if (use_memo) {
     if (!c->hf_ready) {
+      if (int rc = ensure_l2_set_aside(c, (size_t)72 << 20)) return rc;
       if (!c->d_hf_memo) CU(c, cudaMalloc(&c->d_hf_memo, sizeof(uint32_t) << 24));
       pdl_admit(false, st, Span{0, 0}, Span{0, 0});  // plain launch
       hsvfilter_memo_build_kernel<<<(1u << 24) / 256, 256, 0, st>>>(s, c->d_hf_memo);
@@ -399,6 +439,7 @@ int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings 
     if (ss == 4L * w && (long long)w * h < (1LL << 28)) { ww = w * h; hh = 1; }
     const Span sp = span_of(data, stride, (size_t)w * 4, h);
     const bool pdl = pdl_admit(c->pdl && !built_now, st, sp, sp);
+    with_l2_window l2w(c, memo, sizeof(uint32_t) << 24);
     dim3 grid((unsigned)ceil_div(ww, 8 * 32 * 4), grid_rows(hh));
 #define LM(CO, BG) CU(c, launch_k(pdl, map_u32_kernel<HsvFilterMemoOp<CO, BG>, 4>, grid, dim3(256), 0, st, HsvFilterMemoOp<CO, BG>{memo}, (const uint8_t *)data, ss, data, ss, ww, hh))
     if (fi.coff == 0) { if (fi.bgr) LM(0, true); else LM(0, false); }
@@ -623,6 +664,12 @@ int b200vfx_ctx_create(b200vfx_ctx **out, int device) {
   b200vfx_ctx *c = new b200vfx_ctx();
   c->device = device;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, device) == cudaSuccess && v > 0) c->l2_persist_max = (size_t)v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, device) == cudaSuccess && v > 0) c->l2_window_max = (size_t)v;
+    if (const char *e = getenv("B200VFX_L2_PERSIST")) c->l2_persist = atoi(e);
+  }
   if (c->sm_count <= 0) c->sm_count = 148;
   if (const char *e = getenv("B200VFX_STREAM_PATH")) c->stream_path = atoi(e);
   if (const char *e = getenv("B200VFX_STREAM_CFG")) c->stream_cfg = atoi(e);
@@ -694,6 +741,7 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "pdl") c->pdl = value != 0;
   else if (n == "zero_copy") { c->zero_copy = value; c->zc_calls = 0; c->zc_best_ms[0] = c->zc_best_ms[1] = 1e30; }
   else if (n == "blockhash_tma") c->blockhash_tma = value != 0;
+  else if (n == "l2_persist") c->l2_persist = value;
   else if (n == "zc_cfg") c->zc_cfg = value;
   else if (n == "zc_ctas") c->zc_ctas = value;
   else if (n == "zc_grid") c->zc_grid = value;
