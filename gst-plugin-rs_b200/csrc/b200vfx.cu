@@ -56,7 +56,10 @@ struct b200vfx_ctx {
   DevBuf stage_in, stage_out, stage_sums;
   int chunk_rows = 0;
   int sm_count = 148;
-  int l2_persist = 1;        // mark the 2^24-entry answer tables as L2-persisting (access-policy window per launch)
+  int l2_persist = 0;        // 1 = mark the 2^24-entry answer tables as L2-persisting (access-policy window per launch +
+                             // device-wide set-aside).  OFF: measured harmful on B200 -- the set-aside halves the L2 left for
+                             // the frames (frame A 11.5 -> 24.5 us) and does not help frame B, which is L1-gather-bound
+                             // (profiles/r01_l2_persist_experiment.jsonl)
   size_t l2_persist_max = 0, l2_window_max = 0, l2_set_aside = 0;
   bool blockhash_tma = false; // videocompare block sums through the TMA-fed kernel (measured equal or slightly slower than the register-staged LDG kernel: profiles/r01_kernel_matrix.md)
   int zero_copy = 2;       // pinned host frames: TMA kernel reads/writes host memory directly; 0 never, 1 always, 2 auto-probe

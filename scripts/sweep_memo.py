@@ -38,7 +38,9 @@ for name, fn in contents.items():
 fr, out = data["noise"]
 t = timeit(lambda i: out[i % RING].copy_(fr[i % RING]))
 print(json.dumps({"variant": "torch_copy_33MB", "us": round(t * 1e6, 2), "frac": round(2 * W * H * 4 / t / 1e9 / PEAK, 4)}), flush=True)
-variants = [("plain", {"stream_path": 0, "memo_px": px, "pdl": pdl, "l2_persist": l2}) for l2 in (1, 0) for px in (4, 8) for pdl in (0, 1)]
+# (the L2-persisting access window is deliberately not swept here: enabling it once raises a device-wide set-aside that
+#  slows every later variant -- see profiles/r01_l2_persist_experiment.jsonl)
+variants = [("plain", {"stream_path": 0, "memo_px": px, "pdl": pdl}) for px in (4, 8) for pdl in (0, 1)]
 for cfg in (0, 1, 2, 7):
     for pdl in (0, 1):
         variants.append(("tma", {"stream_path": 1, "stream_cfg": cfg, "stream_ctas": 0, "stream_hint": 1, "pdl": pdl}))
