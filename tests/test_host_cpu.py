@@ -21,6 +21,17 @@ def test_library_exports_every_declared_symbol():
     assert b200vfx.lib().b200vfx_abi_version() == 1
 
 
+def test_library_exports_every_element_layer_symbol():
+    import re
+    text = open(os.path.join(b200vfx.REPO_ROOT, "include", "b200gst.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(b200gst_[a-z0-9_]+)\s*\(", text)))
+    assert len(names) >= 20
+    L = C.CDLL(b200vfx.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), "libb200vfx.so does not export %s" % n
+
+
 def test_no_gpu_fails_loudly():
     if b200vfx.device_count() > 0:
         pytest.skip("GPU present")
