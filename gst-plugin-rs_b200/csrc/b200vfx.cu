@@ -64,7 +64,8 @@ struct b200vfx_ctx {
   bool blockhash_tma = false; // videocompare block sums through the TMA-fed kernel (measured equal or slightly slower than the register-staged LDG kernel: profiles/r01_kernel_matrix.md)
   int zero_copy = 2;       // pinned host frames: TMA kernel reads/writes host memory directly; 0 never, 1 always, 2 auto-probe
   int zc_calls = 0, zc_bad_streak = 0; double zc_best_ms[2] = {1e30, 1e30};   // auto-probe state: [0] zero-copy, [1] staged
-  int zc_cfg = 2, zc_ctas = 1, zc_grid = 64;  // stream-kernel variant / CTAs per SM / absolute grid cap for the zero-copy path
+  int zc_cfg = 2, zc_ctas = 1, zc_grid = 64;
+  int zc_hybrid = 0;       // experiment: staged path with one direction zero-copy (1: kernel stores to host, 2: kernel loads from host)  // stream-kernel variant / CTAs per SM / absolute grid cap for the zero-copy path
   int stream_grid = 0;     // absolute cap on the persistent grid of the stream kernels (0 = none)
   bool pdl = true;       // programmatic dependent launch for out-of-place frame kernels
   bool pdl_now = false;  // per launch: false when this call (re)built a table the kernel reads
@@ -540,13 +541,14 @@ struct Staged {
   uint8_t *dst; long dstride; size_t out_row_bytes;        // in place: dst == src plane
   int height;
   bool in_place;
+  int device_addressable = 0;  // bit 0: src, bit 1: dst are pinned host planes the kernel may address directly (zero-copy)
 };
 
 template <typename LaunchFn>
 int run_staged(b200vfx_ctx *c, const Staged &s, LaunchFn launch) {
   if (s.height == 0) return 0;
-  const bool src_dev = !s.src || is_device_ptr(s.src);  // no input plane counts as "nothing to upload"
-  const bool dst_dev = is_device_ptr(s.dst);
+  const bool src_dev = !s.src || (s.device_addressable & 1) || is_device_ptr(s.src);  // no input plane counts as "nothing to upload"
+  const bool dst_dev = (s.device_addressable & 2) || is_device_ptr(s.dst);
   if (s.in_place ? dst_dev : (src_dev && dst_dev)) {  // everything already in HBM: just enqueue
     return launch(s.src, s.sstride, s.dst, s.dstride, 0, s.height, c->stream());
   }
@@ -746,6 +748,7 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "blockhash_tma") c->blockhash_tma = value != 0;
   else if (n == "l2_persist") c->l2_persist = value;
   else if (n == "zc_cfg") c->zc_cfg = value;
+  else if (n == "zc_hybrid") c->zc_hybrid = value;
   else if (n == "zc_ctas") c->zc_ctas = value;
   else if (n == "zc_grid") c->zc_grid = value;
   else if (n == "stream_grid") c->stream_grid = value;
@@ -862,7 +865,7 @@ int b200vfx_colorlut_process(b200vfx_ctx *c, int fmt, int width, int height, con
                         aligned(src, src_stride, 16) && aligned(dst, dst_stride, 16) && pinned_device_ptr(src, &dsrc) &&
                         pinned_device_ptr(dst, &ddst);
   const bool probing = eligible && c->zero_copy == 2 && c->zc_calls < 6;
-  const bool use_zc = eligible && (c->zero_copy == 1 || (probing ? (c->zc_calls % 2 == 0) : (c->zc_best_ms[0] <= c->zc_best_ms[1])));
+  const bool use_zc = eligible && c->zc_hybrid == 0 && (c->zero_copy == 1 || (probing ? (c->zc_calls % 2 == 0) : (c->zc_best_ms[0] <= c->zc_best_ms[1])));
   const auto t_begin = std::chrono::steady_clock::now();
   auto probe_done = [&](int which) {
     if (!eligible || c->zero_copy != 2) return;
@@ -890,6 +893,8 @@ int b200vfx_colorlut_process(b200vfx_ctx *c, int fmt, int width, int height, con
     return 0;
   }
   Staged s{(const uint8_t *)src, src_stride, row, (uint8_t *)dst, dst_stride, row, height, false};
+  if (eligible && c->zc_hybrid == 1) { s.dst = (uint8_t *)ddst; s.device_addressable = 2; }        // copy engine in, kernel stores out
+  else if (eligible && c->zc_hybrid == 2) { s.src = (const uint8_t *)dsrc; s.device_addressable = 1; }  // kernel loads in, copy engine out
   const int rc = run_staged(c, s, [&](const uint8_t *ds, long dss, uint8_t *dd, long dds, int, int rows, cudaStream_t st) {
     return launch_colorlut(c, fmt, Frame{ds, dss, dd, dds, width, rows}, st);
   });
