@@ -13,7 +13,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(HERE)
 REPO_ROOT = os.path.dirname(PKG_ROOT)
-LIB_PATH = os.path.join(PKG_ROOT, "lib", "libb200vfx.so")
+LIB_PATH = os.environ.get("B200VFX_LIB") or os.path.join(PKG_ROOT, "lib", "libb200vfx.so")   # override: A/B builds
 HEADER = os.path.join(REPO_ROOT, "include", "b200vfx.h")
 
 FMT = {"RGBx": 0, "xRGB": 1, "BGRx": 2, "xBGR": 3, "RGBA": 4, "ARGB": 5, "BGRA": 6, "ABGR": 7,

@@ -15,6 +15,19 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) { return __
 __device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v) { __stcs(p, v); }
 __device__ __forceinline__ uint2 ld_stream_u2(const uint2 *p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream_u2(uint2 *p, uint2 v) { __stcs(p, v); }
+// Layout of the 2^24-entry answer tables.  Linear: index = r | g<<8 | b<<16 (a 128-byte line = 32 consecutive r).
+// Blocked (-DB200VFX_MEMO_BLOCKED=1): a line = a 4(r) x 4(g) x 2(b) colour block, so pixels whose colours differ by
+// sensor noise in all three channels share lines instead of spreading over one line per (g,b) pair.
+#ifndef B200VFX_MEMO_BLOCKED
+#define B200VFX_MEMO_BLOCKED 0
+#endif
+__device__ __forceinline__ uint32_t memo_index(uint32_t c) {  // c = r | g<<8 | b<<16
+#if B200VFX_MEMO_BLOCKED
+  return (c & 3u) | ((c >> 6) & 0xCu) | ((c >> 12) & 0x10u) | ((c << 3) & 0x7E0u) | ((c << 1) & 0x1F800u) | (c & 0xFE0000u);
+#else
+  return c;
+#endif
+}
 // PDL: let the next (independent) frame's kernel start as soon as every CTA of this one has been scheduled
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -92,7 +105,7 @@ __global__ void __launch_bounds__(256) colorlut_memo_build_kernel(LutDev L, uint
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;  // idx = r | g<<8 | b<<16
   unsigned o[3];
   colorlut_eval<255>(L, idx & 255u, (idx >> 8) & 255u, idx >> 16, o);
-  memo[idx] = o[0] | (o[1] << 8) | (o[2] << 16);
+  memo[memo_index(idx)] = o[0] | (o[1] << 8) | (o[2] << 16);
 }
 
 // per-channel 256-entry answer tables for a 1D LUT (768 bytes, lives in shared memory)
@@ -125,7 +138,7 @@ __global__ void __launch_bounds__(256) colorlut_memo_apply_kernel(const uint32_t
 #pragma unroll
     for (int k = 0; k < PX; k++) px[k] = (x0 + 32 * k < width) ? ld_stream_u32(s + x0 + 32 * k) : 0u;
 #pragma unroll
-    for (int k = 0; k < PX; k++) o[k] = __ldg(memo + (px[k] & 0x00FFFFFFu));
+    for (int k = 0; k < PX; k++) o[k] = __ldg(memo + memo_index(px[k] & 0x00FFFFFFu));
 #pragma unroll
     for (int k = 0; k < PX; k++)
       if (x0 + 32 * k < width) st_stream_u32(d + x0 + 32 * k, o[k] | (px[k] & 0xFF000000u));
@@ -171,7 +184,7 @@ __global__ void colorlut_memo_apply_bytes_kernel(const uint32_t *__restrict__ me
     uint8_t *d = dst + (size_t)row * dstride + (size_t)x * 4;
     const uint32_t r = s[0], g = s[1], b = s[2];
     if (memo) {
-      const uint32_t o = __ldg(memo + (r | (g << 8) | (b << 16)));
+      const uint32_t o = __ldg(memo + memo_index(r | (g << 8) | (b << 16)));
       d[0] = (uint8_t)o; d[1] = (uint8_t)(o >> 8); d[2] = (uint8_t)(o >> 16);
     } else {
       d[0] = __ldg(memo1d + r); d[1] = __ldg(memo1d + 256 + g); d[2] = __ldg(memo1d + 512 + b);
@@ -196,7 +209,7 @@ __global__ void __launch_bounds__(256) hsvfilter_memo_build_kernel(HsvFilterSett
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned r = idx & 255u, g = (idx >> 8) & 255u, b = idx >> 16;
   hsvfilter_px(st, d255, r, g, b);
-  memo[idx] = r | (g << 8) | (b << 16);
+  memo[memo_index(idx)] = r | (g << 8) | (b << 16);
 }
 
 __global__ void __launch_bounds__(256) hsvdetector_bitmap_build_kernel(HsvDetectSettings st, uint32_t *__restrict__ bitmap) {
@@ -227,7 +240,7 @@ __global__ void __launch_bounds__(256) hsvfilter_kernel(HsvFilterSettings st, co
     }
     unsigned r = BGR ? c2 : c0, g = c1, b = BGR ? c0 : c2;
     if (MEMO) {
-      const uint32_t v = __ldg(memo + (r | (g << 8) | (b << 16)));
+      const uint32_t v = __ldg(memo + memo_index(r | (g << 8) | (b << 16)));
       r = v & 255u; g = (v >> 8) & 255u; b = (v >> 16) & 255u;
     } else {
       hsvfilter_px(st, d255, r, g, b);
@@ -292,7 +305,7 @@ struct HsvFilterMemoOp {  // memo is keyed and valued in R,G,B byte order
   __device__ __forceinline__ uint32_t operator()(uint32_t px) const {
     uint32_t c = (px >> (8 * COFF)) & 0x00FFFFFFu;
     if (BGR) c = swap_c0_c2(c);
-    uint32_t v = __ldg(memo + c);
+    uint32_t v = __ldg(memo + memo_index(c));
     if (BGR) v = swap_c0_c2(v);
     const uint32_t keep = COFF ? (px & 0x000000FFu) : (px & 0xFF000000u);   // x / alpha byte untouched
     return keep | (v << (8 * COFF));

@@ -83,7 +83,7 @@ struct MemoGatherOp {  // out = memo[px & 0xFFFFFF] | alpha
   const uint32_t *memo;
   uint64_t policy;  // 0 = plain read-only load, else an L2 eviction-priority policy (evict_last)
   __device__ __forceinline__ uint32_t operator()(uint32_t px) const {
-    const uint32_t *p = memo + (px & 0x00FFFFFFu);
+    const uint32_t *p = memo + memo_index(px & 0x00FFFFFFu);
     const uint32_t v = policy ? tma::ldg_hint_u32(p, policy) : __ldg(p);
     return v | (px & 0xFF000000u);
   }
