@@ -58,7 +58,7 @@ def ncu_traffic_bytes(mode):
         return None
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return int(json.load(f)["colorlut_memo_apply_kernel<4>"]["mix_ramps_noise_cold"])
+            return int(json.load(f)["dominant_kernel"]["mix_ramps_noise_cold"])
     except Exception:
         return None
 
@@ -382,7 +382,7 @@ def main():
                        "sharding": "row tiles, rank r owns rows [r*H/N,(r+1)*H/N) of every frame; no data-path collective"},
             "gpu_launches": total_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_bytes(args.mode), "kernel": "colorlut_memo_apply_kernel<4>" if args.mode == 0 else "colorlut_direct_kernel<0,true>",
+                         "traffic": ncu_traffic_bytes(args.mode), "kernel": "colorlut_memo_apply_kernel<8>" if args.mode == 0 else "colorlut_direct_kernel<0,true>",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME,
                          "us_per_launch": per_launch_s * 1e6, "by_content": breakdown},
             "clocks": sampler.summary(),

@@ -69,7 +69,7 @@ struct b200vfx_ctx {
   int stream_grid = 0;     // absolute cap on the persistent grid of the stream kernels (0 = none)
   bool pdl = true;       // programmatic dependent launch for out-of-place frame kernels
   bool pdl_now = false;  // per launch: false when this call (re)built a table the kernel reads
-  int stream_cfg = 0, stream_ctas = 0, stream_hint = 1, memo_px = 4;  // tuning knobs (env overrides, see ctx_create)
+  int stream_cfg = 0, stream_ctas = 0, stream_hint = 1, memo_px = 8;  // tuning knobs (env overrides, see ctx_create)
   uint64_t launches = 0;
   std::string err;
 
