@@ -177,7 +177,7 @@ def run_reference(args):
                                        "(the Rust reference cannot be built here)" % (args.steps, threads)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline_sample(np, synth, budget_s=12.0):
@@ -204,8 +204,31 @@ def cpu_baseline_sample(np, synth, budget_s=12.0):
                       "reference loop colorlut/imp.rs:267-294 (Rust toolchain absent)" % (n, threads)}
 
 
+_JSON_FD = None
+
+
+def guard_stdout():
+    """stdout must carry exactly ONE JSON line: libraries (NCCL's version banner, nvcc chatter of a rebuild) write to fd 1
+    behind Python's back, so fd 1 is pointed at stderr for the whole run and the line is written to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 # --------------------------------------------------------------------------------------------------
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -393,7 +416,7 @@ def main():
             line["cpu_baseline"] = cpu
         if allgather is not None:
             line["allgather"] = allgather
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if dist is not None:
         dist.barrier()

@@ -88,6 +88,14 @@ def lib() -> C.CDLL:
         "b200vfx_blockhash_sums": ([vp, ci, ci, ci, vp, ci, ci, ci, vp], ci),
         "b200vfx_blockhash_bits": ([vp, ci, ci, ci, ci, vp], None),
         "b200vfx_hash_distance": ([vp, vp, ci], ci),
+        "b200vfx_peer_alloc": ([vp, C.c_size_t, C.POINTER(vp), C.c_char_p], ci),
+        "b200vfx_peer_free": ([vp, vp], ci),
+        "b200vfx_peer_open": ([vp, C.c_char_p, C.POINTER(vp)], ci),
+        "b200vfx_peer_close": ([vp, vp], ci),
+        "b200vfx_peer_enable_access": ([vp, ci], ci),
+        "b200vfx_peer_status": ([vp, vp, C.POINTER(C.c_uint32)], ci),
+        "b200vfx_colorlut_process_tile_gather": ([vp, ci, ci, ci, vp, ci, ci, ci, C.POINTER(vp), ci, ci, C.POINTER(vp),
+                                                  C.c_uint32], ci),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(L, name)
@@ -209,6 +217,40 @@ class Context:
 
     def colorlut_process(self, fmt, width, height, src, sstride, dst, dstride):
         self._chk(lib().b200vfx_colorlut_process(self._h, FMT[fmt], width, height, _ptr(src), sstride, _ptr(dst), dstride))
+
+    # multi-GPU tile gather (include/b200vfx.h) -----------------------------------
+    def peer_alloc(self, nbytes: int):
+        """(device pointer, 64-byte IPC handle) of zeroed device memory that peers may map"""
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        self._chk(lib().b200vfx_peer_alloc(self._h, nbytes, C.byref(p), h))
+        return int(p.value), bytes(h.raw)
+
+    def peer_free(self, ptr: int):
+        self._chk(lib().b200vfx_peer_free(self._h, ptr))
+
+    def peer_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self._chk(lib().b200vfx_peer_open(self._h, handle, C.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, ptr: int):
+        self._chk(lib().b200vfx_peer_close(self._h, ptr))
+
+    def peer_enable_access(self, peer_device: int):
+        self._chk(lib().b200vfx_peer_enable_access(self._h, peer_device))
+
+    def peer_status(self, flags: int) -> int:
+        e = C.c_uint32(0)
+        self._chk(lib().b200vfx_peer_status(self._h, flags, C.byref(e)))
+        return int(e.value)
+
+    def colorlut_process_tile_gather(self, fmt, width, tile_rows, src, sstride, world, rank, frames, frame_stride,
+                                     frame_row0, flags, epoch):
+        fa = (C.c_void_p * world)(*[int(x) for x in frames])
+        ga = (C.c_void_p * world)(*[int(x) for x in flags])
+        self._chk(lib().b200vfx_colorlut_process_tile_gather(self._h, FMT[fmt], width, tile_rows, _ptr(src), sstride,
+                                                             world, rank, fa, frame_stride, frame_row0, ga, epoch))
 
     # hsv ----------------------------------------------------------------------------------
     def hsvfilter_process(self, fmt, width, height, data, stride, hue_shift=0.0, saturation_mul=1.0,

@@ -50,3 +50,82 @@ def all_reduce_sums(dist, sums):
     t = sums.to(torch.int64)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+class DeviceBuffer:
+    """a raw device allocation seen through __cuda_array_interface__ (torch.as_tensor(buf, device=...) wraps it, no copy)"""
+
+    def __init__(self, ptr: int, shape, owner=None):
+        self.ptr, self.shape, self._owner = ptr, tuple(shape), owner
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class PeerFrames:
+    """Frame buffers for the fused colorlut + all-gather kernel (b200vfx_colorlut_process_tile_gather).
+
+    Every rank owns `nbuf` whole-frame buffers (height x stride bytes) and one flag block in peer-mappable memory; the
+    CUDA IPC handles travel through `dist.all_gather_object` (plumbing only -- the data path is the kernel's own
+    NVLink stores).  process(tile) writes this rank's rows into buffer k = epoch % nbuf of EVERY rank; when the call
+    completes on the context stream, frame(k) on this rank holds all ranks' rows."""
+
+    def __init__(self, ctx, dist, height: int, stride: int, nbuf: int = 2, align: int = 1):
+        self.ctx, self.dist, self.height, self.stride, self.nbuf, self.align = ctx, dist, height, stride, nbuf, align
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.epoch = 0
+        self._own = [ctx.peer_alloc(height * stride) for _ in range(nbuf)]
+        self._own_flags = ctx.peer_alloc(256)
+        mine = {"frames": [h for _, h in self._own], "flags": self._own_flags[1]}
+        everyone = [mine]
+        if self.world > 1:
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine)
+        self._opened = []
+        self.frames = [[0] * self.world for _ in range(nbuf)]   # [buffer][rank] -> address usable on this device
+        self.flags = [0] * self.world
+        for r, info in enumerate(everyone):
+            if r == self.rank:
+                for k in range(nbuf):
+                    self.frames[k][r] = self._own[k][0]
+                self.flags[r] = self._own_flags[0]
+                continue
+            for k in range(nbuf):
+                p = ctx.peer_open(info["frames"][k]); self._opened.append(p); self.frames[k][r] = p
+            p = ctx.peer_open(info["flags"]); self._opened.append(p); self.flags[r] = p
+        if self.world > 1:
+            dist.barrier()
+
+    def rows(self):
+        return row_range(self.height, self.world, self.rank, self.align)
+
+    def process(self, width: int, tile, tile_stride: int):
+        """colorlut on this rank's row tile (device tensor) -> rows of buffer (epoch % nbuf) on every rank; returns k"""
+        r0, r1 = self.rows()
+        self.epoch += 1
+        k = self.epoch % self.nbuf
+        self.ctx.colorlut_process_tile_gather("RGBA", width, r1 - r0, tile, tile_stride, self.world, self.rank,
+                                              self.frames[k], self.stride, r0, self.flags, self.epoch)
+        return k
+
+    def frame(self, k: int):
+        """this rank's whole-frame buffer k as a __cuda_array_interface__ object of shape (height, stride)"""
+        return DeviceBuffer(self._own[k][0], (self.height, self.stride), owner=self)
+
+    def status(self) -> int:
+        """synchronise and return the epoch of the last timed-out peer wait (0 = none)"""
+        return self.ctx.peer_status(self._own_flags[0])
+
+    def close(self):
+        if self.world > 1:
+            self.ctx.synchronize()
+            self.dist.barrier()
+        for p in self._opened:
+            self.ctx.peer_close(p)
+        self._opened = []
+        if self.world > 1:
+            self.dist.barrier()
+        for p, _ in self._own:
+            self.ctx.peer_free(p)
+        self.ctx.peer_free(self._own_flags[0])
+        self._own = []

@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "stream_map.cuh"
 #include "blockhash_tma.cuh"
+#include "tile_gather.cuh"
 
 using namespace b200vfx;
 
@@ -71,6 +72,8 @@ struct b200vfx_ctx {
   bool pdl_now = false;  // per launch: false when this call (re)built a table the kernel reads
   int stream_cfg = 0, stream_ctas = 0, stream_hint = 1, memo_px = 8;  // tuning knobs (env overrides, see ctx_create)
   uint64_t launches = 0;
+  int tg_path = 0, tg_cfg = 0, tg_ctas = 8;   // fused tile gather: 0 register path (LDG/STG), 1 TMA; variant; CTAs per SM
+  int peer_timeout_ms = 2000;  // deadline of the cross-GPU waits in the tile-gather kernel
   std::string err;
 
   // colorlut state (State{lut}, colorlut/imp.rs:50-53)
@@ -323,6 +326,62 @@ int launch_memo_stream(b200vfx_ctx *c, const uint8_t *src, long ss, uint8_t *dst
   }
 }
 
+// once per LUT: evaluate all 2^24 colours (3D) / 3x256 channel values (1D) with the exact direct evaluator
+int ensure_colorlut_memo(b200vfx_ctx *c, const LutDev &p, cudaStream_t st) {
+  if (c->memo_ready) return 0;
+  if (c->lut_kind == 3) {
+    if (int rc = ensure_l2_set_aside(c, (size_t)72 << 20)) return rc;
+    if (!c->d_memo) CU(c, cudaMalloc(&c->d_memo, sizeof(uint32_t) << 24));
+    colorlut_memo_build_kernel<<<(1u << 24) / 256, 256, 0, st>>>(p, c->d_memo);
+  } else {
+    if (!c->d_memo1d) CU(c, cudaMalloc(&c->d_memo1d, 768));
+    colorlut_memo1d_build_kernel<<<3, 256, 0, st>>>(p, c->d_memo1d);
+  }
+  c->launches++;
+  CU(c, cudaGetLastError());
+  c->memo_ready = true;
+  return 0;
+}
+
+// fused tile gather, TMA variant: per-(variant, device) attribute / occupancy cache like launch_memo_stream_t
+template <int TILE, int STAGES, int THREADS, int B>
+int launch_tile_gather_tma_t(b200vfx_ctx *c, bool l1d, const uint8_t *src, long ss, const PeerSet &ps, long ds, long doff,
+                             int row_bytes, int h, cudaStream_t st) {
+  constexpr int smem = stream_smem_bytes<TILE, STAGES>();
+  auto k3 = colorlut_tile_gather_tma_kernel<TILE, STAGES, THREADS, B, false>;
+  auto k1 = colorlut_tile_gather_tma_kernel<TILE, STAGES, THREADS, B, true>;
+  static std::mutex mu;
+  static int per_sm_cache[64] = {0};
+  int per_sm = 0;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    const int dev = (c->device >= 0 && c->device < 64) ? c->device : 0;
+    if (per_sm_cache[dev] == 0) {
+      CU(c, cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CU(c, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      int n = 0;
+      CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k3, THREADS, smem));
+      per_sm_cache[dev] = n < 1 ? 1 : n;
+    }
+    per_sm = per_sm_cache[dev];
+  }
+  if (c->tg_ctas > 0) per_sm = std::min(per_sm, c->tg_ctas);
+  const long long ntiles = (long long)std::max(1, ceil_div(row_bytes, TILE)) * h;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ntiles, (long long)c->sm_count * per_sm));
+  if (l1d) CU(c, launch_k(false, k1, dim3(grid), dim3(THREADS), smem, st, c->d_memo, c->d_memo1d, src, ss, ps, ds, doff, row_bytes, h));
+  else CU(c, launch_k(false, k3, dim3(grid), dim3(THREADS), smem, st, c->d_memo, c->d_memo1d, src, ss, ps, ds, doff, row_bytes, h));
+  return 0;
+}
+int launch_tile_gather_tma(b200vfx_ctx *c, bool l1d, const uint8_t *src, long ss, const PeerSet &ps, long ds, long doff,
+                           int row_bytes, int h, cudaStream_t st) {
+  switch (c->tg_cfg) {
+    case 1: return launch_tile_gather_tma_t<8192, 4, 256, 8>(c, l1d, src, ss, ps, ds, doff, row_bytes, h, st);
+    case 2: return launch_tile_gather_tma_t<4096, 4, 256, 4>(c, l1d, src, ss, ps, ds, doff, row_bytes, h, st);
+    case 3: return launch_tile_gather_tma_t<32768, 3, 512, 8>(c, l1d, src, ss, ps, ds, doff, row_bytes, h, st);
+    default: return launch_tile_gather_tma_t<16384, 4, 256, 8>(c, l1d, src, ss, ps, ds, doff, row_bytes, h, st);
+  }
+}
+
 int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
   if (f.width == 0 || f.height == 0) return 0;
   const bool wide = fmt != B200VFX_FORMAT_RGBA;
@@ -334,19 +393,7 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
   if (int rc = build_axis(c, st)) return rc;
   const LutDev p = lut_dev(c);
   if (fmt == B200VFX_FORMAT_RGBA && c->mode == 0) {
-    if (!c->memo_ready) {  // once per LUT: evaluate all 2^24 colours with the exact direct evaluator
-      if (c->lut_kind == 3) {
-        if (int rc = ensure_l2_set_aside(c, (size_t)72 << 20)) return rc;
-        if (!c->d_memo) CU(c, cudaMalloc(&c->d_memo, sizeof(uint32_t) << 24));
-        colorlut_memo_build_kernel<<<(1u << 24) / 256, 256, 0, st>>>(p, c->d_memo);
-      } else {
-        if (!c->d_memo1d) CU(c, cudaMalloc(&c->d_memo1d, 768));
-        colorlut_memo1d_build_kernel<<<3, 256, 0, st>>>(p, c->d_memo1d);
-      }
-      c->launches++;
-      CU(c, cudaGetLastError());
-      c->memo_ready = true;
-    }
+    if (int rc = ensure_colorlut_memo(c, p, st)) return rc;
     const bool al = aligned(f.src, f.sstride, 4) && aligned(f.dst, f.dstride, 4);
     with_l2_window l2w(c, c->lut_kind == 3 ? c->d_memo : nullptr, sizeof(uint32_t) << 24);
     int w = f.width, h = f.height;
@@ -744,6 +791,10 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "stream_hint") c->stream_hint = value;
   else if (n == "memo_px") c->memo_px = value;
   else if (n == "pdl") c->pdl = value != 0;
+  else if (n == "tile_gather_path") c->tg_path = value;
+  else if (n == "tile_gather_cfg") c->tg_cfg = value;
+  else if (n == "tile_gather_ctas") c->tg_ctas = value;
+  else if (n == "peer_timeout_ms") c->peer_timeout_ms = value > 0 ? value : 1;
   else if (n == "zero_copy") { c->zero_copy = value; c->zc_calls = 0; c->zc_best_ms[0] = c->zc_best_ms[1] = 1e30; }
   else if (n == "blockhash_tma") c->blockhash_tma = value != 0;
   else if (n == "l2_persist") c->l2_persist = value;
@@ -1049,6 +1100,125 @@ int b200vfx_hash_distance(const uint8_t *a, const uint8_t *b, int nbits) {
   int d = 0;
   for (int i = 0; i < nbits; i++) d += (a[i] != 0) != (b[i] != 0);
   return d;
+}
+
+// ---- multi-GPU tile gather (tile_gather.cuh) ----------------------------------------------------
+int b200vfx_peer_alloc(b200vfx_ctx *c, size_t bytes, void **dev_ptr, unsigned char handle_out[B200VFX_IPC_HANDLE_BYTES]) {
+  if (!c || !dev_ptr) return fail(c, B200VFX_ERR_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == B200VFX_IPC_HANDLE_BYTES, "IPC handle size");
+  DeviceGuard g(c->device);
+  void *p = nullptr;
+  CU(c, cudaMalloc(&p, bytes ? bytes : 1));
+  CU(c, cudaMemset(p, 0, bytes ? bytes : 1));
+  CU(c, cudaDeviceSynchronize());
+  if (handle_out) {
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(c, B200VFX_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); }
+    memcpy(handle_out, &h, sizeof h);
+  }
+  *dev_ptr = p;
+  return 0;
+}
+int b200vfx_peer_free(b200vfx_ctx *c, void *dev_ptr) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  DeviceGuard g(c->device);
+  if (dev_ptr) CU(c, cudaFree(dev_ptr));
+  return 0;
+}
+int b200vfx_peer_open(b200vfx_ctx *c, const unsigned char handle[B200VFX_IPC_HANDLE_BYTES], void **dev_ptr) {
+  if (!c || !handle || !dev_ptr) return fail(c, B200VFX_ERR_INVALID, "null argument");
+  DeviceGuard g(c->device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  CU(c, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int b200vfx_peer_close(b200vfx_ctx *c, void *dev_ptr) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  DeviceGuard g(c->device);
+  if (dev_ptr) CU(c, cudaIpcCloseMemHandle(dev_ptr));
+  return 0;
+}
+int b200vfx_peer_enable_access(b200vfx_ctx *c, int peer_device) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (peer_device == c->device) return 0;
+  DeviceGuard g(c->device);
+  int can = 0;
+  CU(c, cudaDeviceCanAccessPeer(&can, c->device, peer_device));
+  if (!can) return fail(c, B200VFX_ERR_UNSUPPORTED, "device %d cannot access device %d", c->device, peer_device);
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+  CU(c, e);
+  return 0;
+}
+int b200vfx_peer_status(b200vfx_ctx *c, const void *flags, uint32_t *error_epoch) {
+  if (!c || !flags || !error_epoch) return fail(c, B200VFX_ERR_INVALID, "null argument");
+  DeviceGuard g(c->device);
+  CU(c, cudaStreamSynchronize(c->stream()));
+  pdl_forget(c->stream());
+  CU(c, cudaMemcpy(error_epoch, (const uint32_t *)flags + PF_ERR, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int b200vfx_colorlut_process_tile_gather(b200vfx_ctx *c, int fmt, int width, int tile_rows, const void *src,
+                                         int src_stride, int world, int rank, void *const *frames, int frame_stride,
+                                         int frame_row0, void *const *flags, uint32_t epoch) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (!c->have_lut) return fail(c, B200VFX_ERR_NOT_NEGOTIATED, "No LUT configured");  // imp.rs:210-213
+  if (fmt != B200VFX_FORMAT_RGBA || c->mode != 0)
+    return fail(c, B200VFX_ERR_UNSUPPORTED, "tile gather: RGBA in memo mode only (format %d, mode %d)", fmt, c->mode);
+  if (world < 1 || world > B200VFX_MAX_PEERS || rank < 0 || rank >= world)
+    return fail(c, B200VFX_ERR_INVALID, "tile gather: bad world/rank %d/%d (max %d ranks)", world, rank, B200VFX_MAX_PEERS);
+  if (!frames || !flags || epoch == 0 || width < 0 || tile_rows < 0 || frame_row0 < 0)
+    return fail(c, B200VFX_ERR_INVALID, "tile gather: null pointer table, zero epoch or negative size");
+  const size_t row = (size_t)width * 4;
+  if (tile_rows > 0 && width > 0 && (!src || (size_t)std::abs(src_stride) < row || (size_t)frame_stride < row || frame_stride < 0))
+    return fail(c, B200VFX_ERR_INVALID, "tile gather: stride smaller than a row (or negative frame stride)");
+  if (tile_rows > 0 && width > 0 && !is_device_ptr(src)) return fail(c, B200VFX_ERR_INVALID, "tile gather: src must be device memory");
+  PeerSet ps = {};
+  for (int p = 0; p < world; p++) {
+    if (!frames[p] || !flags[p]) return fail(c, B200VFX_ERR_INVALID, "tile gather: null frame/flag pointer for rank %d", p);
+    ps.frame[p] = (uint8_t *)frames[p];
+    ps.flags[p] = (uint32_t *)flags[p];
+  }
+  ps.world = world; ps.rank = rank; ps.epoch = epoch; ps.timeout_ms = (uint32_t)c->peer_timeout_ms;
+  DeviceGuard g(c->device);
+  cudaStream_t st = c->stream();
+  const long doff = (long)frame_row0 * frame_stride;
+  // never PDL: the kernel's entry handshake tells the peers that everything before it on this stream has finished
+  pdl_admit(false, st, span_of(src, src_stride, row, tile_rows), span_of(ps.frame[rank] + doff, frame_stride, row, tile_rows));
+  if (int rc = build_axis(c, st)) return rc;
+  if (int rc = ensure_colorlut_memo(c, lut_dev(c), st)) return rc;
+  int w = width, h = tile_rows;
+  long ss = src_stride, ds = frame_stride;
+  if (w == 0 || h == 0) { w = 0; h = 1; }   // an empty tile still takes part in the handshake
+  else if (ss == 4L * w && ds == 4L * w && (long long)w * h < (1LL << 28)) { w = w * h; h = 1; }  // packed: 1-D
+  const bool al4 = w == 0 || (aligned(src, ss, 4) && (doff % 4) == 0 && (ds % 4) == 0);
+  if (!al4) return fail(c, B200VFX_ERR_UNSUPPORTED, "tile gather: planes must be 4-byte aligned");
+  bool vec = (w % 4) == 0 && (ds % 16) == 0 && (doff % 16) == 0;
+  for (int p = 0; p < world; p++) {
+    if ((uintptr_t)ps.frame[p] % 4) return fail(c, B200VFX_ERR_UNSUPPORTED, "tile gather: planes must be 4-byte aligned");
+    if ((uintptr_t)ps.frame[p] % 16) vec = false;
+  }
+  const bool l1d = c->lut_kind != 3;
+  const bool al16 = vec && (w == 0 || (aligned(src, ss, 16)));
+  if (c->tg_path == 1 && al16) {   // TMA: one bulk store per destination out of the shared-memory tile
+    if (int rc = launch_tile_gather_tma(c, l1d, (const uint8_t *)src, ss, ps, ds, doff, 4 * w, h, st)) return rc;
+  } else {
+    constexpr int PX = 8;
+    const long long nwork = (long long)std::max(1, ceil_div(w, 8 * 32 * PX)) * h;
+    dim3 grid((unsigned)std::min<long long>(nwork, (long long)c->sm_count * std::max(1, c->tg_ctas)));
+#define LAUNCH_TG(V, L)                                                                                              \
+  CU(c, launch_k(false, colorlut_tile_gather_kernel<PX, V, L>, grid, dim3(256), 0, st, c->d_memo, c->d_memo1d,       \
+                 (const uint8_t *)src, ss, ps, ds, doff, w, h))
+    if (vec) { if (l1d) LAUNCH_TG(true, true); else LAUNCH_TG(true, false); }
+    else { if (l1d) LAUNCH_TG(false, true); else LAUNCH_TG(false, false); }
+#undef LAUNCH_TG
+  }
+  c->launches++;
+  CU(c, cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

@@ -161,6 +161,35 @@ void b200vfx_blockhash_bits(const uint32_t *sums, int hw, int hh, int width, int
                             uint8_t *bits_out);
 int b200vfx_hash_distance(const uint8_t *bits_a, const uint8_t *bits_b, int nbits);
 
+/* ---- multi-GPU: colorlut on a row tile fused with the all-gather of the tiles over peer memory --------
+ * The reference has no multi-device path; 8(e) shards the frame into contiguous row tiles (one process per GPU) and asks
+ * for one in-place all-gather when a DEVICE-side consumer wants the whole frame.  These entry points replace
+ * "tile kernel + ncclAllGather" by ONE kernel that stores its results into every rank's frame buffer over NVLink.
+ *
+ * Buffers that peers write into must come from b200vfx_peer_alloc (plain cudaMalloc + a CUDA IPC handle the owner sends
+ * to the other processes through any channel it likes, e.g. torch.distributed.all_gather_object); a peer maps it with
+ * b200vfx_peer_open.  Within one process, b200vfx_peer_enable_access + the raw pointers do the same.
+ * A flag block is B200VFX_PEER_FLAG_BYTES of zero-initialised peer memory per rank (b200vfx_peer_alloc zeroes). */
+#define B200VFX_IPC_HANDLE_BYTES 64
+#define B200VFX_MAX_PEERS 16
+#define B200VFX_PEER_FLAG_BYTES 256
+int b200vfx_peer_alloc(b200vfx_ctx *ctx, size_t bytes, void **dev_ptr, unsigned char handle_out[B200VFX_IPC_HANDLE_BYTES]);
+int b200vfx_peer_free(b200vfx_ctx *ctx, void *dev_ptr);
+int b200vfx_peer_open(b200vfx_ctx *ctx, const unsigned char handle[B200VFX_IPC_HANDLE_BYTES], void **dev_ptr);
+int b200vfx_peer_close(b200vfx_ctx *ctx, void *dev_ptr);
+int b200vfx_peer_enable_access(b200vfx_ctx *ctx, int peer_device);
+/* synchronises the context stream and reports the epoch of the last call whose peer wait timed out (0 = none) */
+int b200vfx_peer_status(b200vfx_ctx *ctx, const void *flags, uint32_t *error_epoch);
+/* ColorLut::transform_frame (video/colorlut/src/colorlut/imp.rs:204-235, RGBA arm :267-294) on rows
+ * [frame_row0, frame_row0 + tile_rows) of the frame: reads the tile from src (device memory of this rank), writes the
+ * result into frames[p] + frame_row0 * frame_stride for every p in [0, world) (frames[rank] is this rank's own buffer).
+ * Asynchronous on the context stream; when it completes there, ALL ranks' tiles of this epoch are visible in
+ * frames[rank].  epoch must be > 0, identical on all ranks for one frame and increase by one per call.
+ * RGBA + memo mode only (B200VFX_ERR_UNSUPPORTED otherwise). */
+int b200vfx_colorlut_process_tile_gather(b200vfx_ctx *ctx, int fmt, int width, int tile_rows, const void *src,
+                                         int src_stride, int world, int rank, void *const *frames, int frame_stride,
+                                         int frame_row0, void *const *flags, uint32_t epoch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""torchrun check + timing of the fused colorlut/all-gather kernel (b200vfx_colorlut_process_tile_gather) on N real GPUs,
+one process per GPU, BASELINE config 5 shape (colorlut 65^3 on a 7680x4320 RGBA frame, row-tiled):
+  1. every rank compares its whole reassembled frame bit for bit with the CPU oracle (single- and double-buffered,
+     several epochs, a different frame per epoch);
+  2. device time per frame (CUDA events, max over ranks) of  (a) tile kernel alone, (b) tile kernel + in-place
+     ncclAllGather, (c) the fused kernel -- one JSON line from rank 0.
+    torchrun --nproc-per-node 8 scripts/tile_gather_check.py [--small]"""
+import argparse, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gst-plugin-rs_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+import numpy as np, torch, torch.distributed as dist
+import b200vfx, oracle_binding as orc
+from b200vfx import sharding, synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--small", action="store_true", help="1080p frame, fewer iterations (quick protocol check)")
+ap.add_argument("--iters", type=int, default=100)
+a = ap.parse_args()
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+W, H = (1920, 1080) if a.small else (7680, 4320)
+cube = orc.cube_parse(synth.cube_text_3d(65, "mix"))
+ctx = b200vfx.Context(local)
+ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+ctx.set_option("peer_timeout_ms", 5000)
+ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+r0, r1 = sharding.row_range(H, world, rank)
+rows = r1 - r0
+
+# ---- 1. parity ---------------------------------------------------------------------------------
+ok = True
+gens = [lambda: synth.frame_natural("RGBA", W, H, 0x5EED0005), lambda: synth.frame_noise("RGBA", W, H, 0x5EED0015),
+        lambda: synth.frame_ramps("RGBA", W, H)]
+frames_np = [g() for g in gens]
+exps = [orc.colorlut_apply(cube, "RGBA", W, H, f, threads=16) for f in frames_np]
+tiles = [torch.from_numpy(f[r0:r1].copy()).cuda() for f in frames_np]
+for nbuf, path in ((1, 0), (2, 0), (1, 1), (2, 1)):
+    ctx.set_option("tile_gather_path", path)
+    pf = sharding.PeerFrames(ctx, dist, H, 4 * W, nbuf=nbuf)
+    for e in range(6):   # back to back, no host synchronisation between epochs: the entry handshake orders buffer reuse
+        k = pf.process(W, tiles[e % 3], 4 * W)
+        got = torch.as_tensor(pf.frame(k), device="cuda").clone()   # stream-ordered consumer of the gathered frame
+        good = bool((got.cpu().numpy() == exps[e % 3]).all())
+        ok = ok and good
+    ok = ok and pf.status() == 0
+    pf.close()
+print("rank %d/%d rows [%d,%d): fused tile-gather frame == oracle (STG and TMA variants, nbuf 1 and 2, 6 epochs each): %s" % (rank, world, r0, r1, ok), flush=True)
+
+# ---- 2. timing -----------------------------------------------------------------------------------
+def dev_time(fn, iters, warm=10):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize(); dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(iters):
+        fn(i)
+    e.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e) * 1e-3 / iters], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+R = 4
+d_in = [tiles[0], tiles[1], tiles[2], tiles[1]]
+d_out = [torch.empty_like(d_in[0]) for _ in range(R)]
+full = torch.empty((H, 4 * W), dtype=torch.uint8, device="cuda")
+pf = sharding.PeerFrames(ctx, dist, H, 4 * W, nbuf=2)
+
+def k_only(i):
+    ctx.colorlut_process("RGBA", W, rows, d_in[i % R], 4 * W, d_out[i % R], 4 * W)
+
+def k_nccl(i):   # tile kernel writes straight into its slot of the frame, then ONE in-place all-gather
+    slot = full[r0:r1]
+    ctx.colorlut_process("RGBA", W, rows, d_in[i % R], 4 * W, slot, 4 * W)
+    dist.all_gather_into_tensor(full.view(-1), slot.reshape(-1))
+
+def k_fused(i):
+    pf.process(W, d_in[i % R], 4 * W)
+
+even = H % world == 0
+t_k = dev_time(k_only, a.iters)
+t_n = dev_time(k_nccl, a.iters) if even else float("nan")
+variants = {}
+for name, opts in (("stg_ctas8", (0, 0, 8)), ("stg_ctas4", (0, 0, 4)), ("stg_ctas2", (0, 0, 2)), ("tma_16k", (1, 0, 0)),
+                   ("tma_8k", (1, 1, 0)), ("tma_4k", (1, 2, 0)), ("tma_32k", (1, 3, 0)), ("tma_16k_1cta", (1, 0, 1))):
+    ctx.set_option("tile_gather_path", opts[0]); ctx.set_option("tile_gather_cfg", opts[1]); ctx.set_option("tile_gather_ctas", opts[2] or (8 if opts[0] == 0 else 0))
+    variants[name] = round(dev_time(k_fused, a.iters) * 1e6, 1)
+best = min(variants, key=variants.get)
+t_f = variants[best] * 1e-6
+err = pf.status()
+pf.close()
+if rank == 0:
+    recv = 4 * W * rows * (world - 1)
+    print(json.dumps({"what": "colorlut 65^3, %dx%d RGBA row-tiled over %d GPUs (%d rows each), whole frame wanted on every GPU" % (W, H, world, rows),
+                      "tile_kernel_us": round(t_k * 1e6, 1), "kernel_plus_nccl_allgather_us": round(t_n * 1e6, 1),
+                      "fused_tile_gather_us": round(t_f * 1e6, 1), "fused_variant": best, "fused_variants_us": variants, "speedup_vs_nccl": round(t_n / t_f, 2),
+                      "frames_per_s_nccl": round(1 / t_n), "frames_per_s_fused": round(1 / t_f),
+                      "recv_bytes_per_gpu": recv, "fused_recv_GBps_per_gpu": round(recv / t_f / 1e9, 1),
+                      "nccl_recv_GBps_per_gpu": round(recv / t_n / 1e9, 1), "timeouts": err, "parity": ok}), flush=True)
+ctx.close()
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok and err == 0 else 1)
