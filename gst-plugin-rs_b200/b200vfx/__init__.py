@@ -23,7 +23,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NOT_NEGOTIATED, ERR_UNSUPPORTED, ERR_PARSE, ERR_I
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-SOURCES = ["csrc/b200vfx.cu", "csrc/cube_parser.cpp", "csrc/elements.cpp"]
+SOURCES = ["csrc/b200vfx.cu", "csrc/cube_parser.cpp", "csrc/elements.cpp", "csrc/colordetect_host.cpp"]
 
 
 class B200VfxError(RuntimeError):
@@ -86,8 +86,12 @@ def lib() -> C.CDLL:
         "b200vfx_hsvdetector_process": ([vp, ci, ci, ci, ci, vp, ci, vp, ci] + [cf] * 6, ci),
         "b200vfx_roundmask_generate": ([vp, ci, ci, ci, cu, vp], ci),
         "b200vfx_blockhash_sums": ([vp, ci, ci, ci, vp, ci, ci, ci, vp], ci),
+        "b200vfx_blockhash_sums_batch": ([vp, ci, ci, ci, ci, C.POINTER(vp), C.POINTER(ci), ci, ci, vp], ci),
         "b200vfx_blockhash_bits": ([vp, ci, ci, ci, ci, vp], None),
         "b200vfx_hash_distance": ([vp, vp, ci], ci),
+        "b200vfx_colordetect_histogram": ([vp, ci, ci, ci, vp, ci, ci, vp], ci),
+        "b200vfx_colordetect_palette": ([vp, ci, vp, ci, C.POINTER(ci)], ci),
+        "b200vfx_css_color_similar": ([cu, cu, cu], C.c_char_p),
         "b200vfx_peer_alloc": ([vp, C.c_size_t, C.POINTER(vp), C.c_char_p], ci),
         "b200vfx_peer_free": ([vp, vp], ci),
         "b200vfx_peer_open": ([vp, C.c_char_p, C.POINTER(vp)], ci),
@@ -270,6 +274,31 @@ class Context:
 
     def blockhash_sums(self, fmt, width, height, src, stride, sums, hw=8, hh=8):
         self._chk(lib().b200vfx_blockhash_sums(self._h, FMT[fmt], width, height, _ptr(src), stride, hw, hh, _ptr(sums)))
+
+    def blockhash_sums_batch(self, fmt, width, height, srcs, strides, sums, hw=8, hh=8):
+        n = len(srcs)
+        ptrs = (C.c_void_p * n)(*[_ptr(x) for x in srcs])
+        st = (C.c_int * n)(*strides)
+        self._chk(lib().b200vfx_blockhash_sums_batch(self._h, FMT[fmt], width, height, n, ptrs, st, hw, hh, _ptr(sums)))
+
+    def colordetect_histogram(self, fmt, width, height, src, stride, quality, hist):
+        self._chk(lib().b200vfx_colordetect_histogram(self._h, FMT[fmt], width, height, _ptr(src), stride, quality, _ptr(hist)))
+
+
+def colordetect_palette(hist, max_colors):
+    """-> list of (r, g, b), most significant first (host-side median cut of the product library)"""
+    import numpy as np
+    h = np.ascontiguousarray(hist, np.uint32)
+    pal = np.zeros(3 * 600, np.uint8)
+    n = C.c_int()
+    rc = lib().b200vfx_colordetect_palette(h.ctypes.data, max_colors, pal.ctypes.data, 600, C.byref(n))
+    if rc != 0:
+        raise B200VfxError(rc, "colordetect_palette: invalid argument")
+    return [tuple(int(v) for v in pal[3 * i:3 * i + 3]) for i in range(min(n.value, 600))]
+
+
+def css_color_similar(r, g, b) -> str:
+    return lib().b200vfx_css_color_similar(int(r), int(g), int(b)).decode()
 
 
 def blockhash_bits(sums, width, height, hw=8, hh=8):

@@ -24,6 +24,7 @@
 #include "stream_map.cuh"
 #include "blockhash_tma.cuh"
 #include "tile_gather.cuh"
+#include "colordetect.cuh"
 
 using namespace b200vfx;
 
@@ -73,6 +74,7 @@ struct b200vfx_ctx {
   int stream_cfg = 0, stream_ctas = 0, stream_hint = 1, memo_px = 8;  // tuning knobs (env overrides, see ctx_create)
   uint64_t launches = 0;
   int tg_path = 0, tg_cfg = 0, tg_ctas = 8;   // fused tile gather: 0 register path (LDG/STG), 1 TMA; variant; CTAs per SM
+  int cd_cluster = 2;    // colordetect: CTAs per cluster merging their shared-memory histograms (1, 2, 4, 8)
   int peer_timeout_ms = 2000;  // deadline of the cross-GPU waits in the tile-gather kernel
   std::string err;
 
@@ -500,6 +502,20 @@ int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings 
     CU(c, cudaGetLastError());
     return 0;
   }
+  if (memo && fi.bpp == 3 && aligned(data, stride, 4)) {  // RGB / BGR through the same table: map_rgb24_kernel
+    int ww = w, hh = h;
+    long ss = stride;
+    if (ss == 3L * w && (3LL * w * h) % 4 == 0 && (long long)w * h < (1LL << 28)) { ww = w * h; hh = 1; }
+    const Span sp = span_of(data, stride, (size_t)w * 3, h);
+    const bool pdl = pdl_admit(c->pdl && !built_now, st, sp, sp);
+    constexpr int G = 2;
+    dim3 grid((unsigned)ceil_div(ceil_div(ww, 4), 32 * G * 8), grid_rows(hh));
+    if (fi.bgr) CU(c, launch_k(pdl, map_rgb24_kernel<HsvFilterMemoOp<0, true>, G, false, false>, grid, dim3(256), 0, st, HsvFilterMemoOp<0, true>{memo}, (const uint8_t *)data, ss, data, ss, ww, hh));
+    else CU(c, launch_k(pdl, map_rgb24_kernel<HsvFilterMemoOp<0, false>, G, false, false>, grid, dim3(256), 0, st, HsvFilterMemoOp<0, false>{memo}, (const uint8_t *)data, ss, data, ss, ww, hh));
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return 0;
+  }
   pdl_admit(false, st, Span{0, 0}, Span{0, 0});  // plain launch: waits for, and is waited on by, everything around it
   if (fi.bpp == 3) { if (fi.bgr) launch_hsvfilter_t<3, 0, true>(s, memo, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<3, 0, false>(s, memo, data, stride, w, h, st, c->sm_count); }
   else if (fi.coff == 0) { if (fi.bgr) launch_hsvfilter_t<4, 0, true>(s, memo, data, stride, w, h, st, c->sm_count); else launch_hsvfilter_t<4, 0, false>(s, memo, data, stride, w, h, st, c->sm_count); }
@@ -563,6 +579,23 @@ int launch_hsvdetector(b200vfx_ctx *c, const FmtInfo &fi, const FmtInfo &fo, con
       else { if (fi.bgr) LD2(1, true); else LD2(1, false); }
 #undef LD2
 #undef LD
+      c->launches++;
+      CU(c, cudaGetLastError());
+      return 0;
+    }
+    if (fi.bpp == 3 && aligned(f.src, f.sstride, 4) && aligned(f.dst, f.dstride, 4)) {  // RGB / BGR in: map_rgb24_kernel
+      int ww = f.width, hh = f.height;
+      if (f.sstride == 3L * ww && f.dstride == 4L * ww && (3LL * ww * hh) % 4 == 0 && (long long)ww * hh < (1LL << 28)) { ww = ww * hh; hh = 1; }
+      constexpr int G = 2;
+      dim3 grid((unsigned)ceil_div(ceil_div(ww, 4), 32 * G * 8), grid_rows(hh));
+      const bool d16 = aligned(f.dst, f.dstride, 16);
+#define LD3(IB, OC, OB) do { using OpT = HsvDetectBitmapOp<0, IB, OC, OB>; \
+        if (d16) CU(c, launch_k(pdl, map_rgb24_kernel<OpT, G, true, true>, grid, dim3(256), 0, st, OpT{bitmap}, f.src, f.sstride, f.dst, f.dstride, ww, hh)); \
+        else CU(c, launch_k(pdl, map_rgb24_kernel<OpT, G, true, false>, grid, dim3(256), 0, st, OpT{bitmap}, f.src, f.sstride, f.dst, f.dstride, ww, hh)); } while (0)
+#define LD32(IB) do { if (fo.coff == 0) { if (fo.bgr) LD3(IB, 0, true); else LD3(IB, 0, false); } else { if (fo.bgr) LD3(IB, 1, true); else LD3(IB, 1, false); } } while (0)
+      if (fi.bgr) LD32(true); else LD32(false);
+#undef LD32
+#undef LD3
       c->launches++;
       CU(c, cudaGetLastError());
       return 0;
@@ -797,6 +830,7 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "peer_timeout_ms") c->peer_timeout_ms = value > 0 ? value : 1;
   else if (n == "zero_copy") { c->zero_copy = value; c->zc_calls = 0; c->zc_best_ms[0] = c->zc_best_ms[1] = 1e30; }
   else if (n == "blockhash_tma") c->blockhash_tma = value != 0;
+  else if (n == "cd_cluster") c->cd_cluster = (value == 1 || value == 2 || value == 4 || value == 8) ? value : 2;
   else if (n == "l2_persist") c->l2_persist = value;
   else if (n == "zc_cfg") c->zc_cfg = value;
   else if (n == "zc_hybrid") c->zc_hybrid = value;
@@ -1014,66 +1048,84 @@ int b200vfx_roundmask_generate(b200vfx_ctx *c, int width, int height, int stride
 }
 
 // ---- videocompare / blockhash -----------------------------------------------------------------
-int b200vfx_blockhash_sums(b200vfx_ctx *c, int fmt, int width, int height, const void *src, int stride, int hw,
-                           int hh, uint32_t *sums) {
+int b200vfx_blockhash_sums_batch(b200vfx_ctx *c, int fmt, int width, int height, int n_frames, const void *const *srcs,
+                                 const int *strides, int hw, int hh, uint32_t *sums) {
   if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
   if (fmt != B200VFX_FORMAT_RGB && fmt != B200VFX_FORMAT_RGBA)
     return fail(c, B200VFX_ERR_UNSUPPORTED, "videocompare: format %d is not RGB / RGBA", fmt);
   if (hw <= 0 || hh <= 0 || hw > 4096 || hh > 4096 || !sums) return fail(c, B200VFX_ERR_INVALID, "blockhash: bad hash size");
+  if (n_frames < 1 || n_frames > kBlockhashMaxFrames || !srcs || !strides)
+    return fail(c, B200VFX_ERR_INVALID, "blockhash: 1..%d frames per call", kBlockhashMaxFrames);
   const int bpp = fmt == B200VFX_FORMAT_RGB ? 3 : 4;
   const size_t row = (size_t)width * bpp;
-  if (int rc = check_frame(c, width, height, src, stride, row, nullptr, 0, 0)) return rc;
+  for (int f = 0; f < n_frames; f++)
+    if (int rc = check_frame(c, width, height, srcs[f], strides[f], row, nullptr, 0, 0)) return rc;
   if (width <= 0 || height <= 0 || width % hw || height % hh)
     return fail(c, B200VFX_ERR_UNSUPPORTED,
                 "blockhash: %dx%d is not a multiple of the %dx%d hash grid (image_hasher's fractional-weight path is not implemented)",
                 width, height, hw, hh);
   DeviceGuard g(c->device);
   const int bw = width / hw, bh = height / hh;
-  const bool src_dev = is_device_ptr(src), sums_dev = is_device_ptr(sums);
-  cudaStream_t st = src_dev ? c->stream() : c->s_k;
-  const uint8_t *d_src = (const uint8_t *)src;
-  long d_stride = stride;
-  if (!src_dev) {  // upload (chunked so the copy engine and the reduction overlap is not needed: single pass, copy-bound)
-    d_stride = (long)((row + 15) & ~(size_t)15);
-    CU(c, c->stage_in.reserve((size_t)d_stride * height));
-    if ((size_t)stride == row && (size_t)d_stride == row)
-      CU(c, cudaMemcpyAsync(c->stage_in.p, src, row * (size_t)height, cudaMemcpyHostToDevice, st));
+  bool all_dev = true, on_dev[kBlockhashMaxFrames];
+  for (int f = 0; f < n_frames; f++) { on_dev[f] = is_device_ptr(srcs[f]); all_dev = all_dev && on_dev[f]; }
+  const bool sums_dev = is_device_ptr(sums);
+  cudaStream_t st = all_dev ? c->stream() : c->s_k;
+  BlockhashFrames fr{};
+  const long staged_stride = (long)((row + 15) & ~(size_t)15);
+  size_t staged = 0;
+  for (int f = 0; f < n_frames; f++) if (!on_dev[f]) staged++;
+  if (staged) CU(c, c->stage_in.reserve((size_t)staged_stride * height * staged));
+  size_t slot = 0;
+  for (int f = 0; f < n_frames; f++) {
+    if (on_dev[f]) { fr.src[f] = (const uint8_t *)srcs[f]; fr.stride[f] = strides[f]; continue; }
+    uint8_t *dp = c->stage_in.p + (size_t)staged_stride * height * slot++;   // single pass, copy-bound: no chunking
+    if ((size_t)strides[f] == row && (size_t)staged_stride == row)
+      CU(c, cudaMemcpyAsync(dp, srcs[f], row * (size_t)height, cudaMemcpyHostToDevice, st));
     else
-      CU(c, cudaMemcpy2DAsync(c->stage_in.p, (size_t)d_stride, src, (size_t)stride, row, (size_t)height, cudaMemcpyHostToDevice, st));
-    d_src = c->stage_in.p;
+      CU(c, cudaMemcpy2DAsync(dp, (size_t)staged_stride, srcs[f], (size_t)strides[f], row, (size_t)height, cudaMemcpyHostToDevice, st));
+    fr.src[f] = dp; fr.stride[f] = staged_stride;
   }
+  for (int f = n_frames; f < kBlockhashMaxFrames; f++) { fr.src[f] = fr.src[0]; fr.stride[f] = fr.stride[0]; }
   uint32_t *d_sums = sums;
-  const size_t nb = sizeof(uint32_t) * (size_t)hw * hh;
+  const int nbins = hw * hh * n_frames;
+  const size_t nb = sizeof(uint32_t) * (size_t)nbins;
   if (!sums_dev) { CU(c, c->stage_sums.reserve(nb)); d_sums = (uint32_t *)c->stage_sums.p; }
   pdl_admit(false, st, Span{0, 0}, Span{0, 0});
-  CU(c, cudaMemsetAsync(d_sums, 0, nb, st));
-  // rows per CTA: aim for >= ~8 CTAs per SM
+  // rows per CTA: aim for >= ~8 CTAs per SM over the whole batch
   int rows_per_cta = bh;
-  const long ctas_target = 148L * 8;
-  if ((long)hw * hh < ctas_target) rows_per_cta = std::max(1, (int)((long)bh * hw * hh / ctas_target));
-  dim3 grid((unsigned)hw, (unsigned)hh, (unsigned)ceil_div(bh, rows_per_cta));
-  const bool vec = bpp == 4 && (bw % 4) == 0 && aligned(d_src, d_stride, 16);
-  if (vec && c->blockhash_tma) {  // TMA-fed variant: whole tile in flight through cp.async.bulk, tile <= 32 KB
+  const long ctas_target = (long)c->sm_count * 8;
+  if ((long)hw * hh * n_frames < ctas_target) rows_per_cta = std::max(1, (int)((long)bh * hw * hh * n_frames / ctas_target));
+  const int zchunks = ceil_div(bh, rows_per_cta);
+  dim3 grid((unsigned)hw, (unsigned)hh, (unsigned)(zchunks * n_frames));
+  bool vec = bpp == 4 && (bw % 4) == 0;
+  for (int f = 0; f < n_frames; f++) vec = vec && aligned(fr.src[f], fr.stride[f], 16);
+  if (vec && c->blockhash_tma && n_frames == 1 && bw * 4 <= kBlockhashTileBytes) {
+    // TMA-fed variant (option "blockhash_tma"): whole tile in flight through cp.async.bulk, tile <= 32 KB
+    CU(c, cudaMemsetAsync(d_sums, 0, nb, st));
     const int rows_tma = std::max(1, std::min(rows_per_cta, kBlockhashTileBytes / (bw * 4)));
-    if (bw * 4 <= kBlockhashTileBytes) {
-      dim3 g2((unsigned)hw, (unsigned)hh, (unsigned)ceil_div(bh, rows_tma));
-      blockhash_sums_tma_kernel<<<g2, 128, (size_t)rows_tma * bw * 4, st>>>(d_src, d_stride, bw, bh, hw, rows_tma, d_sums);
-    } else {
-      blockhash_sums_kernel<4, true><<<grid, 128, 0, st>>>(d_src, d_stride, bw, bh, hw, rows_per_cta, d_sums);
-    }
+    dim3 g2((unsigned)hw, (unsigned)hh, (unsigned)ceil_div(bh, rows_tma));
+    blockhash_sums_tma_kernel<<<g2, 128, (size_t)rows_tma * bw * 4, st>>>(fr.src[0], fr.stride[0], bw, bh, hw, rows_tma, d_sums);
+  } else {
+    blockhash_zero_kernel<<<ceil_div(nbins, 256), 256, 0, st>>>(d_sums, nbins);   // PDL primary of the reduction
+    c->launches++;
+    if (vec) CU(c, launch_k(c->pdl, blockhash_sums_kernel<4, true>, grid, dim3(128), 0, st, fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums));
+    else if (bpp == 4) CU(c, launch_k(c->pdl, blockhash_sums_kernel<4, false>, grid, dim3(128), 0, st, fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums));
+    else CU(c, launch_k(c->pdl, blockhash_sums_kernel<3, false>, grid, dim3(128), 0, st, fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums));
   }
-  else if (vec) blockhash_sums_kernel<4, true><<<grid, 128, 0, st>>>(d_src, d_stride, bw, bh, hw, rows_per_cta, d_sums);
-  else if (bpp == 4) blockhash_sums_kernel<4, false><<<grid, 128, 0, st>>>(d_src, d_stride, bw, bh, hw, rows_per_cta, d_sums);
-  else blockhash_sums_kernel<3, false><<<grid, 128, 0, st>>>(d_src, d_stride, bw, bh, hw, rows_per_cta, d_sums);
   c->launches++;
   CU(c, cudaGetLastError());
   if (!sums_dev) {
     CU(c, cudaMemcpyAsync(sums, d_sums, nb, cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));
-  } else if (!src_dev) {
+  } else if (!all_dev) {
     CU(c, cudaStreamSynchronize(st));
   }
   return 0;
+}
+
+int b200vfx_blockhash_sums(b200vfx_ctx *c, int fmt, int width, int height, const void *src, int stride, int hw,
+                           int hh, uint32_t *sums) {
+  return b200vfx_blockhash_sums_batch(c, fmt, width, height, 1, &src, &stride, hw, hh, sums);
 }
 
 void b200vfx_blockhash_bits(const uint32_t *sums, int hw, int hh, int width, int height, uint8_t *bits_out) {
@@ -1100,6 +1152,111 @@ int b200vfx_hash_distance(const uint8_t *a, const uint8_t *b, int nbits) {
   int d = 0;
   for (int i = 0; i < nbits; i++) d += (a[i] != 0) != (b[i] != 0);
   return d;
+}
+
+// ---- colordetect ----------------------------------------------------------------------------------
+int b200vfx_colordetect_histogram(b200vfx_ctx *c, int fmt, int width, int height, const void *src, int stride,
+                                  int quality, uint32_t *hist) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  int bpp, fi;
+  switch (fmt) {  // color_parts() of color-thief per ColorFormat (set_info, colordetect/imp.rs:268-275)
+    case B200VFX_FORMAT_RGB: fi = 0; bpp = 3; break;
+    case B200VFX_FORMAT_RGBA: fi = 1; bpp = 4; break;
+    case B200VFX_FORMAT_ARGB: fi = 2; bpp = 4; break;
+    case B200VFX_FORMAT_BGR: fi = 3; bpp = 3; break;
+    case B200VFX_FORMAT_BGRA: fi = 4; bpp = 4; break;
+    default: return fail(c, B200VFX_ERR_UNSUPPORTED, "colordetect: format %d is not RGB / RGBA / ARGB / BGR / BGRA", fmt);
+  }
+  if (!hist) return fail(c, B200VFX_ERR_INVALID, "colordetect: null histogram");
+  if (quality < 1 || quality > 10) return fail(c, B200VFX_ERR_INVALID, "colordetect: quality %d outside 1..10 (color-thief range check)", quality);
+  const size_t row = (size_t)width * bpp;
+  if (int rc = check_frame(c, width, height, src, stride, row, nullptr, 0, 0)) return rc;
+  DeviceGuard g(c->device);
+  // the reference samples the FLAT plane slice: stride * height bytes, pixel i at byte i * bpp
+  const size_t plane_bytes = (width > 0 && height > 0) ? (size_t)stride * (size_t)height : 0;
+  const long long npix = (long long)(plane_bytes / (size_t)bpp);
+  const long long nsamples = (npix + quality - 1) / quality;
+  const bool src_dev = plane_bytes == 0 || is_device_ptr(src), hist_dev = is_device_ptr(hist);
+  cudaStream_t st = src_dev ? c->stream() : c->s_k;
+  const uint8_t *d_src = (const uint8_t *)src;
+  if (!src_dev) {
+    CU(c, c->stage_in.reserve(plane_bytes));
+    CU(c, cudaMemcpyAsync(c->stage_in.p, src, plane_bytes, cudaMemcpyHostToDevice, st));
+    d_src = c->stage_in.p;
+  }
+  uint32_t *d_hist = hist;
+  const size_t nb = sizeof(uint32_t) * kColorDetectBins;
+  if (!hist_dev) { CU(c, c->stage_sums.reserve(nb)); d_hist = (uint32_t *)c->stage_sums.p; }
+  if (((uintptr_t)d_hist % 4) != 0) return fail(c, B200VFX_ERR_INVALID, "colordetect: histogram pointer is not 4-byte aligned");
+  pdl_admit(false, st, Span{0, 0}, Span{0, 0});
+  colordetect_zero_kernel<<<kColorDetectBins / 256, 256, 0, st>>>(d_hist);   // PDL primary of the histogram kernel
+  c->launches++;
+  CU(c, cudaGetLastError());
+  if (nsamples > 0) {
+    const int mode = (bpp == 4 && quality == 1 && ((uintptr_t)d_src % 16) == 0) ? 2 : ((bpp == 4 && ((uintptr_t)d_src % 4) == 0) ? 1 : 0);
+    using KernelT = void (*)(const uint8_t *, long long, int, uint32_t *);
+    static const KernelT table[5][3] = {
+        {colordetect_hist_kernel<0, 0>, nullptr, nullptr},
+        {colordetect_hist_kernel<1, 0>, colordetect_hist_kernel<1, 1>, colordetect_hist_kernel<1, 2>},
+        {colordetect_hist_kernel<2, 0>, colordetect_hist_kernel<2, 1>, colordetect_hist_kernel<2, 2>},
+        {colordetect_hist_kernel<3, 0>, nullptr, nullptr},
+        {colordetect_hist_kernel<4, 0>, colordetect_hist_kernel<4, 1>, colordetect_hist_kernel<4, 2>}};
+    const KernelT k = table[fi][mode];
+    const int cluster = (c->cd_cluster == 1 || c->cd_cluster == 2 || c->cd_cluster == 4 || c->cd_cluster == 8) ? c->cd_cluster : 2;
+    // per (device, cluster size): opt in to 128 KB dynamic shared memory once, and ask how many clusters are co-resident
+    static std::mutex mu;
+    static bool attr_set[64] = {false};
+    static int max_ctas[64][9] = {{0}};
+    const int dev = (c->device >= 0 && c->device < 64) ? c->device : 0;
+    int resident = 0;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (!attr_set[dev]) {
+        for (int a = 0; a < 5; a++)
+          for (int b = 0; b < 3; b++)
+            if (table[a][b]) CU(c, cudaFuncSetAttribute(table[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nb));
+        attr_set[dev] = true;
+      }
+      if (max_ctas[dev][cluster] == 0) {
+        int n = c->sm_count / cluster;
+        if (cluster > 1) {
+          cudaLaunchConfig_t q = {};
+          q.gridDim = dim3((unsigned)(c->sm_count - c->sm_count % cluster)); q.blockDim = dim3(kColorDetectThreads); q.dynamicSmemBytes = nb;
+          cudaLaunchAttribute qa[1];
+          qa[0].id = cudaLaunchAttributeClusterDimension;
+          qa[0].val.clusterDim.x = (unsigned)cluster; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+          q.attrs = qa; q.numAttrs = 1;
+          int nc = 0;
+          if (cudaOccupancyMaxActiveClusters(&nc, k, &q) == cudaSuccess && nc > 0) n = std::min(n, nc); else cudaGetLastError();
+        }
+        max_ctas[dev][cluster] = std::max(1, n) * cluster;
+      }
+      resident = max_ctas[dev][cluster];
+    }
+    const long long units = mode == 2 ? (nsamples >> 2) : nsamples;
+    const long long per_cta = (long long)kColorDetectThreads * 4;
+    unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(resident, (units + per_cta - 1) / per_cta));
+    const unsigned cl = grid >= (unsigned)cluster ? (unsigned)cluster : 1u;
+    grid -= grid % cl;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kColorDetectThreads); cfg.dynamicSmemBytes = nb; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    CU(c, cudaLaunchKernelEx(&cfg, k, d_src, nsamples, quality, d_hist));
+    c->launches++;
+    CU(c, cudaGetLastError());
+  }
+  if (!hist_dev) {
+    CU(c, cudaMemcpyAsync(hist, d_hist, nb, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+  } else if (!src_dev) {
+    CU(c, cudaStreamSynchronize(st));
+  }
+  return 0;
 }
 
 // ---- multi-GPU tile gather (tile_gather.cuh) ----------------------------------------------------

@@ -291,9 +291,8 @@ struct VideoCompare : b200gst_element {  // video/videofx/src/videocompare/imp.r
       for (int y = 0; y < ref->height; y++)
         std::memcpy((uint8_t *)out->data[0] + (size_t)y * out->stride[0], (const uint8_t *)ref->data[0] + (size_t)y * ref->stride[0], row);
     }
-    std::vector<uint8_t> ref_bits, bits;
-    if (int rc = hash(*ref, ref_bits)) return rc;
-    std::vector<std::pair<int, double>> distances;
+    // collect the other pads' frames first (the size check of :337-346 precedes any hashing of that pad)
+    std::vector<std::pair<int, const b200gst_video_frame *>> others;
     for (int p : pads) {
       if (p == reference_pad) continue;
       const b200gst_video_frame *fr = nullptr;
@@ -301,8 +300,34 @@ struct VideoCompare : b200gst_element {  // video/videofx/src/videocompare/imp.r
       if (!fr) return B200GST_FLOW_OK;  // :326-329
       if (fr->width != ref->width || fr->height != ref->height)
         return fail(B200GST_FLOW_NOT_NEGOTIATED, "Video streams do not have the same sizes (add videoscale and force the sizes to be equal on all sink pads)");
-      if (int rc = hash(*fr, bits)) return rc;
-      distances.push_back({p, (double)b200vfx_hash_distance(ref_bits.data(), bits.data(), 64)});
+      others.push_back({p, fr});
+    }
+    std::vector<std::pair<int, double>> distances;
+    bool same_fmt = true;
+    for (auto &o : others) same_fmt = same_fmt && o.second->format == ref->format;
+    if ((int)values["hash-algo"].d == 4 && same_fmt && !others.empty() && others.size() + 1 <= B200VFX_BLOCKHASH_MAX_FRAMES) {
+      // one launch hashes the reference frame and every other pad's frame
+      const int nf = (int)others.size() + 1;
+      const void *srcs[B200VFX_BLOCKHASH_MAX_FRAMES];
+      int strides[B200VFX_BLOCKHASH_MAX_FRAMES];
+      srcs[0] = ref->data[0]; strides[0] = ref->stride[0];
+      for (int i = 1; i < nf; i++) { srcs[i] = others[(size_t)i - 1].second->data[0]; strides[i] = others[(size_t)i - 1].second->stride[0]; }
+      std::vector<uint32_t> sums((size_t)64 * nf);
+      if (b200vfx_blockhash_sums_batch(ctx, ref->format, ref->width, ref->height, nf, srcs, strides, 8, 8, sums.data()) != 0)
+        return ctx_error(B200GST_FLOW_ERROR);
+      std::vector<uint8_t> ref_bits(64), bits(64);
+      b200vfx_blockhash_bits(sums.data(), 8, 8, ref->width, ref->height, ref_bits.data());
+      for (int i = 1; i < nf; i++) {
+        b200vfx_blockhash_bits(sums.data() + (size_t)64 * i, 8, 8, ref->width, ref->height, bits.data());
+        distances.push_back({others[(size_t)i - 1].first, (double)b200vfx_hash_distance(ref_bits.data(), bits.data(), 64)});
+      }
+    } else {
+      std::vector<uint8_t> ref_bits, bits;
+      if (int rc = hash(*ref, ref_bits)) return rc;
+      for (auto &o : others) {
+        if (int rc = hash(*o.second, bits)) return rc;
+        distances.push_back({o.first, (double)b200vfx_hash_distance(ref_bits.data(), bits.data(), 64)});
+      }
     }
     const double thr = values["max-dist-threshold"].d;
     bool any = false;
@@ -324,12 +349,64 @@ struct VideoCompare : b200gst_element {  // video/videofx/src/videocompare/imp.r
   }
 };
 
+// ---- colordetect ------------------------------------------------------------------------------
+struct ColorDetect : b200gst_element {  // video/videofx/src/colordetect/imp.rs
+  bool have_state = false;
+  int color_format = -1;
+  bool have_color = false;
+  std::string current_color;  // State::current_color survives set_info (:277-284), cleared by stop (:239-243)
+  std::vector<uint32_t> hist;
+  ColorDetect() {
+    factory = "colordetect"; type_name = "GstColorDetect"; plugin = "rsvideofx";
+    add_prop({"quality", PType::UInt, 10, 0, 10, "mutable-playing", {}});       // :126-133
+    add_prop({"max-colors", PType::UInt, 2, 2, 255, "mutable-playing", {}});    // :134-141
+  }
+  std::vector<int> pad_formats(int) const override {  // :214-222
+    return {B200VFX_FORMAT_RGB, B200VFX_FORMAT_RGBA, B200VFX_FORMAT_ARGB, B200VFX_FORMAT_BGR, B200VFX_FORMAT_BGRA};
+  }
+  int set_caps(int in_format, int, int, int) override {  // set_info :253-287
+    if (!contains(pad_formats(0), in_format)) return fail(-1, "unsupported format");
+    color_format = in_format;
+    have_state = true;
+    passthrough = true;  // PASSTHROUGH_ON_SAME_CAPS + TRANSFORM_IP_ON_PASSTHROUGH (:236-238)
+    return 0;
+  }
+  int stop() override { have_state = false; have_color = false; current_color.clear(); return b200gst_element::stop(); }
+  int transform_frame_ip(b200gst_video_frame *fr) override {  // transform_frame_ip_passthrough :289-298 -> detect_color :57-86
+    if (!have_state) return fail(B200GST_FLOW_NOT_NEGOTIATED, "Have no state yet");
+    if (!started) return fail(B200GST_FLOW_ERROR, "not started");
+    if (fr->format != color_format) return fail(B200GST_FLOW_NOT_NEGOTIATED, "format not negotiated");
+    hist.resize(B200VFX_COLORDETECT_BINS);
+    if (b200vfx_colordetect_histogram(ctx, fr->format, fr->width, fr->height, fr->data[0], fr->stride[0],
+                                      (int)values["quality"].d, hist.data()) != 0)
+      return ctx_error(B200GST_FLOW_ERROR);  // get_palette(..).map_err(|_| FlowError::Error)
+    uint8_t pal[3 * 600];
+    int n = 0;
+    if (b200vfx_colordetect_palette(hist.data(), (int)values["max-colors"].d, pal, 600, &n) != 0 || n < 1)
+      return fail(B200GST_FLOW_ERROR, "palette extraction failed");
+    const std::string name = b200vfx_css_color_similar(pal[0], pal[1], pal[2]);
+    if (!have_color || current_color != name) {  // color_changed :88-113
+      have_color = true;
+      current_color = name;
+      std::string m = "colordetect, dominant-color=(string)" + name + ", palette=(uint){ ";
+      for (int i = 0; i < n && i < 600; i++) {
+        const unsigned v = ((unsigned)pal[3 * i] << 16) | ((unsigned)pal[3 * i + 1] << 8) | pal[3 * i + 2];
+        m += std::to_string(v) + (i + 1 < n ? ", " : " ");
+      }
+      m += "};";
+      bus.push_back(m);
+    }
+    return B200GST_FLOW_OK;
+  }
+};
+
 b200gst_element *make(const std::string &n) {
   if (n == "colorlut") return new ColorLut();
   if (n == "hsvfilter") return new HsvFilter();
   if (n == "hsvdetector") return new HsvDetector();
   if (n == "roundedcorners") return new RoundedCorners();
   if (n == "videocompare") return new VideoCompare();
+  if (n == "colordetect") return new ColorDetect();
   return nullptr;
 }
 

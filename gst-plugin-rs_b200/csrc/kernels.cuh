@@ -348,6 +348,86 @@ __global__ void __launch_bounds__(256) map_u32_kernel(Op op, const uint8_t *__re
 }
 
 // --------------------------------------------------------------------------------------------
+// 3-byte pixels (RGB / BGR) through the same answer tables.  A warp owns 32*G groups of 4 pixels (= 3 words each):
+// the 96*G words are loaded with fully coalesced 128-byte instructions, staged in a per-warp shared-memory tile and
+// re-read at a stride of 3 words (3 is coprime with the 32 banks: conflict-free), so lane L holds 4 whole pixels per
+// group and issues 4*G independent gathers.  OUT4 = false: 3-byte result written back the same way (hsvfilter, in
+// place; bytes of the last word that lie beyond the row are read and written back unchanged).  OUT4 = true: 4-byte
+// output pixels, one 16-byte store per group (hsvdetector RGB/BGR input).  Rows must be 4-byte aligned.
+// --------------------------------------------------------------------------------------------
+template <typename Op, int G, bool OUT4, bool DST16>
+__global__ void __launch_bounds__(256) map_rgb24_kernel(Op op, const uint8_t *__restrict__ src, long sstride,
+                                                        uint8_t *dst, long dstride, int width, int height) {
+  pdl_trigger();
+  __shared__ uint32_t tile_all[8][96 * G];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t *tile = tile_all[warp];
+  const int ngroups = (width + 3) >> 2, nwords = (3 * width + 3) >> 2;
+  const int chunk = blockIdx.x * 8 + warp;             // one chunk of 32*G groups per warp
+  const int g0 = chunk * 32 * G;
+  if (g0 >= ngroups) return;
+  const int w0 = g0 * 3;
+  for (int row = blockIdx.y; row < height; row += gridDim.y) {
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)row * sstride);
+#pragma unroll
+    for (int j = 0; j < 3 * G; j++) {
+      const int wi = w0 + lane + 32 * j;
+      tile[lane + 32 * j] = wi < nwords ? ld_stream_u32(s + wi) : 0u;
+    }
+    __syncwarp();
+    uint32_t px[G][4], o[G][4];
+#pragma unroll
+    for (int i = 0; i < G; i++) {
+      const int q = lane + 32 * i;
+      const uint32_t a = tile[3 * q], b = tile[3 * q + 1], c = tile[3 * q + 2];
+      px[i][0] = a & 0x00FFFFFFu;
+      px[i][1] = (a >> 24) | ((b & 0xFFFFu) << 8);
+      px[i][2] = (b >> 16) | ((c & 0xFFu) << 16);
+      px[i][3] = c >> 8;
+    }
+#pragma unroll
+    for (int i = 0; i < G; i++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) o[i][k] = op(px[i][k]);
+    if (OUT4) {
+      uint8_t *drow = dst + (size_t)row * dstride;
+#pragma unroll
+      for (int i = 0; i < G; i++) {
+        const int x = 4 * (g0 + lane + 32 * i);
+        if (x + 3 < width && DST16) {
+          __stcs(reinterpret_cast<uint4 *>(drow + (size_t)x * 4), make_uint4(o[i][0], o[i][1], o[i][2], o[i][3]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (x + k < width) st_stream_u32(reinterpret_cast<uint32_t *>(drow + (size_t)(x + k) * 4), o[i][k]);
+        }
+      }
+      __syncwarp();
+    } else {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < G; i++) {
+        const int q = lane + 32 * i, x = 4 * (g0 + q);
+        uint32_t r[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) r[k] = (x + k < width) ? (o[i][k] & 0x00FFFFFFu) : px[i][k];   // bytes beyond the row: unchanged
+        tile[3 * q] = r[0] | (r[1] << 24);
+        tile[3 * q + 1] = (r[1] >> 8) | (r[2] << 16);
+        tile[3 * q + 2] = (r[2] >> 16) | (r[3] << 8);
+      }
+      __syncwarp();
+      uint32_t *d = reinterpret_cast<uint32_t *>(dst + (size_t)row * dstride);
+#pragma unroll
+      for (int j = 0; j < 3 * G; j++) {
+        const int wi = w0 + lane + 32 * j;
+        if (wi < nwords) st_stream_u32(d + wi, tile[lane + 32 * j]);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
 // videocompare / blockhash block sums.  hashed_image.rs:24-64 -> image_hasher blockhash fast path.
 // One CTA reduces a (bw x rows) tile that lies inside ONE hash block: registers -> warp shuffle
 // -> shared -> a single atomicAdd on the bin.  Integer adds are order independent => exact.
@@ -355,12 +435,27 @@ __global__ void __launch_bounds__(256) map_u32_kernel(Op op, const uint8_t *__re
 // --------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 
+// Up to kBlockhashMaxFrames equally sized frames per launch (videocompare hashes the reference pad's frame and every
+// other pad's frame on each aggregate tick): blockIdx.z = frame * zchunks + row chunk, sums of frame f at
+// sums + f*hw*hh.  The bins are zeroed by blockhash_zero_kernel, this kernel's PDL primary: it only has to wait for
+// it (griddepcontrol.wait) right before its single atomicAdd.
+constexpr int kBlockhashMaxFrames = 8;
+struct BlockhashFrames { const uint8_t *src[kBlockhashMaxFrames]; long stride[kBlockhashMaxFrames]; };
+
+__global__ void blockhash_zero_kernel(uint32_t *__restrict__ sums, int n) {
+  pdl_trigger();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sums[i] = 0u;
+}
+
 template <int BPP, bool VEC>
-__global__ void __launch_bounds__(128) blockhash_sums_kernel(const uint8_t *__restrict__ src, long stride, int bw,
-                                                             int bh, int hw, int rows_per_cta,
-                                                             uint32_t *__restrict__ sums) {
+__global__ void __launch_bounds__(128) blockhash_sums_kernel(BlockhashFrames fr, int zchunks, int bw, int bh, int hw, int hh,
+                                                             int rows_per_cta, uint32_t *__restrict__ sums) {
   const int bx = blockIdx.x, by = blockIdx.y;
-  const int y0 = by * bh + blockIdx.z * rows_per_cta;
+  const int f = (int)blockIdx.z / zchunks, chunk = (int)blockIdx.z - f * zchunks;
+  const uint8_t *__restrict__ src = fr.src[f];
+  const long stride = fr.stride[f];
+  const int y0 = by * bh + chunk * rows_per_cta;
   const int y1 = min(y0 + rows_per_cta, (by + 1) * bh);
   uint32_t acc = 0;
   if (VEC) {  // BPP == 4
@@ -400,7 +495,8 @@ __global__ void __launch_bounds__(128) blockhash_sums_kernel(const uint8_t *__re
   if (threadIdx.x == 0) {
     uint32_t t = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += wsum[w];
-    atomicAdd(sums + by * hw + bx, t);
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the zeroing kernel has completed
+    atomicAdd(sums + (size_t)f * hw * hh + by * hw + bx, t);
   }
 }
 

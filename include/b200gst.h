@@ -11,6 +11,7 @@
  *   hsvdetector       GstHsvDetector       GstVideoFilter       video/hsv/src/hsvdetector/imp.rs
  *   roundedcorners    GstRoundedCorners    GstBaseTransform     video/videofx/src/border/imp.rs
  *   videocompare      GstVideoCompare      GstVideoAggregator   video/videofx/src/videocompare/imp.rs
+ *   colordetect       GstColorDetect       GstVideoFilter       video/videofx/src/colordetect/imp.rs
  *
  * Every element owns one b200vfx_ctx (created in start(), destroyed in stop()) and calls the
  * C ABI of b200vfx.h for all pixel work -- the same calls the Rust shim makes.

@@ -91,7 +91,8 @@ uint64_t b200vfx_ctx_kernel_launches(const b200vfx_ctx *ctx);
  * "stream_ctas" CTAs per SM (0 = occupancy maximum), "stream_hint" 0|1 (L2 evict_last policy on table gathers),
  * "memo_px" 4|8|16 (pixels per thread of the non-TMA kernel),
  * "hsv_memo" -1 auto | 0 never | 1 at once (settings-keyed answer tables of hsvfilter / hsvdetector; auto builds
- * the table after the same settings have processed 2^24 pixels). */
+ * the table after the same settings have processed 2^24 pixels),
+ * "cd_cluster" 1|2|4|8 (colordetect: CTAs per cluster that merge their shared-memory histograms over DSMEM). */
 int b200vfx_ctx_set_option(b200vfx_ctx *ctx, const char *name, int value);
 
 /* Page-locked host memory for a GstAllocator handed out in
@@ -156,10 +157,35 @@ int b200vfx_roundmask_generate(b200vfx_ctx *ctx, int width, int height, int stri
  * (image_hasher's integer fast path).  `sums` may be a host or device pointer. */
 int b200vfx_blockhash_sums(b200vfx_ctx *ctx, int fmt, int width, int height, const void *src,
                            int stride, int hw, int hh, uint32_t *sums);
+/* VideoCompare::aggregate_frames (videocompare/imp.rs:297-353) hashes the reference pad's frame and then every other
+ * pad's frame on each tick: the same block sums for n_frames (1..8) equally sized frames of one format in ONE launch;
+ * sums receives n_frames * hw*hh values, frame f at sums + f*hw*hh.  Host and device frames may be mixed. */
+#define B200VFX_BLOCKHASH_MAX_FRAMES 8
+int b200vfx_blockhash_sums_batch(b200vfx_ctx *ctx, int fmt, int width, int height, int n_frames,
+                                 const void *const *srcs, const int *strides, int hw, int hh, uint32_t *sums);
 /* median/bit rule + Hamming distance (host side, tiny): bits_out hw*hh bytes of 0/1 */
 void b200vfx_blockhash_bits(const uint32_t *sums, int hw, int hh, int width, int height,
                             uint8_t *bits_out);
 int b200vfx_hash_distance(const uint8_t *bits_a, const uint8_t *bits_b, int nbits);
+
+/* ---- colordetect --------------------------------------
+ * ColorDetect::detect_color (video/videofx/src/colordetect/imp.rs:57-86) = color_thief::get_palette(plane 0,
+ * format, quality, max_colors) + color_name::css::Color::similar(palette[0]).  The per-pixel part of get_palette --
+ * the 5-bit-per-channel histogram over every `quality`-th pixel of the FLAT plane (stride * height bytes, stride
+ * padding included, exactly as frame.plane_data(0) exposes it) -- runs on the GPU; pixels with a < 125 or
+ * r,g,b all > 250 are skipped.  hist: 32768 u32 counts, index (r>>3)<<10 | (g>>3)<<5 | (b>>3), host or device
+ * pointer.  fmt: RGB RGBA ARGB BGR BGRA (imp.rs:214-222).  quality 1..10 (0 is accepted by the GObject property
+ * but trips color-thief's range check: B200VFX_ERR_INVALID). */
+#define B200VFX_COLORDETECT_BINS 32768
+int b200vfx_colordetect_histogram(b200vfx_ctx *ctx, int fmt, int width, int height, const void *src, int stride,
+                                  int quality, uint32_t *hist);
+/* host side, once per frame on 32768 integers: modified median cut of color-thief 0.2.2 (third-party, restated
+ * from its published algorithm -- parity unpinned).  Writes min(*n_colors, palette_cap) RGB triples, most
+ * significant first; palette[0] is the dominant colour.  max_colors 2..255 (imp.rs:134-141). */
+int b200vfx_colordetect_palette(const uint32_t *hist, int max_colors, uint8_t *palette_rgb, int palette_cap,
+                                int *n_colors);
+/* color_name::css::Color::similar(rgb).to_lowercase() (imp.rs:76-79): nearest CSS keyword by squared distance */
+const char *b200vfx_css_color_similar(unsigned r, unsigned g, unsigned b);
 
 /* ---- multi-GPU: colorlut on a row tile fused with the all-gather of the tiles over peer memory --------
  * The reference has no multi-device path; 8(e) shards the frame into contiguous row tiles (one process per GPU) and asks

@@ -693,3 +693,188 @@ int orc_roundmask(int width, int height, int stride, unsigned radius_px, uint8_t
   }
   return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* colordetect (video/videofx/src/colordetect/imp.rs:57-86)                   */
+/*   get_palette() of color-thief 0.2.2 and Color::similar() of color-name    */
+/*   1.2.0 are third-party crates not present under /root/reference: this is  */
+/*   a restatement of their published algorithm (MMCQ), PARITY UNPINNED.      */
+/* ------------------------------------------------------------------------- */
+int orc_colordetect_histogram(int fmt, int width, int height, const uint8_t *src,
+                              int stride, int quality, uint32_t *hist) {
+  int ro, go, bo, ao, bpp;
+  switch (fmt) {               /* color_parts(): byte positions per ColorFormat */
+    case ORC_FMT_RGB:  ro = 0; go = 1; bo = 2; ao = -1; bpp = 3; break;
+    case ORC_FMT_RGBA: ro = 0; go = 1; bo = 2; ao = 3;  bpp = 4; break;
+    case ORC_FMT_ARGB: ro = 1; go = 2; bo = 3; ao = 0;  bpp = 4; break;
+    case ORC_FMT_BGR:  ro = 2; go = 1; bo = 0; ao = -1; bpp = 3; break;
+    case ORC_FMT_BGRA: ro = 2; go = 1; bo = 0; ao = 3;  bpp = 4; break;
+    default: return -1;
+  }
+  if (quality < 1 || quality > 10) return -1;
+  memset(hist, 0, sizeof(uint32_t) * 32768);
+  if (width <= 0 || height <= 0) return 0;
+  /* frame.plane_data(0): one flat slice of stride*height bytes; pixel i sits at
+   * byte i*bpp regardless of the stride (imp.rs:68-69) */
+  const size_t len = (size_t)stride * (size_t)height;
+  const size_t pixel_count = len / (size_t)bpp;
+  for (size_t i = 0; i < pixel_count; i += (size_t)quality) {
+    const uint8_t *p = src + i * (size_t)bpp;
+    unsigned r = p[ro], g = p[go], b = p[bo], a = ao < 0 ? 255u : p[ao];
+    if (a >= 125 && !(r > 250 && g > 250 && b > 250))     /* mostly opaque and not white */
+      hist[((r >> 3) << 10) + ((g >> 3) << 5) + (b >> 3)] += 1;
+  }
+  return 0;
+}
+
+typedef struct { int lo[3], hi[3]; int avg[3]; long long count; long long volume; int seq; } orc_vbox;
+
+static long long orc_h(const uint32_t *hist, int r, int g, int b) { return hist[(r << 10) + (g << 5) + b]; }
+
+static void orc_vbox_recalc(const uint32_t *hist, orc_vbox *v) {
+  long long n = 0, s[3] = {0, 0, 0};
+  for (int r = v->lo[0]; r <= v->hi[0]; r++)
+    for (int g = v->lo[1]; g <= v->hi[1]; g++)
+      for (int b = v->lo[2]; b <= v->hi[2]; b++) {
+        double hv = (double)orc_h(hist, r, g, b);
+        n += (long long)hv;
+        s[0] += (long long)(hv * (r + 0.5) * 8.0);   /* truncated per bin, like `as i32` */
+        s[1] += (long long)(hv * (g + 0.5) * 8.0);
+        s[2] += (long long)(hv * (b + 0.5) * 8.0);
+      }
+  for (int c = 0; c < 3; c++) {
+    if (n > 0) v->avg[c] = (int)((s[c] / n) & 255);
+    else { int m = 8 * (v->lo[c] + v->hi[c] + 1) / 2; v->avg[c] = m > 255 ? 255 : m; }
+  }
+  v->count = n;
+  v->volume = (long long)(v->hi[0] - v->lo[0] + 1) * (v->hi[1] - v->lo[1] + 1) * (v->hi[2] - v->lo[2] + 1);
+}
+
+/* population of the slab `i` along `axis` inside the box */
+static long long orc_slab(const uint32_t *hist, const orc_vbox *v, int axis, int i) {
+  int lo[3], hi[3];
+  for (int c = 0; c < 3; c++) { lo[c] = v->lo[c]; hi[c] = v->hi[c]; }
+  lo[axis] = hi[axis] = i;
+  long long s = 0;
+  for (int r = lo[0]; r <= hi[0]; r++) for (int g = lo[1]; g <= hi[1]; g++) for (int b = lo[2]; b <= hi[2]; b++) s += orc_h(hist, r, g, b);
+  return s;
+}
+
+static int orc_median_cut(const uint32_t *hist, const orc_vbox *v, orc_vbox *a, orc_vbox *b) {
+  if (v->count <= 1) return 0;
+  int w[3], axis;
+  for (int c = 0; c < 3; c++) w[c] = v->hi[c] - v->lo[c];
+  int m = w[0] > w[1] ? w[0] : w[1]; if (w[2] > m) m = w[2];
+  axis = (m == w[0]) ? 0 : (m == w[1] ? 1 : 2);
+  long long part[32], look[32], total = 0;
+  for (int i = 0; i < 32; i++) part[i] = look[i] = -1;
+  for (int i = v->lo[axis]; i <= v->hi[axis]; i++) { total += orc_slab(hist, v, axis, i); part[i] = total; }
+  for (int i = 0; i < 32; i++) if (part[i] != -1) look[i] = total - part[i];
+  const int vmin = v->lo[axis], vmax = v->hi[axis];
+  for (int i = vmin; i <= vmax; i++) {
+    if (part[i] <= total / 2) continue;
+    int left = i - vmin, right = vmax - i, d2;
+    if (left <= right) { d2 = i + right / 2; if (d2 > vmax - 1) d2 = vmax - 1; }
+    else { d2 = (int)((double)(i - 1) - (double)left / 2.0); if (d2 < vmin) d2 = vmin; }
+    while (d2 < 0 || part[d2] <= 0) d2++;
+    long long c2 = look[d2];
+    while (c2 == 0 && d2 > 0 && part[d2 - 1] > 0) { d2--; c2 = look[d2]; }
+    *a = *v; *b = *v;
+    a->hi[axis] = d2; b->lo[axis] = d2 + 1;
+    orc_vbox_recalc(hist, a); orc_vbox_recalc(hist, b);
+    return 1;
+  }
+  return 0;
+}
+
+static int orc_cmp_mode;  /* 0: by count, 1: by count*volume (count ties: by volume); seq keeps the sort stable */
+static int orc_vbox_cmp(const void *pa, const void *pb) {
+  const orc_vbox *x = (const orc_vbox *)pa, *y = (const orc_vbox *)pb;
+  long long kx, ky;
+  if (orc_cmp_mode == 0) { kx = x->count; ky = y->count; }
+  else if (x->count == y->count) { kx = x->volume; ky = y->volume; }
+  else { kx = x->count * x->volume; ky = y->count * y->volume; }
+  if (kx != ky) return kx < ky ? -1 : 1;
+  return x->seq - y->seq;
+}
+static void orc_sort(orc_vbox *q, int n, int mode) {
+  for (int i = 0; i < n; i++) q[i].seq = i;
+  orc_cmp_mode = mode;
+  qsort(q, (size_t)n, sizeof(orc_vbox), orc_vbox_cmp);
+}
+static void orc_iterate(const uint32_t *hist, orc_vbox *q, int *n, int mode, int target) {
+  int color = 1;
+  for (int it = 0; it < 1000; it++) {
+    orc_vbox last = q[*n - 1];
+    if (last.count == 0) { orc_sort(q, *n, mode); continue; }
+    orc_vbox a, b;
+    if (orc_median_cut(hist, &last, &a, &b)) { q[*n - 1] = a; q[*n] = b; (*n)++; color++; }
+    orc_sort(q, *n, mode);
+    if (color >= target) return;
+  }
+}
+
+int orc_colordetect_palette(const uint32_t *hist, int max_colors, uint8_t *rgb, int cap) {
+  if (max_colors < 2 || max_colors > 255) return -1;
+  orc_vbox *q = (orc_vbox *)calloc(2100, sizeof(orc_vbox));
+  int n = 1;
+  for (int c = 0; c < 3; c++) { q[0].lo[c] = 255; q[0].hi[c] = 0; }
+  for (int i = 0; i < 32768; i++)
+    if (hist[i]) {
+      int v[3] = {i >> 10, (i >> 5) & 31, i & 31};
+      for (int c = 0; c < 3; c++) { if (v[c] < q[0].lo[c]) q[0].lo[c] = v[c]; if (v[c] > q[0].hi[c]) q[0].hi[c] = v[c]; }
+    }
+  orc_vbox_recalc(hist, &q[0]);
+  int target = (int)ceil(0.75 * (double)max_colors);
+  orc_iterate(hist, q, &n, 0, target);
+  orc_sort(q, n, 1);
+  orc_iterate(hist, q, &n, 1, max_colors - n);
+  for (int i = 0; i < n && i < cap; i++) {         /* reversed: most significant first */
+    const orc_vbox *v = &q[n - 1 - i];
+    rgb[3 * i] = (uint8_t)v->avg[0]; rgb[3 * i + 1] = (uint8_t)v->avg[1]; rgb[3 * i + 2] = (uint8_t)v->avg[2];
+  }
+  free(q);
+  return n;
+}
+
+static const struct { const char *n; unsigned char r, g, b; } orc_css[] = {
+  {"aliceblue",240,248,255},{"antiquewhite",250,235,215},{"aqua",0,255,255},{"aquamarine",127,255,212},{"azure",240,255,255},
+  {"beige",245,245,220},{"bisque",255,228,196},{"black",0,0,0},{"blanchedalmond",255,235,205},{"blue",0,0,255},
+  {"blueviolet",138,43,226},{"brown",165,42,42},{"burlywood",222,184,135},{"cadetblue",95,158,160},{"chartreuse",127,255,0},
+  {"chocolate",210,105,30},{"coral",255,127,80},{"cornflowerblue",100,149,237},{"cornsilk",255,248,220},{"crimson",220,20,60},
+  {"cyan",0,255,255},{"darkblue",0,0,139},{"darkcyan",0,139,139},{"darkgoldenrod",184,134,11},{"darkgray",169,169,169},
+  {"darkgreen",0,100,0},{"darkgrey",169,169,169},{"darkkhaki",189,183,107},{"darkmagenta",139,0,139},{"darkolivegreen",85,107,47},
+  {"darkorange",255,140,0},{"darkorchid",153,50,204},{"darkred",139,0,0},{"darksalmon",233,150,122},{"darkseagreen",143,188,143},
+  {"darkslateblue",72,61,139},{"darkslategray",47,79,79},{"darkslategrey",47,79,79},{"darkturquoise",0,206,209},{"darkviolet",148,0,211},
+  {"deeppink",255,20,147},{"deepskyblue",0,191,255},{"dimgray",105,105,105},{"dimgrey",105,105,105},{"dodgerblue",30,144,255},
+  {"firebrick",178,34,34},{"floralwhite",255,250,240},{"forestgreen",34,139,34},{"fuchsia",255,0,255},{"gainsboro",220,220,220},
+  {"ghostwhite",248,248,255},{"gold",255,215,0},{"goldenrod",218,165,32},{"gray",128,128,128},{"green",0,128,0},
+  {"greenyellow",173,255,47},{"grey",128,128,128},{"honeydew",240,255,240},{"hotpink",255,105,180},{"indianred",205,92,92},
+  {"indigo",75,0,130},{"ivory",255,255,240},{"khaki",240,230,140},{"lavender",230,230,250},{"lavenderblush",255,240,245},
+  {"lawngreen",124,252,0},{"lemonchiffon",255,250,205},{"lightblue",173,216,230},{"lightcoral",240,128,128},{"lightcyan",224,255,255},
+  {"lightgoldenrodyellow",250,250,210},{"lightgray",211,211,211},{"lightgreen",144,238,144},{"lightgrey",211,211,211},{"lightpink",255,182,193},
+  {"lightsalmon",255,160,122},{"lightseagreen",32,178,170},{"lightskyblue",135,206,250},{"lightslategray",119,136,153},{"lightslategrey",119,136,153},
+  {"lightsteelblue",176,196,222},{"lightyellow",255,255,224},{"lime",0,255,0},{"limegreen",50,205,50},{"linen",250,240,230},
+  {"magenta",255,0,255},{"maroon",128,0,0},{"mediumaquamarine",102,205,170},{"mediumblue",0,0,205},{"mediumorchid",186,85,211},
+  {"mediumpurple",147,112,219},{"mediumseagreen",60,179,113},{"mediumslateblue",123,104,238},{"mediumspringgreen",0,250,154},{"mediumturquoise",72,209,204},
+  {"mediumvioletred",199,21,133},{"midnightblue",25,25,112},{"mintcream",245,255,250},{"mistyrose",255,228,225},{"moccasin",255,228,181},
+  {"navajowhite",255,222,173},{"navy",0,0,128},{"oldlace",253,245,230},{"olive",128,128,0},{"olivedrab",107,142,35},
+  {"orange",255,165,0},{"orangered",255,69,0},{"orchid",218,112,214},{"palegoldenrod",238,232,170},{"palegreen",152,251,152},
+  {"paleturquoise",175,238,238},{"palevioletred",219,112,147},{"papayawhip",255,239,213},{"peachpuff",255,218,185},{"peru",205,133,63},
+  {"pink",255,192,203},{"plum",221,160,221},{"powderblue",176,224,230},{"purple",128,0,128},{"red",255,0,0},
+  {"rosybrown",188,143,143},{"royalblue",65,105,225},{"saddlebrown",139,69,19},{"salmon",250,128,114},{"sandybrown",244,164,96},
+  {"seagreen",46,139,87},{"seashell",255,245,238},{"sienna",160,82,45},{"silver",192,192,192},{"skyblue",135,206,235},
+  {"slateblue",106,90,205},{"slategray",112,128,144},{"slategrey",112,128,144},{"snow",255,250,250},{"springgreen",0,255,127},
+  {"steelblue",70,130,180},{"tan",210,180,140},{"teal",0,128,128},{"thistle",216,191,216},{"tomato",255,99,71},
+  {"turquoise",64,224,208},{"violet",238,130,238},{"wheat",245,222,179},{"white",255,255,255},{"whitesmoke",245,245,245},
+  {"yellow",255,255,0},{"yellowgreen",154,205,50},
+};
+const char *orc_css_similar(unsigned r, unsigned g, unsigned b) {
+  long best = 0; const char *name = "";
+  for (size_t i = 0; i < sizeof orc_css / sizeof orc_css[0]; i++) {
+    long dr = (long)r - orc_css[i].r, dg = (long)g - orc_css[i].g, db = (long)b - orc_css[i].b;
+    long d = dr * dr + dg * dg + db * db;
+    if (i == 0 || d < best) { best = d; name = orc_css[i].n; }
+  }
+  return name;
+}

@@ -15,8 +15,9 @@
  *                          and the Rust toolchain is absent here); pinned
  *                          instead against an independent numpy-f32
  *                          restatement and SURVEY Appendix C vectors.
- *   - blockhash bit rule, rounded-corner mask: third-party arithmetic
- *                          (image_hasher 3.1.1, cairo) absent from
+ *   - blockhash bit rule, rounded-corner mask, colordetect palette / colour
+ *     name: third-party arithmetic (image_hasher 3.1.1, cairo,
+ *                          color-thief 0.2.2, color-name 1.2.0) absent from
  *                          /root/reference -> "parity unpinned".
  *
  * All arithmetic is IEEE-754 binary32, one rounding per operator, never fused:
@@ -93,6 +94,16 @@ int orc_hamming(const uint8_t *a, const uint8_t *b, int n);
  * Analytic restatement of the cairo drawing (parity unpinned). */
 int orc_roundmask(int width, int height, int stride, unsigned radius_px,
                   uint8_t *a8);
+
+/* ---- colordetect (video/videofx/src/colordetect/imp.rs:57-86 -> color-thief 0.2.2, color-name 1.2.0;
+ * both third-party and absent from /root/reference: restated from their published algorithm, PARITY UNPINNED
+ * except for tests/colordetect.rs:67 (red frame -> "red")).
+ * histogram: the per-pixel pass of get_palette over the flat plane slice (stride*height bytes). */
+int orc_colordetect_histogram(int fmt, int width, int height, const uint8_t *src,
+                              int stride, int quality, uint32_t *hist /*32768*/);
+/* modified median cut; returns the number of palette colours, writes up to cap RGB triples */
+int orc_colordetect_palette(const uint32_t *hist, int max_colors, uint8_t *rgb, int cap);
+const char *orc_css_similar(unsigned r, unsigned g, unsigned b);
 
 #ifdef __cplusplus
 }

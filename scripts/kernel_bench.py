@@ -131,9 +131,32 @@ def main():
         sums = torch.zeros(64, dtype=torch.int32, device="cuda")
         t = timeit(lambda i: ctx.blockhash_sums("RGBA", W, H, frames[i % RING], 4 * W, sums), args.iters)
         report("blockhash_sums_rgba", t, W * H * 4, content="noise", frame="3840x2160", note="one stream; config 4 = two streams")
+        sums2 = torch.zeros(128, dtype=torch.int32, device="cuda")
+        t = timeit(lambda i: ctx.blockhash_sums_batch("RGBA", W, H, [frames[i % RING], frames[(i + 1) % RING]], [4 * W, 4 * W], sums2), args.iters)
+        report("blockhash_sums_rgba_batch2", t, 2 * W * H * 4, content="noise", frame="2 x 3840x2160", note="BASELINE config 4: both streams in one launch")
         m = torch.empty((1080, 1920), dtype=torch.uint8, device="cuda")
         t = timeit(lambda i: ctx.roundmask_generate(1920, 1080, 1920, 64, m), 20)
         report("roundmask_a8", t, 1920 * 1080, frame="1920x1080", radius=64, note="once per caps/radius change")
+    if want("colordetect"):
+        hist = torch.zeros(32768, dtype=torch.int32, device="cuda")
+        for cname in ("ramps", "noise", "natural"):
+            frames, _ = ring_of(contents[cname])
+            for q, cl in ((10, 2), (1, 2), (1, 1), (1, 4), (1, 8), (10, 1)):
+                ctx.set_option("cd_cluster", cl)
+                t = timeit(lambda i: ctx.colordetect_histogram("RGBA", W, H, frames[i % RING], 4 * W, q, hist), args.iters)
+                # quality q reads one 4-byte pixel every 4q bytes: every 32-byte sector is still touched up to q = 8
+                report("colordetect_hist_rgba", t, W * H * 4, content=cname, frame="3840x2160", quality=q, cluster=cl,
+                       samples=(W * H + q - 1) // q, note="algorithmic bytes = the whole plane (sector granularity)")
+            del frames
+        ctx.set_option("cd_cluster", 2)
+    if want("hsv24"):
+        for memo in (0, 1):
+            ctx.set_option("hsv_memo", memo)
+            for cname in ("ramps", "noise"):
+                fr = [torch.from_numpy((synth.frame_ramps("RGB", W, H) if cname == "ramps" else synth.frame_noise("RGB", W, H, 50 + i))[:, :3 * W].copy()).cuda() for i in range(RING)]
+                t = timeit(lambda i: ctx.hsvfilter_process("RGB", W, H, fr[i % RING], 3 * W, hue_shift=90.0), max(args.iters // (1 if memo else 3), 5))
+                report("hsvfilter_rgb_" + ("memo" if memo else "direct"), t, 2 * W * H * 3, content=cname, frame="3840x2160")
+        ctx.set_option("hsv_memo", -1)
     if want("e2e"):
         k, s, v, sc, of = b200vfx.cube_parse(synth.cube_text_3d(33, "mix"))
         ctx.colorlut_set_lut(k, s, v, sc, of)

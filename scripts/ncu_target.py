@@ -13,10 +13,11 @@ import b200vfx
 from b200vfx import synth
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--kernel", default="memo", choices=["memo", "direct", "direct64", "hsvfilter", "hsvdetector", "blockhash"])
+ap.add_argument("--kernel", default="memo", choices=["memo", "direct", "direct64", "hsvfilter", "hsvdetector", "blockhash", "colordetect"])
 ap.add_argument("--content", default="ramps", choices=["ramps", "noise", "natural"])
 ap.add_argument("--lut", type=int, default=33)
 ap.add_argument("--launches", type=int, default=6)
+ap.add_argument("--quality", type=int, default=1)
 a = ap.parse_args()
 W, H = 3840, 2160
 ctx = b200vfx.Context(0)
@@ -52,6 +53,11 @@ elif a.kernel == "hsvdetector":
     for i in range(a.launches):
         ctx.hsvdetector_process("BGRx", "RGBA", w, h, fr[i % 4], 4 * w, out[i % 4], 4 * w, hue_ref=120.0, hue_var=30.0,
                                 saturation_ref=0.8, saturation_var=0.2, value_ref=0.8, value_var=0.2)
+elif a.kernel == "colordetect":
+    fr = [torch.from_numpy(frame("RGBA", W, H, i)).cuda() for i in range(4)]
+    hist = torch.zeros(32768, dtype=torch.int32, device="cuda")
+    for i in range(a.launches):
+        ctx.colordetect_histogram("RGBA", W, H, fr[i % 4], 4 * W, a.quality, hist)
 else:
     fr = [torch.from_numpy(frame("RGBA", W, H, i)).cuda() for i in range(4)]
     sums = torch.zeros(64, dtype=torch.int32, device="cuda")

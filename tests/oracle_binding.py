@@ -50,6 +50,10 @@ def lib() -> C.CDLL:
         _lib.orc_blockhash_bits.argtypes = [u32p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         _lib.orc_hamming.argtypes = [u8p, u8p, C.c_int]
         _lib.orc_roundmask.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p]
+        _lib.orc_colordetect_histogram.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        _lib.orc_colordetect_palette.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        _lib.orc_css_similar.argtypes = [C.c_uint, C.c_uint, C.c_uint]
+        _lib.orc_css_similar.restype = C.c_char_p
         for n in ("orc_hsv_from_rgb", "orc_hsv_from_bgr"):
             getattr(_lib, n).argtypes = [u8p, f32p]
             getattr(_lib, n).restype = None
@@ -177,3 +181,27 @@ def hsv_to(hsv, bgr=False):
     o = (C.c_uint8 * 3)()
     (lib().orc_hsv_to_bgr if bgr else lib().orc_hsv_to_rgb)(p, o)
     return [o[0], o[1], o[2]]
+
+
+def colordetect_histogram(fmt, width, height, src: np.ndarray, quality=10) -> np.ndarray:
+    """src: (height, stride) uint8 plane; the reference samples the flat stride*height slice"""
+    src = np.ascontiguousarray(src, np.uint8)
+    hist = np.zeros(32768, np.uint32)
+    stride = src.shape[1] if src.ndim == 2 else 0
+    rc = lib().orc_colordetect_histogram(FMT[fmt], width, height, src.ctypes.data, stride, quality, hist.ctypes.data)
+    if rc:
+        raise RuntimeError("orc_colordetect_histogram rc=%d" % rc)
+    return hist
+
+
+def colordetect_palette(hist: np.ndarray, max_colors=2):
+    hist = np.ascontiguousarray(hist, np.uint32)
+    pal = np.zeros(3 * 600, np.uint8)
+    n = lib().orc_colordetect_palette(hist.ctypes.data, max_colors, pal.ctypes.data, 600)
+    if n < 0:
+        raise RuntimeError("orc_colordetect_palette rc=%d" % n)
+    return [tuple(int(v) for v in pal[3 * i:3 * i + 3]) for i in range(min(n, 600))]
+
+
+def css_similar(r, g, b) -> str:
+    return lib().orc_css_similar(int(r), int(g), int(b)).decode()

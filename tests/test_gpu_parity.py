@@ -314,6 +314,39 @@ def test_hsvdetector_format_matrix(ctx, ifmt, ofmt, memo):
     ctx.set_option("hsv_memo", -1)
 
 
+@pytest.mark.parametrize("fmt", ["RGB", "BGR"])
+def test_hsv_rgb24_memo_device_frames(ctx, fmt):
+    """3-byte pixels through the answer tables (map_rgb24_kernel): device-resident frames, packed (flattened to one
+    row when 3*w*h is a multiple of 4) and padded strides, widths that are not multiples of 4, in place for hsvfilter
+    and 3->4 bytes for hsvdetector; padding bytes must stay untouched."""
+    torch = pytest.importorskip("torch")
+    fkw = dict(hue_shift=77.0, saturation_mul=1.2, value_off=0.05)
+    dkw = dict(hue_ref=200.0, hue_var=90.0, saturation_ref=0.5, saturation_var=0.5, value_ref=0.5, value_var=0.5)
+    ctx.set_option("hsv_memo", 1)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        for (w, h, pad) in ((640, 48, 0), (1000, 3, 0), (333, 4, 1), (4, 1, 0), (2049, 5, 3), (3840, 16, 0), (6, 2, 2), (333, 4, 0), (5, 3, 0)):
+            stride = 3 * w + pad
+            if stride % 4:
+                stride += 4 - stride % 4 if pad else 0
+            fr = np.full((h, stride), 0xA5, np.uint8)
+            fr[:, :3 * w] = synth.frame_noise(fmt, w, h, 21 + w)[:, :3 * w]
+            exp = orc.hsvfilter(fmt, w, h, fr.copy(), **_orc_kw(fkw))
+            d = torch.from_numpy(fr).cuda()
+            ctx.hsvfilter_process(fmt, w, h, d, stride, **fkw)
+            torch.cuda.synchronize()
+            assert (d.cpu().numpy() == exp).all(), (w, h, pad)
+            for ofmt, dpad in (("RGBA", 0), ("ABGR", 4), ("BGRA", 16)):
+                dstride = 4 * w + dpad
+                expd = orc.hsvdetector(fmt, ofmt, w, h, fr, dst_stride=dstride, **_orc_dkw(dkw))
+                dd = torch.full((h, dstride), 0x5A, dtype=torch.uint8, device="cuda")
+                ctx.hsvdetector_process(fmt, ofmt, w, h, torch.from_numpy(fr).cuda(), stride, dd, dstride, **dkw)
+                torch.cuda.synchronize()
+                assert (dd.cpu().numpy() == expd).all(), (w, h, pad, ofmt)
+    finally:
+        ctx.set_option("hsv_memo", -1)
+
+
 def test_hsvdetector_rejects_formats_outside_caps(ctx):
     src = np.zeros((1, 8), np.uint8)
     for ifmt, ofmt in (("RGBA", "RGBA"), ("RGBx", "RGBx"), ("RGBA64_LE", "RGBA"), ("RGB", "BGR")):
@@ -371,6 +404,32 @@ def test_blockhash_device_and_videocompare_semantics(ctx):
     with pytest.raises(b200vfx.B200VfxError) as e:
         ctx.blockhash_sums("RGBA", 30, 16, a, 4 * w, np.zeros(64, np.uint32))
     assert e.value.code == b200vfx.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("fmt,w,h", [("RGBA", 3840, 2160), ("RGBA", 72, 40), ("RGB", 640, 480), ("RGBA", 1920, 1080)])
+def test_blockhash_batch_matches_per_frame(ctx, fmt, w, h):
+    """videocompare hashes the reference frame and every other pad's frame per tick: one launch for up to 8 frames,
+    host and device frames mixed, strides differing per frame (BASELINE config 4 = two 4K RGBA streams)"""
+    torch = pytest.importorskip("torch")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    for n in (1, 2, 3, 8):
+        frames = [synth.frame_noise(fmt, w, h, 40 + i, stride=synth.default_stride(fmt, w) + (16 * (i % 2))) if i % 3 else
+                  synth.frame_ramps(fmt, w, h) for i in range(n)]
+        if fmt == "RGBA":
+            frames[-1][::5, 3:4 * w:8] = 0
+        exp = np.concatenate([orc.blockhash_sums(fmt, w, h, f) for f in frames])
+        keep = [torch.from_numpy(f).cuda() if i % 2 == 0 else None for i, f in enumerate(frames)]
+        srcs = [keep[i] if keep[i] is not None else frames[i] for i in range(n)]
+        sums = np.full(64 * n, 0xDEADBEEF, np.uint32)
+        ctx.blockhash_sums_batch(fmt, w, h, srcs, [f.shape[1] for f in frames], sums)
+        assert (sums == exp).all(), n
+        if n == 2:  # all-device frames, device sums: asynchronous on the context stream
+            d_sums = torch.full((128,), -1, dtype=torch.int32, device="cuda")
+            ctx.blockhash_sums_batch(fmt, w, h, [torch.from_numpy(f).cuda() for f in frames], [f.shape[1] for f in frames], d_sums)
+            torch.cuda.synchronize()
+            assert (d_sums.cpu().numpy().view(np.uint32) == exp).all()
+    with pytest.raises(b200vfx.B200VfxError):
+        ctx.blockhash_sums_batch(fmt, w, h, [frames[0]] * 9, [frames[0].shape[1]] * 9, np.zeros(64 * 9, np.uint32))
 
 
 # ---- roundedcorners --------------------------------------------------------------------------------
