@@ -389,6 +389,42 @@ def main():
         ag = torch.tensor([a.elapsed_time(b) / 20], dtype=torch.float64, device="cuda")
         dist.all_reduce(ag, op=dist.ReduceOp.MAX)
         allgather = {"ms_per_frame": float(ag.item()), "bytes_per_rank": int(tile.numel()), "note": "ncclAllGather of one 4K frame's row tiles; not part of value"}
+        # the same reassembly two ways, device-timed per frame, max over ranks: (a) tile kernel + in-place ncclAllGather,
+        # (b) ONE fused kernel that stores its results into every rank's frame buffer over NVLink (b200vfx_colorlut_process_tile_gather)
+        if os.environ.get("B200VFX_BENCH_FUSED", "1") != "0":
+            try:
+                from b200vfx import sharding
+                full2 = torch.empty((H4K, 4 * W4K), dtype=torch.uint8, device="cuda")
+                tiles_in = [d_in[i][:rows] for i in range(4)]
+                pf = sharding.PeerFrames(ctx, dist, H4K, 4 * W4K, nbuf=2)
+
+                def k_nccl(i):
+                    slot = full2[rank * rows:(rank + 1) * rows]
+                    ctx.colorlut_process("RGBA", W4K, rows, tiles_in[i % 4], 4 * W4K, slot, 4 * W4K)
+                    dist.all_gather_into_tensor(full2.view(-1), slot.reshape(-1))
+
+                def k_fused(i):
+                    pf.process(W4K, tiles_in[i % 4], 4 * W4K)
+
+                res = {}
+                for name, fn in (("kernel_plus_nccl_ms", k_nccl), ("fused_tile_gather_ms", k_fused)):
+                    for i in range(5):
+                        fn(i)
+                    barrier()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for i in range(40):
+                        fn(i)
+                    b.record()
+                    torch.cuda.synchronize()
+                    tt = torch.tensor([a.elapsed_time(b) / 40], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    res[name] = float(tt.item())
+                res["fused_timeouts"] = int(pf.status())
+                pf.close()
+                allgather.update(res)
+            except Exception as exc:   # the reassembly comparison is informative only; never lose the bench line over it
+                allgather["fused_error"] = str(exc)[:200]
 
     cpu = None
     if rank == 0 and N == 1 and not args.no_cpu:

@@ -110,8 +110,42 @@ extern "C" {
         hh: c_int,
         sums: *mut u32,
     ) -> c_int;
+    // videocompare: reference frame + every other pad's frame in one launch (aggregate_frames, imp.rs:297-353)
+    pub fn b200vfx_blockhash_sums_batch(
+        ctx: *mut b200vfx_ctx,
+        fmt: c_int,
+        width: c_int,
+        height: c_int,
+        n_frames: c_int,
+        srcs: *const *const c_void,
+        strides: *const c_int,
+        hw: c_int,
+        hh: c_int,
+        sums: *mut u32,
+    ) -> c_int;
     pub fn b200vfx_blockhash_bits(sums: *const u32, hw: c_int, hh: c_int, width: c_int, height: c_int, bits_out: *mut u8);
     pub fn b200vfx_hash_distance(a: *const u8, b: *const u8, nbits: c_int) -> c_int;
+
+    // colordetect (video/videofx/src/colordetect/imp.rs:57-86): get_palette's pixel pass on the GPU,
+    // median cut + CSS name on the host
+    pub fn b200vfx_colordetect_histogram(
+        ctx: *mut b200vfx_ctx,
+        fmt: c_int,
+        width: c_int,
+        height: c_int,
+        src: *const c_void,
+        stride: c_int,
+        quality: c_int,
+        hist: *mut u32, // 32768 bins
+    ) -> c_int;
+    pub fn b200vfx_colordetect_palette(
+        hist: *const u32,
+        max_colors: c_int,
+        palette_rgb: *mut u8,
+        palette_cap: c_int,
+        n_colors: *mut c_int,
+    ) -> c_int;
+    pub fn b200vfx_css_color_similar(r: c_uint, g: c_uint, b: c_uint) -> *const c_char;
 }
 
 /// Owning wrapper: one context per element instance, created in `start()`, dropped in `stop()`.
