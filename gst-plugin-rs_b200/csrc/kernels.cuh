@@ -22,7 +22,12 @@ __device__ __forceinline__ void st_stream_u2(uint2 *p, uint2 v) { __stcs(p, v); 
 #ifndef B200VFX_MEMO_BLOCKED
 #define B200VFX_MEMO_BLOCKED 1
 #endif
-__device__ __forceinline__ uint32_t memo_index(uint32_t c) {  // c = r | g<<8 | b<<16
+#ifndef B200VFX_EXP_MEMO_SHIFT   // timing experiment only (wrong results): table footprint 64 MiB >> shift
+#define B200VFX_EXP_MEMO_SHIFT 0
+#endif
+__device__ __forceinline__ uint32_t memo_index_full(uint32_t c);
+__device__ __forceinline__ uint32_t memo_index(uint32_t c) { return memo_index_full(c) >> B200VFX_EXP_MEMO_SHIFT; }
+__device__ __forceinline__ uint32_t memo_index_full(uint32_t c) {  // c = r | g<<8 | b<<16
 #if B200VFX_MEMO_BLOCKED
   return (c & 3u) | ((c >> 6) & 0xCu) | ((c >> 12) & 0x10u) | ((c << 3) & 0x7E0u) | ((c << 1) & 0x1F800u) | (c & 0xFE0000u);
 #else
