@@ -889,11 +889,14 @@ int b200vfx_colorlut_set_lut(b200vfx_ctx *c, int kind, int size, const float *va
     const size_t N = (size_t)size;
     for (size_t i = 0; i < n; i++) {
       const size_t x = i % N, i1 = (x + 1 < N) ? i + 1 : i;
+      float av[3], dv[3];
       for (int k = 0; k < 3; k++) {
         const volatile float a = values[3 * i + k], b = values[3 * i1 + k];
         const volatile float d = b - a;  // volatile: one IEEE binary32 subtraction, no extended precision / fusion
-        h[i].a[k] = a; h[i].d[k] = d;
+        av[k] = a; dv[k] = d;
       }
+      // register-pair friendly order for the packed f32x2 evaluator: {a.r,a.g | d.r,d.g | a.b,d.b | pad}
+      h[i].a_rg[0] = av[0]; h[i].a_rg[1] = av[1]; h[i].d_rg[0] = dv[0]; h[i].d_rg[1] = dv[1]; h[i].a_b = av[2]; h[i].d_b = dv[2];
       h[i].pad[0] = h[i].pad[1] = 0.0f;
     }
     CU(c, cudaMalloc(&c->d_pair, n * sizeof(LutPair)));

@@ -6,18 +6,42 @@
 //        i0 = min(floor(pos), size-1); i1 = min(i0+1, size-1); t = pos - i0  (sample_*,   imp.rs:482-503)
 //        o0/o1 = i0/i1 pre-multiplied by the axis stride (1, size, size^2); 1D LUTs use stride 1.
 //    The IEEE division, the clamps, floor and the index clamps leave the pixel loop; t is the same f32.
-//  * x-pair table pair[x + y*size + z*size^2] = {a.r,a.g,a.b, d.r,d.g,d.b, 0,0} (32 bytes = one L2 sector) with
+//  * x-pair table pair[x + y*size + z*size^2] = {a.r,a.g, d.r,d.g, a.b,d.b, 0,0} (32 bytes = one L2 sector) with
 //        a = lut.at(x,y,z), d = lut.at(min(x+1,size-1),y,z) - a   -- the SAME rounded f32 difference that
 //        lerp4's `b - a` produces at run time (imp.rs:528-535), so `a + d*tx` is bit-identical to the x-lerp
 //        and the 8 corner fetches become 4 sector-sized 256-bit loads (LDG.E.256).
 // Every remaining operator is a single RN operation (__f*_rn, compiled with -fmad=false).
+//
+// Packed f32x2 (Blackwell FADD2 / FMUL2 / FFMA2): the R and G channels travel as the two lanes of one 64-bit register
+// pair (the table layout puts a.rg and d.rg in adjacent registers of the 256-bit load), B stays scalar.  Packed ADDs and
+// SUBs are exact lane-wise RN operations; every multiplication whose product feeds an addition stays a scalar FMUL,
+// because ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 whatever -fmad says (tests/test_sass_lint.py keeps watch).
+// Per pixel this removes ~30 of ~160 issue slots of the RGBA64 kernel, which is issue-bound.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace b200vfx {
 
-struct __align__(32) LutPair { float a[3]; float d[3]; float pad[2]; };
+struct __align__(32) LutPair { float a_rg[2]; float d_rg[2]; float a_b, d_b; float pad[2]; };
+
+// ---- packed f32x2 helpers (one 64-bit register pair = {lo, hi}) ------------------------------------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk2(f32x2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t add2_rn(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t sub2_rn(f32x2_t a, f32x2_t b) { f32x2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t add2_rd(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t mul2_rn(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t fma2_rn(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// lane-wise a + d*t with the products rounded by scalar FMULs (never contracted)
+__device__ __forceinline__ f32x2_t lerp_pre2(f32x2_t a, f32x2_t d, float t) {
+  float dl, dh;
+  unpk2(d, dl, dh);
+  return add2_rn(a, pk2(__fmul_rn(dl, t), __fmul_rn(dh, t)));
+}
+// lane-wise a + (b - a)*t, three roundings per lane (imp.rs:528-535)
+__device__ __forceinline__ f32x2_t lerp_exact2(f32x2_t a, f32x2_t b, float t) { return lerp_pre2(a, sub2_rn(b, a), t); }
 
 struct LutDev {
   const LutPair *pair;   // 3D: size^3 x-pair entries
@@ -105,10 +129,54 @@ __device__ __forceinline__ unsigned quantize_round(float v) {
   return __float_as_uint(__fadd_rd(__fadd_rd(q, 0.5f), 8388608.0f)) & 0x007FFFFFu;
 }
 
-__device__ __forceinline__ void ldg256(const LutPair *p, float (&v)[8]) {
-  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-      : "l"(p));
+struct PairRegs { f32x2_t a_rg, d_rg, b_ad, pad; };   // one x-pair entry = one 256-bit load
+__device__ __forceinline__ PairRegs ldg256(const LutPair *p) {
+  PairRegs v;
+  asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(v.a_rg), "=l"(v.d_rg), "=l"(v.b_ad), "=l"(v.pad) : "l"(p));
+  return v;
+}
+
+// (v.clamp(0,1) * MAXV).round() for the two lanes of a pair: clamps and products scalar, the two round-down adds packed
+template <int MAXV>
+__device__ __forceinline__ void quantize_round2(f32x2_t v, unsigned &o_lo, unsigned &o_hi) {
+  float lo, hi;
+  unpk2(v, lo, hi);
+  const float ql = __fmul_rn(fminf(fmaxf(lo, 0.0f), 1.0f), (float)MAXV), qh = __fmul_rn(fminf(fmaxf(hi, 0.0f), 1.0f), (float)MAXV);
+  const f32x2_t y = add2_rd(add2_rd(pk2(ql, qh), pk2(0.5f, 0.5f)), pk2(8388608.0f, 8388608.0f));
+  float yl, yh;
+  unpk2(y, yl, yh);
+  o_lo = __float_as_uint(yl) & 0x007FFFFFu;
+  o_hi = __float_as_uint(yh) & 0x007FFFFFu;
+}
+
+// RGBA64: the axis entries of the R and G channels evaluated as one f32x2 pair (operator sequence of axis_entry_u16)
+template <bool IDENT>
+__device__ __forceinline__ void axis_entry_u16_pair(unsigned vr, unsigned vg, const float *scale, const float *offset, int size,
+                                                    int stride_g, uint4 &ax, uint4 &ay) {
+  const f32x2_t MAGIC2 = pk2(8388608.0f, 8388608.0f);
+  const float c = 1.0f / 65535.0f;
+  const f32x2_t C2 = pk2(c, c);
+  const f32x2_t vf = sub2_rn(pk2(__uint_as_float(0x4B000000u | vr), __uint_as_float(0x4B000000u | vg)), MAGIC2);
+  const f32x2_t q0 = mul2_rn(vf, C2);                                  // div65535_exact on both lanes:
+  const f32x2_t r = fma2_rn(q0, pk2(-65535.0f, -65535.0f), vf);        //   q0 is consumed by explicit FMAs only
+  const f32x2_t q = fma2_rn(r, C2, q0);
+  float nl, nh;
+  unpk2(q, nl, nh);
+  if (!IDENT) {
+    nl = clamp01_nanpass(__fadd_rn(__fmul_rn(nl, scale[0]), offset[0]));
+    nh = clamp01_nanpass(__fadd_rn(__fmul_rn(nh, scale[1]), offset[1]));
+  }
+  const float sm1 = __fsub_rn((float)size, 1.0f);
+  const f32x2_t pos = pk2(__fmul_rn(nl, sm1), __fmul_rn(nh, sm1));
+  float yl, yh;
+  unpk2(add2_rd(pos, MAGIC2), yl, yh);
+  const unsigned m = (unsigned)(size - 1);
+  const unsigned i0r = min(__float_as_uint(yl) & 0x007FFFFFu, m), i0g = min(__float_as_uint(yh) & 0x007FFFFFu, m);
+  const f32x2_t f0 = sub2_rn(pk2(__uint_as_float(0x4B000000u | i0r), __uint_as_float(0x4B000000u | i0g)), MAGIC2);
+  float tl, th;
+  unpk2(sub2_rn(pos, f0), tl, th);
+  ax = make_uint4(i0r, min(i0r + 1u, m), __float_as_uint(tl), 0u);
+  ay = make_uint4(i0g * (unsigned)stride_g, min(i0g + 1u, m) * (unsigned)stride_g, __float_as_uint(th), 0u);
 }
 
 // apply_1d / apply_3d for one pixel whose channel values are (vr, vg, vb); MAXV = 255 (table axis) or 65535 (inline axis)
@@ -120,30 +188,32 @@ __device__ __forceinline__ void colorlut_eval(const LutDev &L, unsigned vr, unsi
   } else {
     const int s1 = (L.kind == 3) ? L.size : 1, s2 = (L.kind == 3) ? L.size * L.size : 1;
     if (L.ident_domain) {
-      ax = axis_entry_u16<true>(vr, 1.0f, 0.0f, L.size, 1);
-      ay = axis_entry_u16<true>(vg, 1.0f, 0.0f, L.size, s1);
+      axis_entry_u16_pair<true>(vr, vg, L.scale, L.offset, L.size, s1, ax, ay);
       az = axis_entry_u16<true>(vb, 1.0f, 0.0f, L.size, s2);
     } else {
-      ax = axis_entry_u16<false>(vr, L.scale[0], L.offset[0], L.size, 1);
-      ay = axis_entry_u16<false>(vg, L.scale[1], L.offset[1], L.size, s1);
+      axis_entry_u16_pair<false>(vr, vg, L.scale, L.offset, L.size, s1, ax, ay);
       az = axis_entry_u16<false>(vb, L.scale[2], L.offset[2], L.size, s2);
     }
   }
   const float tx = __uint_as_float(ax.z), ty = __uint_as_float(ay.z), tz = __uint_as_float(az.z);
   if (L.kind == 3) {
-    float e00[8], e10[8], e01[8], e11[8];
     const LutPair *base = L.pair + ax.x;
-    ldg256(base + ay.x + az.x, e00);   // (x0|x1, y0, z0)
-    ldg256(base + ay.y + az.x, e10);   // (x0|x1, y1, z0)
-    ldg256(base + ay.x + az.y, e01);   // (x0|x1, y0, z1)
-    ldg256(base + ay.y + az.y, e11);   // (x0|x1, y1, z1)
-#pragma unroll
-    for (int k = 0; k < 3; k++) {      // lerp order x (R) -> y (G) -> z (B), imp.rs:514-525
-      const float c00 = lerp_pre(e00[k], e00[3 + k], tx), c10 = lerp_pre(e10[k], e10[3 + k], tx);
-      const float c01 = lerp_pre(e01[k], e01[3 + k], tx), c11 = lerp_pre(e11[k], e11[3 + k], tx);
-      const float c0 = lerp_exact(c00, c10, ty), c1 = lerp_exact(c01, c11, ty);
-      out[k] = quantize_round<MAXV>(lerp_exact(c0, c1, tz));
-    }
+    const PairRegs e00 = ldg256(base + ay.x + az.x);   // (x0|x1, y0, z0)
+    const PairRegs e10 = ldg256(base + ay.y + az.x);   // (x0|x1, y1, z0)
+    const PairRegs e01 = ldg256(base + ay.x + az.y);   // (x0|x1, y0, z1)
+    const PairRegs e11 = ldg256(base + ay.y + az.y);   // (x0|x1, y1, z1)
+    // lerp order x (R) -> y (G) -> z (B), imp.rs:514-525.  R and G as the two lanes of a pair ...
+    const f32x2_t c00 = lerp_pre2(e00.a_rg, e00.d_rg, tx), c10 = lerp_pre2(e10.a_rg, e10.d_rg, tx);
+    const f32x2_t c01 = lerp_pre2(e01.a_rg, e01.d_rg, tx), c11 = lerp_pre2(e11.a_rg, e11.d_rg, tx);
+    const f32x2_t c0 = lerp_exact2(c00, c10, ty), c1 = lerp_exact2(c01, c11, ty);
+    quantize_round2<MAXV>(lerp_exact2(c0, c1, tz), out[0], out[1]);
+    // ... B scalar
+    float a, d;
+    unpk2(e00.b_ad, a, d); const float b00 = lerp_pre(a, d, tx);
+    unpk2(e10.b_ad, a, d); const float b10 = lerp_pre(a, d, tx);
+    unpk2(e01.b_ad, a, d); const float b01 = lerp_pre(a, d, tx);
+    unpk2(e11.b_ad, a, d); const float b11 = lerp_pre(a, d, tx);
+    out[2] = quantize_round<MAXV>(lerp_exact(lerp_exact(b00, b10, ty), lerp_exact(b01, b11, ty), tz));
   } else {  // three independent 1D tables (imp.rs:399-429, 482-490)
     const float *r = L.lut1d, *g = L.lut1d + L.size, *b = L.lut1d + 2 * L.size;
     out[0] = quantize_round<MAXV>(lerp_exact(__ldg(r + ax.x), __ldg(r + ax.y), tx));

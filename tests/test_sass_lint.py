@@ -1,6 +1,6 @@
 """SASS lint (CPU, needs only cuobjdump): the reference never fuses `a + (b - a) * t`, so the interpolation code of
 the colorlut kernels must not contain FFMA; the only FMAs allowed are the two Newton-correction FMAs of the exact
-x/65535 division in the RGBA64 kernels (3 channels x 2 FMAs x {ident, general domain}) and whatever the compiler's
+x/65535 division in the RGBA64 kernels (scalar for B, one packed f32x2 pair for R,G, x {ident, general domain}) and whatever the compiler's
 own IEEE division / fmodf sequences use in the hsv kernels.  Also proves the Blackwell-native pieces are really in
 the binary: UBLKCP (cp.async.bulk through the TMA engine), SYNCS (mbarrier) and 256-bit LDG."""
 import re
@@ -50,7 +50,11 @@ def test_no_fused_multiply_add_in_u8_colorlut_paths(sass):
 def test_rgba64_kernels_only_contain_the_division_fmas(sass):
     for k in ("colorlut_direct_kernelILi1ELb1E", "colorlut_direct_kernelILi2ELb1E"):
         n = count(sass, k, "FFMA")
-        assert 0 < n <= 12, (k, n)          # 3 channels x 2 FMAs x 2 domain variants
+        assert 0 < n <= 12, (k, n)          # B channel: 2 scalar FMAs x 2 domain variants (R,G: the packed pair below)
+        # R and G share one f32x2 division: FMUL2 (its product feeds explicit FMAs only) + 2 FFMA2 per domain variant;
+        # no other packed multiply may exist (ptxas would contract it with a packed add into FFMA2)
+        assert count(sass, k, "FFMA2") <= 4 and count(sass, k, "FMUL2") <= 2, k
+        assert count(sass, k, "FADD2") >= 8, k   # the packed R,G lerps really are in the binary
         # per-pixel conversions use the 2^23 magic number; the only conversion left is the per-thread `size as f32`
         assert count(sass, k, "F2I") == 0 and count(sass, k, "I2F") == 0 and count(sass, k, "I2FP") <= 2, k
         assert count(sass, k, r"LDG\.E\.ENL2\.256") >= 4 or any("256" in i for n_, b in sass.items() if k in n_ for i in b if i.startswith("LDG")), k
