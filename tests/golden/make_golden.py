@@ -70,10 +70,25 @@ def cases():
     out.append(("blockhash/RGBA/3840x2160/ramps", lambda api: api.blockhash("RGBA", 3840, 2160, synth.frame_ramps("RGBA", 3840, 2160))))
     for (w, h, stride, r) in ((1920, 1080, 1920, 64), (64, 50, 64, 12), (33, 17, 36, 5), (640, 480, 640, 0)):
         out.append(("roundmask/%dx%d/r%d" % (w, h, r), lambda api, w=w, h=h, stride=stride, r=r: api.roundmask(w, h, stride, r)))
+    for fmt in ("RGB", "RGBA", "ARGB", "BGR", "BGRA"):
+        bpp = 3 if fmt in ("RGB", "BGR") else 4
+        for (w, h, q, mc) in ((317, 43, 10, 2), (640, 480, 1, 5)):
+            out.append(("colordetect/%s/%dx%d/q%d/noise" % (fmt, w, h, q),
+                        lambda api, fmt=fmt, w=w, h=h, q=q, mc=mc, bpp=bpp: api.colordetect(fmt, w, h, synth.frame_noise("RGBA", w, h, 0x5EED0006)[:, :bpp * w].copy(), q, mc)))
+    out.append(("colordetect/RGBA/3840x2160/q10/ramps", lambda api: api.colordetect("RGBA", 3840, 2160, synth.frame_ramps("RGBA", 3840, 2160), 10, 2)))
+    out.append(("colordetect/RGBA/3840x2160/q1/natural", lambda api: api.colordetect("RGBA", 3840, 2160, synth.frame_natural("RGBA", 3840, 2160, 0x5EED0007, amp=3), 1, 8)))
     return out
 
 
+def _cd_pack(hist, pal):
+    return np.concatenate([np.asarray(hist, np.uint32), np.asarray(pal, np.uint32).reshape(-1)])
+
+
 class OracleApi:
+    def colordetect(self, fmt, w, h, frame, quality, max_colors):
+        hist = orc.colordetect_histogram(fmt, w, h, frame, quality)
+        return _cd_pack(hist, orc.colordetect_palette(hist, max_colors))
+
     def colorlut(self, text, fmt, w, h, frame):
         return orc.colorlut_apply(orc.cube_parse(text), fmt, w, h, frame, threads=8)
 
