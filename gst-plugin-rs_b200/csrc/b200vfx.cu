@@ -25,6 +25,7 @@
 #include "blockhash_tma.cuh"
 #include "tile_gather.cuh"
 #include "colordetect.cuh"
+#include "memo_tile.cuh"
 
 using namespace b200vfx;
 
@@ -74,6 +75,7 @@ struct b200vfx_ctx {
   int stream_cfg = 0, stream_ctas = 0, stream_hint = 1, memo_px = 8;  // tuning knobs (env overrides, see ctx_create)
   uint64_t launches = 0;
   int tg_path = 0, tg_cfg = 0, tg_ctas = 8;   // fused tile gather: 0 register path (LDG/STG), 1 TMA; variant; CTAs per SM
+  int memo_tile = 0;     // 4-byte-pixel table lookups through memo_tile_kernel (per-tile shared-memory copy of the colour sub-cube)
   int cd_cluster = 2;    // colordetect: CTAs per cluster merging their shared-memory histograms (1, 2, 4, 8)
   int peer_timeout_ms = 2000;  // deadline of the cross-GPU waits in the tile-gather kernel
   std::string err;
@@ -400,6 +402,13 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
     with_l2_window l2w(c, c->lut_kind == 3 ? c->d_memo : nullptr, sizeof(uint32_t) << 24);
     int w = f.width, h = f.height;
     long ss = f.sstride, ds = f.dstride;
+    if (c->memo_tile && c->lut_kind == 3 && (w % 4) == 0 && aligned(f.src, ss, 16) && aligned(f.dst, ds, 16)) {
+      dim3 grid((unsigned)ceil_div(w, kTileW), (unsigned)ceil_div(h, kTileH));
+      CU(c, launch_k(c->pdl_now, memo_tile_kernel<0, false>, grid, dim3(256), 0, st, c->d_memo, f.src, ss, f.dst, ds, w, h));
+      c->launches++;
+      CU(c, cudaGetLastError());
+      return 0;
+    }
     if (al && ss == 4L * w && ds == 4L * w && (long long)w * h < (1LL << 28)) { w = w * h; h = 1; }  // packed: 1-D
     const bool al16 = aligned(f.src, ss, 16) && aligned(f.dst, ds, 16) && (w % 4) == 0;
     const bool use_stream = c->stream_path == 1 || (c->stream_path < 0 && c->lut_kind == 1);
@@ -492,6 +501,16 @@ int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings 
     if (ss == 4L * w && (long long)w * h < (1LL << 28)) { ww = w * h; hh = 1; }
     const Span sp = span_of(data, stride, (size_t)w * 4, h);
     const bool pdl = pdl_admit(c->pdl && !built_now, st, sp, sp);
+    if (c->memo_tile && (w % 4) == 0 && aligned(data, stride, 16)) {
+      dim3 tgrid((unsigned)ceil_div(w, kTileW), (unsigned)ceil_div(h, kTileH));
+#define LT(CO, BG) CU(c, launch_k(pdl, memo_tile_kernel<CO, BG>, tgrid, dim3(256), 0, st, memo, (const uint8_t *)data, stride, data, stride, w, h))
+      if (fi.coff == 0) { if (fi.bgr) LT(0, true); else LT(0, false); }
+      else { if (fi.bgr) LT(1, true); else LT(1, false); }
+#undef LT
+      c->launches++;
+      CU(c, cudaGetLastError());
+      return 0;
+    }
     with_l2_window l2w(c, memo, sizeof(uint32_t) << 24);
     dim3 grid((unsigned)ceil_div(ww, 8 * 32 * 4), grid_rows(hh));
 #define LM(CO, BG) CU(c, launch_k(pdl, map_u32_kernel<HsvFilterMemoOp<CO, BG>, 4>, grid, dim3(256), 0, st, HsvFilterMemoOp<CO, BG>{memo}, (const uint8_t *)data, ss, data, ss, ww, hh))
@@ -830,6 +849,7 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "peer_timeout_ms") c->peer_timeout_ms = value > 0 ? value : 1;
   else if (n == "zero_copy") { c->zero_copy = value; c->zc_calls = 0; c->zc_best_ms[0] = c->zc_best_ms[1] = 1e30; }
   else if (n == "blockhash_tma") c->blockhash_tma = value != 0;
+  else if (n == "memo_tile") c->memo_tile = value != 0;
   else if (n == "cd_cluster") c->cd_cluster = (value == 1 || value == 2 || value == 4 || value == 8) ? value : 2;
   else if (n == "l2_persist") c->l2_persist = value;
   else if (n == "zc_cfg") c->zc_cfg = value;

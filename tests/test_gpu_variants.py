@@ -76,3 +76,59 @@ def test_videocompare_config4_two_4k_streams(ctx):
     ba, bb = b200vfx.blockhash_bits(sa, w, h), b200vfx.blockhash_bits(sb, w, h)
     assert (ba == orc.blockhash_bits(sa, w, h)).all() and (bb == orc.blockhash_bits(sb, w, h)).all()
     assert b200vfx.hash_distance(ba, ba) == 0 and 0 <= b200vfx.hash_distance(ba, bb) <= 8
+
+
+@pytest.mark.parametrize("content", ["natural", "ramps", "noise", "mixed"])
+def test_memo_tile_kernel_matches_oracle(ctx, content):
+    """memo_tile_kernel (option memo_tile=1): per-tile shared-memory copy of the colour sub-cube when it fits, direct
+    gathers otherwise -- decided per 64x64 tile; partial tiles at the right/bottom edge, padded strides, host + device"""
+    torch = pytest.importorskip("torch")
+    cube = orc.cube_parse(synth.cube_text_3d(33, "mix"))
+    ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+    ctx.set_option("memo_tile", 1)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        for (w, h, pad) in ((3840, 2160, 0), (1920, 1080, 0), (100, 70, 16), (64, 64, 0), (4, 1, 0), (1000, 3, 48), (260, 129, 0)):
+            stride = 4 * w + pad
+            if content == "natural":
+                frame = synth.frame_natural("RGBA", w, h, 11, amp=3)
+            elif content == "ramps":
+                frame = synth.frame_ramps("RGBA", w, h)
+            elif content == "noise":
+                frame = synth.frame_noise("RGBA", w, h, 12)
+            else:  # left half smooth (cached tiles), right half random (gather tiles), one constant tile
+                frame = synth.frame_natural("RGBA", w, h, 13, amp=2)
+                nz = synth.frame_noise("RGBA", w, h, 14)
+                frame[:, 2 * w:] = nz[:, 2 * w:4 * w]
+                frame[: min(h, 64), : min(4 * w, 256)] = 0x40
+            src = np.full((h, stride), 0xA5, np.uint8)
+            src[:, :4 * w] = frame[:, :4 * w]
+            exp = orc.colorlut_apply(cube, "RGBA", w, h, src, dst_stride=stride, threads=8)
+            d_in = torch.from_numpy(src).cuda()
+            d_out = torch.full((h, stride), 0x5A, dtype=torch.uint8, device="cuda")
+            ctx.colorlut_process("RGBA", w, h, d_in, stride, d_out, stride)
+            torch.cuda.synchronize()
+            assert (d_out.cpu().numpy() == exp).all(), (w, h, pad)       # includes the untouched padding (0x5A)
+    finally:
+        ctx.set_option("memo_tile", 0)
+
+
+@pytest.mark.parametrize("fmt", ["RGBA", "xRGB", "BGRx", "ABGR"])
+def test_memo_tile_kernel_hsvfilter_in_place(ctx, fmt):
+    torch = pytest.importorskip("torch")
+    kw = dict(hue_shift=33.0, saturation_mul=1.1, value_off=-0.05)
+    okw = dict(hue_shift=33.0, sat_mul=1.1, val_off=-0.05)
+    ctx.set_option("memo_tile", 1)
+    ctx.set_option("hsv_memo", 1)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        for (w, h) in ((1920, 1080), (132, 70), (64, 5)):
+            for frame in (synth.frame_natural(fmt, w, h, 5, amp=3), synth.frame_noise(fmt, w, h, 6)):
+                exp = orc.hsvfilter(fmt, w, h, frame.copy(), threads=8, **okw)
+                d = torch.from_numpy(frame).cuda()
+                ctx.hsvfilter_process(fmt, w, h, d, frame.shape[1], **kw)
+                torch.cuda.synchronize()
+                assert (d.cpu().numpy() == exp).all(), (fmt, w, h)
+    finally:
+        ctx.set_option("memo_tile", 0)
+        ctx.set_option("hsv_memo", -1)
