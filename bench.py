@@ -324,8 +324,15 @@ def main():
     # per-content breakdown (rank 0, N=1 only): ramps-only / noise-only GOPs
     breakdown = {}
     if N == 1:
-        for name in ("ramps", "noise"):
+        # "natural" (ramps +- 3 of sensor-like noise, not part of `value`) is reported next to the two contents the workload names
+        nat_in = [torch.from_numpy(synth.frame_natural("RGBA", W4K, H4K, 0x5EED0020 + i, amp=3)).cuda() for i in range(4)]
+        nat_out = [torch.empty_like(t_) for t_ in nat_in]
+        for name in ("ramps", "noise", "natural"):
             idx = [i for i in range(RING) if kinds[i] == name]
+            if name == "natural":
+                base_n = len(d_in)
+                d_in.extend(nat_in); d_out.extend(nat_out)
+                idx = list(range(base_n, base_n + 4))
             def run_kind():
                 for i in range(args.gop):
                     j = idx[i % len(idx)]

@@ -124,3 +124,84 @@ def test_blockhash_bits_and_distance_host_side():
     assert b200vfx.blockhash_bits(solid, 3840, 2160).sum() == 0
     a = b200vfx.blockhash_bits(rng.integers(0, 2 ** 31, 64, dtype=np.uint32), 3840, 2160)
     assert b200vfx.hash_distance(a, a) == 0 and b200vfx.hash_distance(a, 1 - a) == 64
+
+
+# ---- differential fuzz: product parser (C++) vs oracle parser (C) on generated .cube-like text ------------------------
+def _fuzz_strategy():
+    from hypothesis import strategies as st
+    num = st.one_of(
+        st.sampled_from(["0", "1", "0.5", "-0.25", "+1.5", ".5", "5.", "1e-3", "1E+2", "1e400", "-1e-60", "inf", "-inf", "NaN", "nan",
+                         "infinity", "+Infinity", "0x10", "1f", "1_0", "1e", "e5", ".", "+", "--1", "1.2.3", "٣", "1e+", "0.1e-0"]),
+        st.floats(allow_nan=False, allow_infinity=False, width=32).map(lambda v: repr(float(v))),
+        st.integers(-3, 70000).map(str))
+    ws = st.sampled_from([" ", "  ", "\t", "　", " \t ", " "])
+    data_line = st.lists(num, min_size=1, max_size=5).flatmap(lambda xs: ws.map(lambda w: w.join(xs)))
+    kw_line = st.one_of(
+        st.tuples(st.sampled_from(["LUT_1D_SIZE", "LUT_3D_SIZE", "lut_1d_size", "LUT_2D_SIZE"]), st.sampled_from(["2", "3", "1", "+2", "-2", "2 2", "", "257", "x", "2.0"])).map(" ".join),
+        st.tuples(st.sampled_from(["DOMAIN_MIN", "DOMAIN_MAX"]), st.lists(num, min_size=2, max_size=4).map(" ".join)).map(" ".join),
+        st.sampled_from(['TITLE "a b"', "TITLE", "# comment", "", "   ", "LUT_3D_INPUT_RANGE 0 1", "#LUT_1D_SIZE 9"]))
+    line = st.one_of(kw_line, data_line, data_line, data_line)
+    eol = st.sampled_from(["\n", "\r\n", "\n", "\r", "\n\n"])
+    return st.lists(st.tuples(line, eol), min_size=0, max_size=14).map(lambda ls: "".join(a + b for a, b in ls))
+
+
+def test_product_parser_differential_fuzz():
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, HealthCheck
+
+    seen = {"ok": 0, "bad": 0}
+
+    @settings(max_examples=600, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(_fuzz_strategy())
+    def run(text):
+        try:
+            o = orc.cube_parse(text)
+        except orc.CubeError:
+            o = None
+        try:
+            p = b200vfx.cube_parse(text)
+        except b200vfx.B200VfxError as e:
+            assert e.code == b200vfx.ERR_PARSE
+            p = None
+        assert (o is None) == (p is None), repr(text)
+        if o is not None:
+            k, s, v, sc, of = p
+            assert (k, s) == (o.kind, o.size), repr(text)
+            assert v.tobytes() == o.values.tobytes() and sc.tobytes() == o.scale.tobytes() and of.tobytes() == o.offset.tobytes(), repr(text)
+            seen["ok"] += 1
+        else:
+            seen["bad"] += 1
+
+    run()
+    assert seen["bad"] > 50   # most random texts are invalid; valid ones are exercised by the structured generator below
+
+
+def test_product_parser_differential_fuzz_valid_shapes():
+    """structured generator: always a well-formed header + the right number of data lines, numbers in odd but legal forms"""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, HealthCheck, strategies as st
+
+    forms = st.sampled_from(["0", "1", "0.5", "-0.25", "+1.5", ".5", "5.", "1e-3", "1E+2", "1e400", "-1e-60", "inf", "-inf", "NaN",
+                             "infinity", "0.1e-0", "007", "1e0000000002", "0.30000001192092896", "16777217", "3.4028236e38"])
+    n_ok = {"n": 0}
+
+    @settings(max_examples=150, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(st.data())
+    def run(data):
+        kind = data.draw(st.sampled_from([1, 3]))
+        size = data.draw(st.integers(2, 4))
+        n = size if kind == 1 else size ** 3
+        head = ["LUT_%dD_SIZE %d" % (kind, size)]
+        if data.draw(st.booleans()):
+            head.insert(data.draw(st.integers(0, 1)), "DOMAIN_MIN %s" % " ".join(data.draw(st.lists(st.sampled_from(["0", "-1", "0.25", "-0.5"]), min_size=3, max_size=3))))
+            head.insert(data.draw(st.integers(0, 2)), "DOMAIN_MAX %s" % " ".join(data.draw(st.lists(st.sampled_from(["1", "2", "0.75", "1.5"]), min_size=3, max_size=3))))
+        lines = head + [" ".join(data.draw(st.lists(forms, min_size=3, max_size=3))) for _ in range(n)]
+        text = data.draw(st.sampled_from(["\n", "\r\n"])).join(lines) + "\n"
+        o = orc.cube_parse(text)
+        k, s, v, sc, of = b200vfx.cube_parse(text)
+        assert (k, s) == (o.kind, o.size) and v.tobytes() == o.values.tobytes(), repr(text)
+        assert sc.tobytes() == o.scale.tobytes() and of.tobytes() == o.offset.tobytes(), repr(text)
+        n_ok["n"] += 1
+
+    run()
+    assert n_ok["n"] >= 100
