@@ -18,10 +18,12 @@ ap.add_argument("--content", default="ramps", choices=["ramps", "noise", "natura
 ap.add_argument("--lut", type=int, default=33)
 ap.add_argument("--launches", type=int, default=6)
 ap.add_argument("--quality", type=int, default=1)
+ap.add_argument("--memo-tile", type=int, default=0)
 a = ap.parse_args()
 W, H = 3840, 2160
 ctx = b200vfx.Context(0)
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+ctx.set_option("memo_tile", a.memo_tile)
 
 
 def frame(fmt, w, h, i):
