@@ -7,7 +7,7 @@ launched under torchrun, one rank per GPU.  Rank 0 prints ONE JSON line.
 Workload = BASELINE.json configs[1]: colorlut, generated "mix" 33^3 .cube, 3840x2160 RGBA frames,
 synthetic frames A ("ramps", coherent) and B ("noise", PCG32) of SURVEY Appendix F, alternating.
 A STEP = one GOP of `--gop` (default 64) frames through the element; the inputs of a step are a ring
-of 8 distinct frames and 8 distinct outputs (531 MB > the 126 MB L2), so no frame is L2-resident when
+of 12 distinct frames and 12 distinct outputs (796 MB > the 126 MB L2), so no frame is L2-resident when
 it is processed ("inputs larger than L2"; no explicit flush: the memo LUT is *meant* to live in L2).
   value : device-resident frames/s (frames already in HBM), CUDA events on the launching stream.
   e2e   : the same GOPs through the same C-ABI call with HOST (pinned) buffers, H2D and D2H inside.
@@ -33,7 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 W4K, H4K = 3840, 2160
 FRAME_BYTES = W4K * H4K * 4
 ALGO_BYTES_PER_FRAME = 2 * FRAME_BYTES  # 33 177 600 read + 33 177 600 written
-RING = 8
+RING = 12
 METRIC = "colorlut_4k_rgba_frames_per_sec"
 WORKLOAD = "colorlut 33^3 .cube on 3840x2160 RGBA synthetic stream (frames A ramps / B noise alternating)"
 
@@ -92,7 +92,7 @@ def hbm_peak_gbs():
 
 
 def make_frames(np, synth):
-    """ring of 8 distinct 4K frames: A (ramps, rolled so each is distinct) and B (noise, 4 seeds) alternating"""
+    """ring of RING distinct 4K frames: A (ramps, rolled so each is distinct) and B (noise, distinct seeds) alternating"""
     base = synth.frame_ramps("RGBA", W4K, H4K)
     frames, kinds = [], []
     for i in range(RING):
@@ -465,7 +465,7 @@ def main():
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 (f32 LUT arithmetic)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "lut": "33^3 mix .cube", "frame": "3840x2160 RGBA stride 15360",
-                       "frames_per_step": args.gop * N, "ring_frames": RING, "l2": "inputs larger than L2 (8 in + 8 out frames = 531 MB ring, no flush)",
+                       "frames_per_step": args.gop * N, "ring_frames": RING, "l2": "inputs larger than L2 (%d in + %d out frames = %d MB ring, no flush)" % (RING, RING, 2 * RING * FRAME_BYTES // 1000000),
                        "colorlut_mode": "memo" if args.mode == 0 else "direct",
                        "sharding": "row tiles, rank r owns rows [r*H/N,(r+1)*H/N) of every frame; no data-path collective"},
             "gpu_launches": total_launches,

@@ -75,6 +75,8 @@ struct b200vfx_ctx {
   int stream_cfg = 0, stream_ctas = 0, stream_hint = 1, memo_px = 8;  // tuning knobs (env overrides, see ctx_create)
   uint64_t launches = 0;
   int tg_path = 0, tg_cfg = 0, tg_ctas = 8;   // fused tile gather: 0 register path (LDG/STG), 1 TMA; variant; CTAs per SM
+  int memo_ctas = 4;     // CTAs per SM of the persistent table-lookup kernels: 4 x 256 threads = half the thread slots, so the next
+                         // frame's kernel (PDL) is resident beside this one (profiles/r01_memo_ctas_experiment.jsonl)
   int memo_tile = 0;     // 4-byte-pixel table lookups through memo_tile_kernel (per-tile shared-memory copy of the colour sub-cube)
   int cd_cluster = 2;    // colordetect: CTAs per cluster merging their shared-memory histograms (1, 2, 4, 8)
   int peer_timeout_ms = 2000;  // deadline of the cross-GPU waits in the tile-gather kernel
@@ -232,10 +234,20 @@ int ensure_l2_set_aside(b200vfx_ctx *c, size_t want) {
 // PDL overlap is only used when the new kernel cannot conflict with any of OUR recent (possibly still running)
 // kernels on the same stream: its output must not touch their inputs/outputs and its input must not be one of
 // their outputs.  The tracker is process-wide (elements chained on one stream use different contexts).
+// Which of OUR earlier launches on a stream may still be running when a new PDL launch starts?
+//  * Persistent kernels with a capped grid (large frames) end on griddepcontrol.wait ("linger"): they complete in launch
+//    order and their CTAs keep their SM slots until the previous kernel has completed.  Kernel i starts only after i-1 is
+//    fully resident; if an older kernel j is still incomplete, ALL CTAs of j+1 .. i-1 are still resident, so their thread
+//    counts sum to less than what the device holds.  Walking back from the newest launch, the point where that sum reaches
+//    the device's thread capacity ends the list of possibly-running launches (2 launches for 4 CTAs per SM).
+//  * Anything else (small frames, non-persistent kernels) does not linger -- the wait costs ~3 us of completion latency per
+//    kernel, which small frames cannot hide: there the last 4 launches are assumed to be possibly running, as before.
+constexpr size_t kPdlQueueMax = 16;
 struct Span { uintptr_t lo, hi; };
-struct RecentLaunch { Span src, dst; };
+struct RecentLaunch { Span src, dst; long long threads; bool lingers; };
 std::mutex g_recent_mu;
 std::map<cudaStream_t, std::deque<RecentLaunch>> g_recent;
+long long g_capacity_threads = 148LL * 2048;   // largest (SM count x resident threads per SM) of the devices in use
 
 inline Span span_of(const void *p, long stride, size_t row_bytes, int rows) {
   if (!p || rows <= 0) return Span{0, 0};
@@ -249,13 +261,33 @@ bool pdl_admit(bool want, cudaStream_t st, Span src, Span dst) {
   std::lock_guard<std::mutex> g(g_recent_mu);
   std::deque<RecentLaunch> &q = g_recent[st];
   bool ok = want;
-  if (ok)
-    for (const RecentLaunch &r : q)
-      if (overlap(dst, r.src) || overlap(dst, r.dst) || overlap(src, r.dst)) { ok = false; break; }
+  if (ok) {
+    long long newer = 0;   // threads of the launches newer than the one being examined
+    int count = 0;
+    bool all_linger = true;
+    for (auto r = q.rbegin(); r != q.rend(); ++r) {
+      if (all_linger ? newer >= g_capacity_threads : count >= 4) break;   // *r and everything older has completed
+      if (overlap(dst, r->src) || overlap(dst, r->dst) || overlap(src, r->dst)) { ok = false; break; }
+      newer += r->threads;
+      all_linger = all_linger && r->lingers;
+      count++;
+    }
+  }
   if (!ok) q.clear();  // a normal launch starts only after everything before it has completed
-  q.push_back(RecentLaunch{src, dst});
-  if (q.size() > 4) q.pop_front();
+  q.push_back(RecentLaunch{src, dst, 0, false});
+  if (q.size() > kPdlQueueMax) q.pop_front();
   return ok;
+}
+void pdl_note_linger(cudaStream_t st) {   // the launch just admitted ends on griddepcontrol.wait
+  std::lock_guard<std::mutex> g(g_recent_mu);
+  auto it = g_recent.find(st);
+  if (it != g_recent.end() && !it->second.empty()) it->second.back().lingers = true;
+}
+// size of the launch just admitted (called by launch_k)
+void pdl_note_threads(cudaStream_t st, long long threads) {
+  std::lock_guard<std::mutex> g(g_recent_mu);
+  auto it = g_recent.find(st);
+  if (it != g_recent.end() && !it->second.empty()) it->second.back().threads = threads;
 }
 void pdl_forget(cudaStream_t st) {  // after a stream synchronisation nothing of ours is in flight
   std::lock_guard<std::mutex> g(g_recent_mu);
@@ -266,6 +298,7 @@ template <typename... KArgs, typename... Args>
 cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  pdl_note_threads(st, (long long)grid.x * grid.y * grid.z * block.x * block.y * block.z);
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
@@ -416,10 +449,13 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
       if (int rc = launch_memo_stream(c, f.src, ss, f.dst, ds, 4 * w, h, st)) return rc;
     } else if (al) {
       const int PX = c->memo_px;
-      dim3 grid((unsigned)ceil_div(w, 8 * 32 * PX), grid_rows(h));
+      const long long items = (long long)ceil_div(w, 8 * 32 * PX) * h, cap = (long long)c->sm_count * c->memo_ctas;
+      dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(items, cap)));
+      const int linger = (c->pdl_now && items > cap) ? 1 : 0;   // capped grid: consecutive frames overlap deeply
+      if (linger) pdl_note_linger(st);
 #define LAUNCH_PLAIN(P)                                                                                               \
   do {                                                                                                                \
-    if (c->lut_kind == 3) CU(c, launch_k(c->pdl_now, colorlut_memo_apply_kernel<P>, grid, dim3(256), 0, st, c->d_memo, f.src, ss, f.dst, ds, w, h));  \
+    if (c->lut_kind == 3) CU(c, launch_k(c->pdl_now, colorlut_memo_apply_kernel<P>, grid, dim3(256), 0, st, c->d_memo, f.src, ss, f.dst, ds, w, h, linger));  \
     else CU(c, launch_k(c->pdl_now, colorlut_memo1d_apply_kernel<P>, grid, dim3(256), 0, st, c->d_memo1d, f.src, ss, f.dst, ds, w, h));              \
   } while (0)
       if (PX == 16) LAUNCH_PLAIN(16); else if (PX == 8) LAUNCH_PLAIN(8); else LAUNCH_PLAIN(4);
@@ -512,8 +548,11 @@ int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings 
       return 0;
     }
     with_l2_window l2w(c, memo, sizeof(uint32_t) << 24);
-    dim3 grid((unsigned)ceil_div(ww, 8 * 32 * 4), grid_rows(hh));
-#define LM(CO, BG) CU(c, launch_k(pdl, map_u32_kernel<HsvFilterMemoOp<CO, BG>, 4>, grid, dim3(256), 0, st, HsvFilterMemoOp<CO, BG>{memo}, (const uint8_t *)data, ss, data, ss, ww, hh))
+    const long long items = (long long)ceil_div(ww, 8 * 32 * 4) * hh, cap = (long long)c->sm_count * c->memo_ctas;
+    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(items, cap)));
+    const int linger = (pdl && items > cap) ? 1 : 0;
+    if (linger) pdl_note_linger(st);
+#define LM(CO, BG) CU(c, launch_k(pdl, map_u32_kernel<HsvFilterMemoOp<CO, BG>, 4>, grid, dim3(256), 0, st, HsvFilterMemoOp<CO, BG>{memo}, (const uint8_t *)data, ss, data, ss, ww, hh, linger))
     if (fi.coff == 0) { if (fi.bgr) LM(0, true); else LM(0, false); }
     else { if (fi.bgr) LM(1, true); else LM(1, false); }
 #undef LM
@@ -591,8 +630,11 @@ int launch_hsvdetector(b200vfx_ctx *c, const FmtInfo &fi, const FmtInfo &fo, con
     if (fi.bpp == 4 && aligned(f.src, f.sstride, 4) && aligned(f.dst, f.dstride, 4)) {  // table-lookup map kernel
       int ww = f.width, hh = f.height;
       if (f.sstride == 4L * ww && f.dstride == 4L * ww && (long long)ww * hh < (1LL << 28)) { ww = ww * hh; hh = 1; }
-      dim3 grid((unsigned)ceil_div(ww, 8 * 32 * 4), grid_rows(hh));
-#define LD(IC, IB, OC, OB) CU(c, launch_k(pdl, map_u32_kernel<HsvDetectBitmapOp<IC, IB, OC, OB>, 4>, grid, dim3(256), 0, st, HsvDetectBitmapOp<IC, IB, OC, OB>{bitmap}, f.src, f.sstride, f.dst, f.dstride, ww, hh))
+      const long long items = (long long)ceil_div(ww, 8 * 32 * 4) * hh, cap = (long long)c->sm_count * c->memo_ctas;
+      dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(items, cap)));
+      const int linger = (pdl && items > cap) ? 1 : 0;
+      if (linger) pdl_note_linger(st);
+#define LD(IC, IB, OC, OB) CU(c, launch_k(pdl, map_u32_kernel<HsvDetectBitmapOp<IC, IB, OC, OB>, 4>, grid, dim3(256), 0, st, HsvDetectBitmapOp<IC, IB, OC, OB>{bitmap}, f.src, f.sstride, f.dst, f.dstride, ww, hh, linger))
 #define LD2(IC, IB) do { if (fo.coff == 0) { if (fo.bgr) LD(IC, IB, 0, true); else LD(IC, IB, 0, false); } else { if (fo.bgr) LD(IC, IB, 1, true); else LD(IC, IB, 1, false); } } while (0)
       if (fi.coff == 0) { if (fi.bgr) LD2(0, true); else LD2(0, false); }
       else { if (fi.bgr) LD2(1, true); else LD2(1, false); }
@@ -775,6 +817,12 @@ int b200vfx_ctx_create(b200vfx_ctx **out, int device) {
     if (const char *e = getenv("B200VFX_L2_PERSIST")) c->l2_persist = atoi(e);
   }
   if (c->sm_count <= 0) c->sm_count = 148;
+  {
+    int tps = 0;
+    if (cudaDeviceGetAttribute(&tps, cudaDevAttrMaxThreadsPerMultiProcessor, device) != cudaSuccess || tps <= 0) tps = 2048;
+    std::lock_guard<std::mutex> g(g_recent_mu);
+    g_capacity_threads = std::max(g_capacity_threads, (long long)c->sm_count * tps);   // larger = more conservative
+  }
   if (const char *e = getenv("B200VFX_STREAM_PATH")) c->stream_path = atoi(e);
   if (const char *e = getenv("B200VFX_STREAM_CFG")) c->stream_cfg = atoi(e);
   if (const char *e = getenv("B200VFX_STREAM_CTAS")) c->stream_ctas = atoi(e);
@@ -850,6 +898,7 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "zero_copy") { c->zero_copy = value; c->zc_calls = 0; c->zc_best_ms[0] = c->zc_best_ms[1] = 1e30; }
   else if (n == "blockhash_tma") c->blockhash_tma = value != 0;
   else if (n == "memo_tile") c->memo_tile = value != 0;
+  else if (n == "memo_ctas") c->memo_ctas = std::max(2, std::min(8, value));
   else if (n == "cd_cluster") c->cd_cluster = (value == 1 || value == 2 || value == 4 || value == 8) ? value : 2;
   else if (n == "l2_persist") c->l2_persist = value;
   else if (n == "zc_cfg") c->zc_cfg = value;

@@ -36,6 +36,18 @@ __device__ __forceinline__ uint32_t memo_index_full(uint32_t c) {  // c = r | g<
 }
 // PDL: let the next (independent) frame's kernel start as soon as every CTA of this one has been scheduled
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// ... and (persistent, capped grids) do not RETIRE before the previous kernel of the stream has completed: such kernels
+// complete in launch order however deeply consecutive frames overlap, and their CTAs hold their SM slots until then, which
+// bounds how many of them can be in flight (pdl_admit, b200vfx.cu).  No-op for a normal launch.  Costs ~3 us of completion
+// latency per kernel, hidden for large frames, not for 640x480 ones -- hence only for capped grids.
+#ifndef B200VFX_EXP_NO_TAIL_WAIT   // timing experiment only
+#define B200VFX_EXP_NO_TAIL_WAIT 0
+#endif
+__device__ __forceinline__ void pdl_wait_prior() {
+#if !B200VFX_EXP_NO_TAIL_WAIT
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 
 // --------------------------------------------------------------------------------------------
 // colorlut table builders (once per LUT): axis tables and, on the host, the x-pair table
@@ -132,12 +144,18 @@ template <int PX>
 __global__ void __launch_bounds__(256) colorlut_memo_apply_kernel(const uint32_t *__restrict__ memo,
                                                                   const uint8_t *__restrict__ src, long sstride,
                                                                   uint8_t *__restrict__ dst, long dstride,
-                                                                  int width, int height) {
+                                                                  int width, int height, int linger) {
   pdl_trigger();
+  // Persistent: the grid is capped at a few CTAs per SM (option "memo_ctas") and every CTA walks over work items
+  // (item = row x 2048*PX/8-pixel chunk).  All CTAs are resident at once, so the NEXT frame's kernel (PDL) starts
+  // immediately and runs beside this one: a gather-bound frame and an HBM-bound frame then share the SMs.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int x0 = (blockIdx.x * (blockDim.x >> 5) + warp) * (32 * PX) + lane;
-  if (x0 - lane >= width) return;
-  for (int row = blockIdx.y; row < height; row += gridDim.y) {
+  const int chunks_x = (width + 8 * 32 * PX - 1) / (8 * 32 * PX);
+  const long long items = (long long)chunks_x * height;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int row = (int)(item / chunks_x), cx = (int)(item - (long long)row * chunks_x);
+    const int x0 = (cx * 8 + warp) * (32 * PX) + lane;
+    if (x0 - lane >= width) continue;
     const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)row * sstride);
     uint32_t *d = reinterpret_cast<uint32_t *>(dst + (size_t)row * dstride);
     uint32_t px[PX], o[PX];
@@ -149,6 +167,7 @@ __global__ void __launch_bounds__(256) colorlut_memo_apply_kernel(const uint32_t
     for (int k = 0; k < PX; k++)
       if (x0 + 32 * k < width) st_stream_u32(d + x0 + 32 * k, o[k] | (px[k] & 0xFF000000u));
   }
+  if (linger) pdl_wait_prior();   // capped grids only (large frames): see pdl_admit in b200vfx.cu
 }
 
 // 1D LUT: three 256-byte tables in shared memory
@@ -333,12 +352,16 @@ struct HsvDetectBitmapOp {  // bitmap bit index = r | g<<8 | b<<16
 
 template <typename Op, int PX>
 __global__ void __launch_bounds__(256) map_u32_kernel(Op op, const uint8_t *__restrict__ src, long sstride,
-                                                      uint8_t *__restrict__ dst, long dstride, int width, int height) {
+                                                      uint8_t *__restrict__ dst, long dstride, int width, int height,
+                                                      int linger) {
   pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int x0 = (blockIdx.x * (blockDim.x >> 5) + warp) * (32 * PX) + lane;
-  if (x0 - lane >= width) return;
-  for (int row = blockIdx.y; row < height; row += gridDim.y) {
+  const int chunks_x = (width + 8 * 32 * PX - 1) / (8 * 32 * PX);   // persistent like colorlut_memo_apply_kernel
+  const long long items = (long long)chunks_x * height;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int row = (int)(item / chunks_x), cx = (int)(item - (long long)row * chunks_x);
+    const int x0 = (cx * 8 + warp) * (32 * PX) + lane;
+    if (x0 - lane >= width) continue;
     const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)row * sstride);
     uint32_t *d = reinterpret_cast<uint32_t *>(dst + (size_t)row * dstride);
     uint32_t px[PX], o[PX];
@@ -350,6 +373,7 @@ __global__ void __launch_bounds__(256) map_u32_kernel(Op op, const uint8_t *__re
     for (int k = 0; k < PX; k++)
       if (x0 + 32 * k < width) st_stream_u32(d + x0 + 32 * k, o[k]);
   }
+  if (linger) pdl_wait_prior();
 }
 
 // --------------------------------------------------------------------------------------------

@@ -93,6 +93,7 @@ uint64_t b200vfx_ctx_kernel_launches(const b200vfx_ctx *ctx);
  * "hsv_memo" -1 auto | 0 never | 1 at once (settings-keyed answer tables of hsvfilter / hsvdetector; auto builds
  * the table after the same settings have processed 2^24 pixels),
  * "cd_cluster" 1|2|4|8 (colordetect: CTAs per cluster that merge their shared-memory histograms over DSMEM),
+ * "memo_ctas" 2..8 (CTAs per SM of the persistent table-lookup kernels; 4 = two consecutive frames resident together),
  * "memo_tile" 0|1 (4-byte-pixel table lookups through a per-tile shared-memory copy of the colour sub-cube; wins on
  * medium-noise content only, profiles/r01_memo_tile_experiment.jsonl). */
 int b200vfx_ctx_set_option(b200vfx_ctx *ctx, const char *name, int value);
