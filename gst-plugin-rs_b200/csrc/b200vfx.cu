@@ -487,6 +487,11 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
   return 0;
 }
 
+#ifndef B200VFX_MAP_PX
+#define B200VFX_MAP_PX 8
+#endif
+constexpr int kMapPx = B200VFX_MAP_PX;   // pixels (independent gathers) per thread of map_u32_kernel
+
 // rent-or-buy: build the answer table once the current settings have processed as many pixels as the table has entries
 bool hsv_memo_decide(int option, bool key_same, uint64_t &px_seen, uint64_t npx, bool &ready) {
   if (!key_same) { ready = false; px_seen = 0; }
@@ -548,11 +553,11 @@ int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings 
       return 0;
     }
     with_l2_window l2w(c, memo, sizeof(uint32_t) << 24);
-    const long long items = (long long)ceil_div(ww, 8 * 32 * 4) * hh, cap = (long long)c->sm_count * c->memo_ctas;
+    const long long items = (long long)ceil_div(ww, 8 * 32 * kMapPx) * hh, cap = (long long)c->sm_count * c->memo_ctas;
     dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(items, cap)));
     const int linger = (pdl && items > cap) ? 1 : 0;
     if (linger) pdl_note_linger(st);
-#define LM(CO, BG) CU(c, launch_k(pdl, map_u32_kernel<HsvFilterMemoOp<CO, BG>, 4>, grid, dim3(256), 0, st, HsvFilterMemoOp<CO, BG>{memo}, (const uint8_t *)data, ss, data, ss, ww, hh, linger))
+#define LM(CO, BG) CU(c, launch_k(pdl, map_u32_kernel<HsvFilterMemoOp<CO, BG>, kMapPx>, grid, dim3(256), 0, st, HsvFilterMemoOp<CO, BG>{memo}, (const uint8_t *)data, ss, data, ss, ww, hh, linger))
     if (fi.coff == 0) { if (fi.bgr) LM(0, true); else LM(0, false); }
     else { if (fi.bgr) LM(1, true); else LM(1, false); }
 #undef LM
@@ -630,11 +635,11 @@ int launch_hsvdetector(b200vfx_ctx *c, const FmtInfo &fi, const FmtInfo &fo, con
     if (fi.bpp == 4 && aligned(f.src, f.sstride, 4) && aligned(f.dst, f.dstride, 4)) {  // table-lookup map kernel
       int ww = f.width, hh = f.height;
       if (f.sstride == 4L * ww && f.dstride == 4L * ww && (long long)ww * hh < (1LL << 28)) { ww = ww * hh; hh = 1; }
-      const long long items = (long long)ceil_div(ww, 8 * 32 * 4) * hh, cap = (long long)c->sm_count * c->memo_ctas;
+      const long long items = (long long)ceil_div(ww, 8 * 32 * kMapPx) * hh, cap = (long long)c->sm_count * c->memo_ctas;
       dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(items, cap)));
       const int linger = (pdl && items > cap) ? 1 : 0;
       if (linger) pdl_note_linger(st);
-#define LD(IC, IB, OC, OB) CU(c, launch_k(pdl, map_u32_kernel<HsvDetectBitmapOp<IC, IB, OC, OB>, 4>, grid, dim3(256), 0, st, HsvDetectBitmapOp<IC, IB, OC, OB>{bitmap}, f.src, f.sstride, f.dst, f.dstride, ww, hh, linger))
+#define LD(IC, IB, OC, OB) CU(c, launch_k(pdl, map_u32_kernel<HsvDetectBitmapOp<IC, IB, OC, OB>, kMapPx>, grid, dim3(256), 0, st, HsvDetectBitmapOp<IC, IB, OC, OB>{bitmap}, f.src, f.sstride, f.dst, f.dstride, ww, hh, linger))
 #define LD2(IC, IB) do { if (fo.coff == 0) { if (fo.bgr) LD(IC, IB, 0, true); else LD(IC, IB, 0, false); } else { if (fo.bgr) LD(IC, IB, 1, true); else LD(IC, IB, 1, false); } } while (0)
       if (fi.coff == 0) { if (fi.bgr) LD2(0, true); else LD2(0, false); }
       else { if (fi.bgr) LD2(1, true); else LD2(1, false); }

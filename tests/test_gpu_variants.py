@@ -132,3 +132,36 @@ def test_memo_tile_kernel_hsvfilter_in_place(ctx, fmt):
     finally:
         ctx.set_option("memo_tile", 0)
         ctx.set_option("hsv_memo", -1)
+
+
+@pytest.mark.parametrize("ctas", [2, 3, 4, 8])
+def test_persistent_lookup_kernels_any_grid_cap(ctx, ctas):
+    """memo_ctas caps the persistent grid of the table-lookup kernels (CTAs per SM): every cap gives the same bytes, for
+    packed frames (flattened to one row of items), padded strides (row x chunk items) and frames smaller than one CTA"""
+    torch = pytest.importorskip("torch")
+    cube = orc.cube_parse(synth.cube_text_3d(17, "mix"))
+    ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+    ctx.set_option("memo_ctas", ctas)
+    ctx.set_option("hsv_memo", 1)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        for (w, h, pad) in ((3840, 2160, 0), (3840, 700, 64), (5000, 3, 0), (33, 1, 4), (2049, 257, 12)):
+            stride = 4 * w + pad
+            src = np.full((h, stride), 0xA5, np.uint8)
+            src[:, :4 * w] = synth.frame_noise("RGBA", w, h, 31 + w)[:, :4 * w]
+            exp = orc.colorlut_apply(cube, "RGBA", w, h, src, dst_stride=stride, threads=8)
+            d_in = torch.from_numpy(src).cuda()
+            outs = [torch.full((h, stride), 0x5A, dtype=torch.uint8, device="cuda") for _ in range(3)]
+            for o in outs:                                   # back to back: consecutive frames overlap (PDL)
+                ctx.colorlut_process("RGBA", w, h, d_in, stride, o, stride)
+            torch.cuda.synchronize()
+            for o in outs:
+                assert (o.cpu().numpy() == exp).all(), (w, h, pad)
+            expf = orc.hsvfilter("RGBA", w, h, src.copy(), hue_shift=45.0, threads=8)
+            d = torch.from_numpy(src).cuda()
+            ctx.hsvfilter_process("RGBA", w, h, d, stride, hue_shift=45.0)
+            torch.cuda.synchronize()
+            assert (d.cpu().numpy() == expf).all(), (w, h, pad)
+    finally:
+        ctx.set_option("memo_ctas", 4)
+        ctx.set_option("hsv_memo", -1)
