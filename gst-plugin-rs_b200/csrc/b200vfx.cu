@@ -67,7 +67,7 @@ struct b200vfx_ctx {
   bool blockhash_tma = false; // videocompare block sums through the TMA-fed kernel (measured equal or slightly slower than the register-staged LDG kernel: profiles/r01_kernel_matrix.md)
   int zero_copy = 2;       // pinned host frames: TMA kernel reads/writes host memory directly; 0 never, 1 always, 2 auto-probe
   int zc_calls = 0, zc_bad_streak = 0; double zc_best_ms[2] = {1e30, 1e30};   // auto-probe state: [0] zero-copy, [1] staged
-  int zc_cfg = 2, zc_ctas = 1, zc_grid = 64;
+  int zc_cfg = 2, zc_ctas = 1, zc_grid = 96;
   int zc_hybrid = 0;       // experiment: staged path with one direction zero-copy (1: kernel stores to host, 2: kernel loads from host)  // stream-kernel variant / CTAs per SM / absolute grid cap for the zero-copy path
   int stream_grid = 0;     // absolute cap on the persistent grid of the stream kernels (0 = none)
   bool pdl = true;       // programmatic dependent launch for out-of-place frame kernels
