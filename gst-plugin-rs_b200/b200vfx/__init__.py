@@ -72,6 +72,10 @@ def lib() -> C.CDLL:
         "b200vfx_ctx_set_option": ([vp, C.c_char_p, ci], ci),
         "b200vfx_host_alloc": ([C.c_size_t], vp),
         "b200vfx_host_free": ([vp], None),
+        "b200vfx_device_alloc": ([vp, C.c_size_t], vp),
+        "b200vfx_device_free": ([vp, vp], None),
+        "b200vfx_upload": ([vp, vp, ci, vp, ci, C.c_size_t, ci], ci),
+        "b200vfx_download": ([vp, vp, ci, vp, ci, C.c_size_t, ci], ci),
         "b200vfx_cube_parse": ([C.c_char_p, C.c_size_t, C.POINTER(ci), C.POINTER(ci), C.POINTER(f32p), f32p, f32p,
                                 C.c_char_p, C.c_size_t], ci),
         "b200vfx_cube_parse_file": ([C.c_char_p, C.POINTER(ci), C.POINTER(ci), C.POINTER(f32p), f32p, f32p,
@@ -274,6 +278,21 @@ class Context:
 
     def blockhash_sums(self, fmt, width, height, src, stride, sums, hw=8, hh=8):
         self._chk(lib().b200vfx_blockhash_sums(self._h, FMT[fmt], width, height, _ptr(src), stride, hw, hh, _ptr(sums)))
+
+    def device_alloc(self, nbytes) -> int:
+        p = lib().b200vfx_device_alloc(self._h, nbytes)
+        if not p:
+            raise B200VfxError(ERR_CUDA, (lib().b200vfx_last_error(self._h) or b"").decode())
+        return int(p)
+
+    def device_free(self, p):
+        lib().b200vfx_device_free(self._h, p)
+
+    def upload(self, dev_dst, dst_stride, host_src, src_stride, row_bytes, rows):
+        self._chk(lib().b200vfx_upload(self._h, _ptr(dev_dst), dst_stride, _ptr(host_src), src_stride, row_bytes, rows))
+
+    def download(self, host_dst, dst_stride, dev_src, src_stride, row_bytes, rows):
+        self._chk(lib().b200vfx_download(self._h, _ptr(host_dst), dst_stride, _ptr(dev_src), src_stride, row_bytes, rows))
 
     def blockhash_sums_batch(self, fmt, width, height, srcs, strides, sums, hw=8, hh=8):
         n = len(srcs)

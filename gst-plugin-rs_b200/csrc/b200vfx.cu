@@ -923,6 +923,40 @@ void *b200vfx_host_alloc(size_t bytes) {
 }
 void b200vfx_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+// ---- device-resident frames ---------------------------------------------------------------------
+void *b200vfx_device_alloc(b200vfx_ctx *c, size_t bytes) {
+  if (!c) { fail(nullptr, B200VFX_ERR_INVALID, "null context"); return nullptr; }
+  DeviceGuard g(c->device);
+  void *p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { fail(c, B200VFX_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError())); return nullptr; }
+  return p;
+}
+void b200vfx_device_free(b200vfx_ctx *c, void *p) {
+  if (!c || !p) return;
+  DeviceGuard g(c->device);
+  cudaStreamSynchronize(c->stream());   // nothing of ours may still use it
+  pdl_forget(c->stream());
+  cudaFree(p);
+}
+static int copy_rows(b200vfx_ctx *c, void *dst, int dstride, const void *src, int sstride, size_t row_bytes, int rows, cudaMemcpyKind kind) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (rows < 0 || dstride < 0 || sstride < 0 || (rows > 0 && row_bytes > 0 && (!dst || !src || (size_t)dstride < row_bytes || (size_t)sstride < row_bytes)))
+    return fail(c, B200VFX_ERR_INVALID, "bad plane description");
+  if (rows == 0 || row_bytes == 0) return 0;
+  DeviceGuard g(c->device);
+  cudaStream_t st = c->stream();
+  pdl_admit(false, st, Span{0, 0}, Span{0, 0});   // a copy is an ordinary stream operation: everything before it completes first
+  if ((size_t)dstride == row_bytes && (size_t)sstride == row_bytes) CU(c, cudaMemcpyAsync(dst, src, row_bytes * (size_t)rows, kind, st));
+  else CU(c, cudaMemcpy2DAsync(dst, (size_t)dstride, src, (size_t)sstride, row_bytes, (size_t)rows, kind, st));
+  return 0;
+}
+int b200vfx_upload(b200vfx_ctx *c, void *dev_dst, int dst_stride, const void *host_src, int src_stride, size_t row_bytes, int rows) {
+  return copy_rows(c, dev_dst, dst_stride, host_src, src_stride, row_bytes, rows, cudaMemcpyHostToDevice);
+}
+int b200vfx_download(b200vfx_ctx *c, void *host_dst, int dst_stride, const void *dev_src, int src_stride, size_t row_bytes, int rows) {
+  return copy_rows(c, host_dst, dst_stride, dev_src, src_stride, row_bytes, rows, cudaMemcpyDeviceToHost);
+}
+
 // ---- colorlut --------------------------------------------------------------------------------
 int b200vfx_colorlut_clear(b200vfx_ctx *c) {
   if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");

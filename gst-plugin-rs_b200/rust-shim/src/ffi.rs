@@ -44,6 +44,12 @@ extern "C" {
     pub fn b200vfx_last_error(ctx: *const b200vfx_ctx) -> *const c_char;
     pub fn b200vfx_host_alloc(bytes: usize) -> *mut c_void;
     pub fn b200vfx_host_free(p: *mut c_void);
+    // device-resident frames: what a memory:CUDAMemory-style allocator of these elements needs
+    pub fn b200vfx_device_alloc(ctx: *mut b200vfx_ctx, bytes: usize) -> *mut c_void;
+    pub fn b200vfx_device_free(ctx: *mut b200vfx_ctx, p: *mut c_void);
+    pub fn b200vfx_upload(ctx: *mut b200vfx_ctx, dev_dst: *mut c_void, dst_stride: c_int, host_src: *const c_void, src_stride: c_int, row_bytes: usize, rows: c_int) -> c_int;
+    pub fn b200vfx_download(ctx: *mut b200vfx_ctx, host_dst: *mut c_void, dst_stride: c_int, dev_src: *const c_void, src_stride: c_int, row_bytes: usize, rows: c_int) -> c_int;
+    pub fn b200vfx_ctx_synchronize(ctx: *mut b200vfx_ctx) -> c_int;
 
     pub fn b200vfx_colorlut_load_file(ctx: *mut b200vfx_ctx, location: *const c_char) -> c_int;
     pub fn b200vfx_colorlut_clear(ctx: *mut b200vfx_ctx) -> c_int;

@@ -104,6 +104,19 @@ int b200vfx_ctx_set_option(b200vfx_ctx *ctx, const char *name, int value);
 void *b200vfx_host_alloc(size_t bytes);
 void b200vfx_host_free(void *p);
 
+/* ---- device-resident frames (chaining without PCIe round trips) ----------------------
+ * What a `memory:CUDAMemory`-style GstAllocator of these elements needs: device frames that several elements
+ * process back to back (every *_process call accepts device pointers and then only enqueues its kernel), one
+ * upload at the head of the chain and one download at its tail.  upload/download are asynchronous on the
+ * context stream (use b200vfx_ctx_synchronize, or stream order, before touching the host buffer again);
+ * full PCIe rate needs page-locked host memory (b200vfx_host_alloc). */
+void *b200vfx_device_alloc(b200vfx_ctx *ctx, size_t bytes);
+void b200vfx_device_free(b200vfx_ctx *ctx, void *dev_ptr);
+int b200vfx_upload(b200vfx_ctx *ctx, void *dev_dst, int dst_stride, const void *host_src, int src_stride,
+                   size_t row_bytes, int rows);
+int b200vfx_download(b200vfx_ctx *ctx, void *host_dst, int dst_stride, const void *dev_src, int src_stride,
+                     size_t row_bytes, int rows);
+
 /* ---- .cube parser -------------------------------------------------------
  * replaces CubeLut::parse / parse_file, video/colorlut/src/parser.rs:105-281
  * (same grammar, same error cases).  kind: 1 = LUT_1D, 3 = LUT_3D.

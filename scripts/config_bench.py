@@ -109,6 +109,33 @@ def configs_1_to_4():
                       "elements cannot be linked directly: SURVEY D1)", "device_us": round(t_dev * 1e6, 2), "device_fps": round(1 / t_dev),
                       "algo_GBps": round(2 * w * h * 4 / t_dev / 1e9, 1), "device_us_direct_kernel": round(t_dev_direct * 1e6, 2), "e2e_fps": round(1 / t_e2e),
                       "cpu_fps_1thread": round(1 / t_cpu1, 1), "cpu_fps_%dthreads" % T: round(1 / t_cpuN, 1), "mask_device_us": round(t_mask * 1e6, 1), "mask_cpu_us": round(t_mask_cpu * 1e6, 1)}), flush=True)
+    # ---- chain: hsvfilter -> hsvdetector on 1920x1080 BGRx, host frame in, host frame out -------------
+    # (a) as two unchanged elements with system memory between them: every element uploads and downloads its frame;
+    # (b) device-resident: one upload (b200vfx_upload), both kernels on the frame in HBM, one download
+    d_a, d_b = ctx.device_alloc(4 * w * h), ctx.device_alloc(4 * w * h)
+    mid = [pin(np.zeros_like(f)) for f in frames]
+
+    def chain_host(i):
+        mid[i % R].copy_(hp[i % R])                                                     # hsvfilter works in place on its input buffer
+        ctx.hsvfilter_process("BGRx", w, h, mid[i % R].numpy(), 4 * w, hue_shift=90.0)
+        ctx.hsvdetector_process("BGRx", "RGBA", w, h, mid[i % R].numpy(), 4 * w, ho[i % R].numpy(), 4 * w, **kw)
+
+    def chain_device(i):
+        ctx.upload(d_a, 4 * w, hp[i % R].numpy(), 4 * w, 4 * w, h)
+        ctx.hsvfilter_process("BGRx", w, h, d_a, 4 * w, hue_shift=90.0)
+        ctx.hsvdetector_process("BGRx", "RGBA", w, h, d_a, 4 * w, d_b, 4 * w, **kw)
+        ctx.download(ho[i % R].numpy(), 4 * w, d_b, 4 * w, 4 * w, h)
+        ctx.synchronize()
+
+    warm = 2 * ((1 << 24) // (w * h) + 4)
+    t_host = wall_time(chain_host, 60, warm)
+    ref_out = ho[0].clone()
+    t_devc = wall_time(chain_device, 60, warm)
+    same = bool((ho[0] == ref_out).all())
+    print(json.dumps({"config": "3-chain", "what": "hsvfilter (in place) -> hsvdetector BGRx->RGBA, 1920x1080, pinned host frame in and out",
+                      "two_host_elements_fps": round(1 / t_host), "device_resident_chain_fps": round(1 / t_devc), "identical": same,
+                      "note": "device-resident: one upload + two kernels + one download per frame (b200vfx_upload / _download)"}), flush=True)
+    ctx.device_free(d_a); ctx.device_free(d_b)
     # ---- config 4: videocompare blockhash on two 3840x2160 RGBA streams ---------------------------------------------
     w, h = 3840, 2160
     a = synth.frame_ramps("RGBA", w, h)

@@ -165,3 +165,39 @@ def test_persistent_lookup_kernels_any_grid_cap(ctx, ctas):
     finally:
         ctx.set_option("memo_ctas", 4)
         ctx.set_option("hsv_memo", -1)
+
+
+def test_device_resident_chain_one_upload_one_download():
+    """hsvfilter -> hsvdetector -> colordetect + blockhash on frames that stay in HBM (library-owned
+    device buffers, one upload at the head, one download at the tail, all elements on one stream) == the oracle chain."""
+    w, h = 1920, 1080
+    src = synth.frame_natural("BGRx", w, h, 77, amp=4)
+    fkw = dict(hue_shift=40.0, saturation_mul=1.1)
+    dkw = dict(hue_ref=120.0, hue_var=60.0, saturation_ref=0.6, saturation_var=0.4, value_ref=0.6, value_var=0.4)
+    step1 = orc.hsvfilter("BGRx", w, h, src.copy(), hue_shift=40.0, sat_mul=1.1, threads=8)
+    step2 = orc.hsvdetector("BGRx", "RGBA", w, h, step1, hue_ref=120.0, hue_var=60.0, sat_ref=0.6, sat_var=0.4, val_ref=0.6, val_var=0.4, threads=8)
+    with b200vfx.Context(0) as ctx:
+        ctx.set_option("hsv_memo", 1)
+        nb = 4 * w * h
+        d_a, d_b = ctx.device_alloc(nb), ctx.device_alloc(nb)
+        d_hist, d_sums = ctx.device_alloc(4 * 32768), ctx.device_alloc(4 * 64)
+        host_in = np.ascontiguousarray(src)
+        out = np.zeros((h, 4 * w), np.uint8)
+        hist, sums = np.zeros(32768, np.uint32), np.zeros(64, np.uint32)
+        for _ in range(3):   # repeated: frames of a stream reuse the same device buffers
+            ctx.upload(d_a, 4 * w, host_in, 4 * w, 4 * w, h)
+            ctx.hsvfilter_process("BGRx", w, h, d_a, 4 * w, **fkw)                               # in place, device
+            ctx.hsvdetector_process("BGRx", "RGBA", w, h, d_a, 4 * w, d_b, 4 * w, **dkw)        # device -> device
+            ctx.colordetect_histogram("RGBA", w, h, d_b, 4 * w, 10, d_hist)                     # device -> device
+            ctx.blockhash_sums("RGBA", w, h, d_b, 4 * w, d_sums)
+            ctx.download(out, 4 * w, d_b, 4 * w, 4 * w, h)
+            ctx.download(hist, 4 * 32768, d_hist, 4 * 32768, 4 * 32768, 1)
+            ctx.download(sums, 256, d_sums, 256, 256, 1)
+            ctx.synchronize()
+            assert (out == step2).all()
+            assert (hist == orc.colordetect_histogram("RGBA", w, h, step2, 10)).all()
+            assert (sums == orc.blockhash_sums("RGBA", w, h, step2)).all()
+        for p in (d_a, d_b, d_hist, d_sums):
+            ctx.device_free(p)
+        with pytest.raises(b200vfx.B200VfxError):
+            ctx.upload(0, 4 * w, host_in, 4 * w, 4 * w, h)
