@@ -957,6 +957,11 @@ int b200vfx_download(b200vfx_ctx *c, void *host_dst, int dst_stride, const void 
   return copy_rows(c, host_dst, dst_stride, dev_src, src_stride, row_bytes, rows, cudaMemcpyDeviceToHost);
 }
 
+int b200vfx_copy_plane(b200vfx_ctx *c, void *dst, int dst_stride, const void *src, int src_stride, size_t row_bytes, int rows) {
+  return copy_rows(c, dst, dst_stride, src, src_stride, row_bytes, rows, cudaMemcpyDefault);
+}
+int b200vfx_pointer_is_device(const void *p) { return p && is_device_ptr(p) ? 1 : 0; }
+
 // ---- colorlut --------------------------------------------------------------------------------
 int b200vfx_colorlut_clear(b200vfx_ctx *c) {
   if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");

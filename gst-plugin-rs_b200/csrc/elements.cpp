@@ -288,8 +288,14 @@ struct VideoCompare : b200gst_element {  // video/videofx/src/videocompare/imp.r
     if (!contains(pad_formats(0), ref->format)) return fail(B200GST_FLOW_NOT_NEGOTIATED, "format not negotiated");
     if (out && out->data[0]) {  // output = the reference buffer (:310-313)
       const size_t row = (size_t)ref->width * (ref->format == B200VFX_FORMAT_RGB ? 3 : 4);
-      for (int y = 0; y < ref->height; y++)
-        std::memcpy((uint8_t *)out->data[0] + (size_t)y * out->stride[0], (const uint8_t *)ref->data[0] + (size_t)y * ref->stride[0], row);
+      if (b200vfx_pointer_is_device(out->data[0]) || b200vfx_pointer_is_device(ref->data[0])) {  // device-resident pipeline
+        if (b200vfx_copy_plane(ctx, out->data[0], out->stride[0], ref->data[0], ref->stride[0], row, ref->height) != 0 ||
+            b200vfx_ctx_synchronize(ctx) != 0)
+          return ctx_error(B200GST_FLOW_ERROR);
+      } else {
+        for (int y = 0; y < ref->height; y++)
+          std::memcpy((uint8_t *)out->data[0] + (size_t)y * out->stride[0], (const uint8_t *)ref->data[0] + (size_t)y * ref->stride[0], row);
+      }
     }
     // collect the other pads' frames first (the size check of :337-346 precedes any hashing of that pad)
     std::vector<std::pair<int, const b200gst_video_frame *>> others;

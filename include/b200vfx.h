@@ -116,6 +116,11 @@ int b200vfx_upload(b200vfx_ctx *ctx, void *dev_dst, int dst_stride, const void *
                    size_t row_bytes, int rows);
 int b200vfx_download(b200vfx_ctx *ctx, void *host_dst, int dst_stride, const void *dev_src, int src_stride,
                      size_t row_bytes, int rows);
+/* plane copy between any two of {host, device} (direction inferred through UVA), asynchronous on the context stream;
+ * 1 if p is device (or managed) memory, 0 otherwise */
+int b200vfx_copy_plane(b200vfx_ctx *ctx, void *dst, int dst_stride, const void *src, int src_stride, size_t row_bytes,
+                       int rows);
+int b200vfx_pointer_is_device(const void *p);
 
 /* ---- .cube parser -------------------------------------------------------
  * replaces CubeLut::parse / parse_file, video/colorlut/src/parser.rs:105-281

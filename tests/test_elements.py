@@ -194,3 +194,26 @@ def test_videocompare_red_vs_red_posts_message_and_snow_does_not():
     vc.set_property("hash-algo", "mean")
     assert vc.aggregate_frames([fr(red), fr(red2)], [ref, other]) == gst.FLOW_ERROR
     vc.stop()
+
+
+@pytest.mark.gpu
+def test_videocompare_with_device_resident_frames():
+    """frames that live in HBM (memory:CUDAMemory-style pipeline): the element must not touch them with host code"""
+    torch = pytest.importorskip("torch")
+    w, h = 640, 480
+    vc = gst.Element("videocompare")
+    assert vc.start() == 0
+    ref, other = vc.request_pad(), vc.request_pad()
+    red = synth.frame_solid("RGBA", w, h)
+    d_red, d_red2 = torch.from_numpy(red).cuda(), torch.from_numpy(red.copy()).cuda()
+    d_snow = torch.from_numpy(synth.frame_noise("RGBA", w, h, 7)).cuda()
+    d_out = torch.zeros_like(d_red)
+    fr = lambda t: gst.frame("RGBA", w, h, [t], [4 * w])
+    assert vc.aggregate_frames([fr(d_red), fr(d_red2)], [ref, other], 0, fr(d_out)) == gst.FLOW_OK
+    msg = vc.pop_message()
+    assert msg is not None and "distance\\=(double)0" in msg
+    assert (d_out.cpu().numpy() == red).all()                     # output = the reference buffer, copied device to device
+    host_out = np.zeros_like(red)
+    assert vc.aggregate_frames([fr(d_red), fr(d_snow)], [ref, other], 1, fr(host_out)) == gst.FLOW_OK
+    assert vc.pop_message() is None and (host_out == red).all()   # device reference -> host output buffer
+    vc.stop()
