@@ -49,6 +49,15 @@ struct DevBuf {
 
 }  // namespace
 
+// A lookup table is built by a kernel on whatever stream the first frame came in on (context / user stream for device
+// frames, the internal pipeline stream for host frames); a later call on ANOTHER stream must not read it before that build
+// has finished: the build records an event, launches on other streams wait for it.
+struct TableSync {
+  cudaEvent_t ev = nullptr;
+  cudaStream_t st = nullptr;
+  bool valid = false;
+};
+
 struct b200vfx_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;   // default stream for device-pointer calls
@@ -95,6 +104,7 @@ struct b200vfx_ctx {
   uint32_t *d_memo = nullptr;   // 2^24 x u32 (3D)
   uint8_t *d_memo1d = nullptr;  // 768 bytes (1D)
   bool memo_ready = false;
+  TableSync ts_colorlut, ts_hf, ts_hd;   // axis + memo tables / hsvfilter table / hsvdetector bitmap
 
   // hsvfilter / hsvdetector memoisation (settings-keyed; built after 2^24 pixels with unchanged settings)
   int hsv_memo = -1;  // -1 auto (rent-or-buy), 0 never, 1 build on first use
@@ -123,6 +133,17 @@ int fail(b200vfx_ctx *ctx, int code, const char *fmt, ...) {
     if (e__ != cudaSuccess)                                                                    \
       return fail(ctx, B200VFX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));     \
   } while (0)
+
+int table_built(b200vfx_ctx *c, TableSync &t, cudaStream_t st) {
+  if (!t.ev) CU(c, cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
+  CU(c, cudaEventRecord(t.ev, st));
+  t.st = st; t.valid = true;
+  return 0;
+}
+int table_wait(b200vfx_ctx *c, const TableSync &t, cudaStream_t st) {
+  if (t.valid && t.st != st) CU(c, cudaStreamWaitEvent(st, t.ev, 0));
+  return 0;
+}
 
 bool is_device_ptr(const void *p) {
   cudaPointerAttributes a;
@@ -365,7 +386,7 @@ int launch_memo_stream(b200vfx_ctx *c, const uint8_t *src, long ss, uint8_t *dst
 
 // once per LUT: evaluate all 2^24 colours (3D) / 3x256 channel values (1D) with the exact direct evaluator
 int ensure_colorlut_memo(b200vfx_ctx *c, const LutDev &p, cudaStream_t st) {
-  if (c->memo_ready) return 0;
+  if (c->memo_ready) return table_wait(c, c->ts_colorlut, st);
   if (c->lut_kind == 3) {
     if (int rc = ensure_l2_set_aside(c, (size_t)72 << 20)) return rc;
     if (!c->d_memo) CU(c, cudaMalloc(&c->d_memo, sizeof(uint32_t) << 24));
@@ -377,7 +398,7 @@ int ensure_colorlut_memo(b200vfx_ctx *c, const LutDev &p, cudaStream_t st) {
   c->launches++;
   CU(c, cudaGetLastError());
   c->memo_ready = true;
-  return 0;
+  return table_built(c, c->ts_colorlut, st);
 }
 
 // fused tile gather, TMA variant: per-(variant, device) attribute / occupancy cache like launch_memo_stream_t
@@ -533,7 +554,8 @@ int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings 
       CU(c, cudaGetLastError());
       c->hf_ready = true;
       built_now = true;
-    }
+      if (int rc = table_built(c, c->ts_hf, st)) return rc;
+    } else if (int rc = table_wait(c, c->ts_hf, st)) return rc;
     memo = c->d_hf_memo;
   }
   if (memo && fi.bpp == 4 && aligned(data, stride, 4)) {  // table-lookup map kernel, PDL-overlapped when frames are disjoint
@@ -628,7 +650,8 @@ int launch_hsvdetector(b200vfx_ctx *c, const FmtInfo &fi, const FmtInfo &fo, con
       CU(c, cudaGetLastError());
       c->hd_ready = true;
       built_now = true;
-    }
+      if (int rc = table_built(c, c->ts_hd, st)) return rc;
+    } else if (int rc = table_wait(c, c->ts_hd, st)) return rc;
     bitmap = c->d_hd_bitmap;
     pdl = pdl_admit(c->pdl && !built_now, st, span_of(f.src, f.sstride, (size_t)f.width * fi.bpp, f.height),
                     span_of(f.dst, f.dstride, (size_t)f.width * 4, f.height));
@@ -676,6 +699,31 @@ int launch_hsvdetector(b200vfx_ctx *c, const FmtInfo &fi, const FmtInfo &fo, con
   if (rc) return rc;
   c->launches++;
   CU(c, cudaGetLastError());
+  return 0;
+}
+
+// zero-copy host path of the memoised hsv elements: one persistent TMA streaming kernel reads the pinned host frame over
+// PCIe and writes the result straight back (in place for hsvfilter), like the colorlut zero-copy path
+template <typename Op>
+int launch_map_zero_copy(b200vfx_ctx *c, Op op, const uint8_t *dsrc, long ss, uint8_t *ddst, long ds, int row_bytes, int h) {
+  constexpr int TILE = 4096, STAGES = 4, THREADS = 256, B = 4;
+  constexpr int smem = stream_smem_bytes<TILE, STAGES>();
+  auto k = map_stream_kernel<TILE, STAGES, THREADS, B, Op>;
+  static std::mutex mu;
+  static bool attr_set[64] = {false};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    const int dev = (c->device >= 0 && c->device < 64) ? c->device : 0;
+    if (!attr_set[dev]) { CU(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set[dev] = true; }
+  }
+  const long long ntiles = (long long)ceil_div(row_bytes, TILE) * h;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ntiles, c->zc_grid > 0 ? c->zc_grid : 96));
+  pdl_admit(false, c->s_k, Span{0, 0}, Span{0, 0});
+  k<<<grid, THREADS, smem, c->s_k>>>(op, dsrc, ss, ddst, ds, row_bytes, h);
+  c->launches++;
+  CU(c, cudaGetLastError());
+  CU(c, cudaStreamSynchronize(c->s_k));
+  pdl_forget(c->s_k);
   return 0;
 }
 
@@ -855,6 +903,7 @@ void b200vfx_ctx_destroy(b200vfx_ctx *c) {
   b200vfx_colorlut_clear(c);
   if (c->d_hf_memo) cudaFree(c->d_hf_memo);
   if (c->d_hd_bitmap) cudaFree(c->d_hd_bitmap);
+  for (TableSync *t : {&c->ts_colorlut, &c->ts_hf, &c->ts_hd}) if (t->ev) cudaEventDestroy(t->ev);
   for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
   c->stage_in.release(); c->stage_out.release(); c->stage_sums.release();
@@ -1115,6 +1164,18 @@ int b200vfx_hsvfilter_process(b200vfx_ctx *c, int fmt, int width, int height, vo
   if (width == 0 || height == 0) return 0;
   DeviceGuard g(c->device);
   const HsvFilterSettings hs{hue_shift, saturation_mul, saturation_off, value_mul, value_off};
+  {  // pinned host frame + answer table already built for exactly these settings: zero-copy, in place over PCIe
+    void *dptr = nullptr;
+    if (c->zero_copy != 0 && fi.bpp == 4 && (width % 4) == 0 && aligned(data, stride, 16) && c->hf_ready && c->hf_key_valid &&
+        c->hsv_memo != 0 && std::memcmp(&c->hf_key, &hs, sizeof hs) == 0 && pinned_device_ptr(data, &dptr)) {
+      uint8_t *d = (uint8_t *)dptr;
+      if (int rc = table_wait(c, c->ts_hf, c->s_k)) return rc;
+#define ZF(CO, BG) return launch_map_zero_copy(c, HsvFilterMemoOp<CO, BG>{c->d_hf_memo}, d, stride, d, stride, 4 * width, height)
+      if (fi.coff == 0) { if (fi.bgr) ZF(0, true); else ZF(0, false); }
+      else { if (fi.bgr) ZF(1, true); else ZF(1, false); }
+#undef ZF
+    }
+  }
   Staged s{(const uint8_t *)data, stride, row, (uint8_t *)data, stride, row, height, true};
   return run_staged(c, s, [&](const uint8_t *, long, uint8_t *dd, long dds, int, int rows, cudaStream_t st) {
     return launch_hsvfilter(c, fi, hs, dd, dds, width, rows, st);
@@ -1135,6 +1196,22 @@ int b200vfx_hsvdetector_process(b200vfx_ctx *c, int in_fmt, int out_fmt, int wid
   if (width == 0 || height == 0) return 0;
   DeviceGuard g(c->device);
   const HsvDetectSettings hs{hue_ref, hue_var, saturation_ref, saturation_var, value_ref, value_var};
+  {  // pinned host frames + hit bitmap already built for exactly these settings: zero-copy over PCIe
+    void *dsrc = nullptr, *ddst = nullptr;
+    if (c->zero_copy != 0 && fi.bpp == 4 && (width % 4) == 0 && aligned(src, src_stride, 16) && aligned(dst, dst_stride, 16) &&
+        c->hd_ready && c->hd_key_valid && c->hsv_memo != 0 && std::memcmp(&c->hd_key, &hs, sizeof hs) == 0 &&
+        pinned_device_ptr(src, &dsrc) && pinned_device_ptr(dst, &ddst)) {
+      const uint8_t *ps = (const uint8_t *)dsrc;
+      uint8_t *pd = (uint8_t *)ddst;
+      if (int rc = table_wait(c, c->ts_hd, c->s_k)) return rc;
+#define ZD(IC, IB, OC, OB) return launch_map_zero_copy(c, HsvDetectBitmapOp<IC, IB, OC, OB>{c->d_hd_bitmap}, ps, src_stride, pd, dst_stride, 4 * width, height)
+#define ZD2(IC, IB) do { if (fo.coff == 0) { if (fo.bgr) ZD(IC, IB, 0, true); else ZD(IC, IB, 0, false); } else { if (fo.bgr) ZD(IC, IB, 1, true); else ZD(IC, IB, 1, false); } } while (0)
+      if (fi.coff == 0) { if (fi.bgr) ZD2(0, true); else ZD2(0, false); }
+      else { if (fi.bgr) ZD2(1, true); else ZD2(1, false); }
+#undef ZD2
+#undef ZD
+    }
+  }
   Staged s{(const uint8_t *)src, src_stride, irow, (uint8_t *)dst, dst_stride, orow, height, false};
   return run_staged(c, s, [&](const uint8_t *ds, long dss, uint8_t *dd, long dds, int, int rows, cudaStream_t st) {
     return launch_hsvdetector(c, fi, fo, hs, Frame{ds, dss, dd, dds, width, rows}, st);

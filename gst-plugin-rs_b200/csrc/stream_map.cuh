@@ -98,6 +98,14 @@ __global__ void __launch_bounds__(THREADS) colorlut_memo_stream_kernel(const uin
   stream_map_u32<TILE, STAGES, THREADS, B>(op, src, sstride, dst, dstride, row_bytes, height);
 }
 
+// any 4-byte -> 4-byte pixel op (HsvFilterMemoOp, HsvDetectBitmapOp of kernels.cuh) through the same skeleton: used for
+// the zero-copy host path of hsvfilter / hsvdetector (tiles bulk-loaded from and bulk-stored to pinned host memory)
+template <int TILE, int STAGES, int THREADS, int B, typename Op>
+__global__ void __launch_bounds__(THREADS) map_stream_kernel(Op op, const uint8_t *__restrict__ src, long sstride,
+                                                            uint8_t *dst, long dstride, int row_bytes, int height) {
+  stream_map_u32<TILE, STAGES, THREADS, B>(op, src, sstride, dst, dstride, row_bytes, height);
+}
+
 struct Memo1dOp {  // three 256-byte tables staged in shared memory
   const uint8_t *tab;
   __device__ __forceinline__ uint32_t operator()(uint32_t px) const {

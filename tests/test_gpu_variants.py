@@ -201,3 +201,44 @@ def test_device_resident_chain_one_upload_one_download():
             ctx.device_free(p)
         with pytest.raises(b200vfx.B200VfxError):
             ctx.upload(0, 4 * w, host_in, 4 * w, 4 * w, h)
+
+
+def test_hsv_zero_copy_host_path_and_cross_stream_table_use():
+    """memoised hsvfilter / hsvdetector on PINNED host frames: once the answer table exists the frame is processed by one
+    TMA streaming kernel that reads and writes host memory directly (in place for hsvfilter).  Also the cross-stream
+    case: the table is built by a DEVICE-frame call on the caller's stream and used right away by a host-frame call on
+    the library's own stream (must wait for the build)."""
+    torch = pytest.importorskip("torch")
+    fkw, fokw = dict(hue_shift=70.0, value_mul=0.9), dict(hue_shift=70.0, val_mul=0.9)
+    dkw = dict(hue_ref=100.0, hue_var=80.0, saturation_ref=0.5, saturation_var=0.5, value_ref=0.5, value_var=0.5)
+    dokw = dict(hue_ref=100.0, hue_var=80.0, sat_ref=0.5, sat_var=0.5, val_ref=0.5, val_var=0.5)
+    for fmt, ofmt in (("RGBx", "RGBA"), ("xBGR", "ARGB"), ("BGRx", "ABGR")):
+        for (w, h) in ((1280, 360), (644, 33), (62, 7)):           # 62: not a multiple of 4 -> staged pipeline
+            with b200vfx.Context(0) as ctx:
+                s = torch.cuda.Stream()
+                ctx.set_stream(s.cuda_stream)
+                ctx.set_option("hsv_memo", 1)
+                frame = synth.frame_noise(fmt, w, h, 91 + w)
+                exp_f = orc.hsvfilter(fmt, w, h, frame.copy(), threads=8, **fokw)
+                exp_d = orc.hsvdetector(fmt, ofmt, w, h, frame, threads=8, **dokw)
+                # table built by a device-frame call on stream s ...
+                d = torch.from_numpy(frame).cuda()
+                with torch.cuda.stream(s):
+                    ctx.hsvfilter_process(fmt, w, h, d, frame.shape[1], **fkw)
+                    dd = torch.empty((h, 4 * w), dtype=torch.uint8, device="cuda")
+                    ctx.hsvdetector_process(fmt, ofmt, w, h, torch.from_numpy(frame).cuda(), frame.shape[1], dd, 4 * w, **dkw)
+                # ... and used at once by host-frame calls (pinned: zero-copy kernel on the library's stream)
+                for rep in range(2):
+                    hp = torch.from_numpy(frame.copy()).pin_memory()
+                    ctx.hsvfilter_process(fmt, w, h, hp.numpy(), frame.shape[1], **fkw)
+                    assert (hp.numpy() == exp_f).all(), (fmt, w, h, rep)
+                    hi = torch.from_numpy(frame.copy()).pin_memory()
+                    ho = torch.full((h, 4 * w), 0x5A, dtype=torch.uint8).pin_memory()
+                    ctx.hsvdetector_process(fmt, ofmt, w, h, hi.numpy(), frame.shape[1], ho.numpy(), 4 * w, **dkw)
+                    assert (ho.numpy() == exp_d).all(), (fmt, ofmt, w, h, rep)
+                s.synchronize()
+                assert (d.cpu().numpy() == exp_f).all() and (dd.cpu().numpy() == exp_d).all()
+                ctx.set_option("zero_copy", 0)                      # the staged pipeline gives the same bytes
+                hp = torch.from_numpy(frame.copy()).pin_memory()
+                ctx.hsvfilter_process(fmt, w, h, hp.numpy(), frame.shape[1], **fkw)
+                assert (hp.numpy() == exp_f).all()
