@@ -78,6 +78,8 @@ def lib() -> C.CDLL:
         "b200vfx_download": ([vp, vp, ci, vp, ci, C.c_size_t, ci], ci),
         "b200vfx_copy_plane": ([vp, vp, ci, vp, ci, C.c_size_t, ci], ci),
         "b200vfx_pointer_is_device": ([vp], ci),
+        "b200vfx_debug_pdl_admit": ([vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, ci, C.c_longlong, ci], ci),
+        "b200vfx_debug_pdl_reset": ([vp], None),
         "b200vfx_cube_parse": ([C.c_char_p, C.c_size_t, C.POINTER(ci), C.POINTER(ci), C.POINTER(f32p), f32p, f32p,
                                 C.c_char_p, C.c_size_t], ci),
         "b200vfx_cube_parse_file": ([C.c_char_p, C.POINTER(ci), C.POINTER(ci), C.POINTER(f32p), f32p, f32p,

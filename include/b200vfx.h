@@ -237,6 +237,15 @@ int b200vfx_colorlut_process_tile_gather(b200vfx_ctx *ctx, int fmt, int width, i
                                          int src_stride, int world, int rank, void *const *frames, int frame_stride,
                                          int frame_row0, void *const *flags, uint32_t epoch);
 
+/* ---- test hooks (host logic only, no GPU needed) ---------------------------------------------------------------
+ * The admission rule for overlapping consecutive frames (programmatic dependent launch): would a launch with these
+ * source / destination byte ranges be allowed to start before our earlier launches on `stream_key` have completed?
+ * Records the launch exactly like a real one (threads = grid x block size, lingers = it ends on griddepcontrol.wait).
+ * b200vfx_debug_pdl_reset forgets the stream (what a stream synchronisation does). */
+int b200vfx_debug_pdl_admit(void *stream_key, uintptr_t src_lo, uintptr_t src_hi, uintptr_t dst_lo, uintptr_t dst_hi,
+                            int want_pdl, long long threads, int lingers);
+void b200vfx_debug_pdl_reset(void *stream_key);
+
 #ifdef __cplusplus
 }
 #endif

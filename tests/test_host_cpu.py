@@ -205,3 +205,56 @@ def test_product_parser_differential_fuzz_valid_shapes():
 
     run()
     assert n_ok["n"] >= 100
+
+
+# ---- the PDL admission rule (host logic) ----------------------------------------------------------------
+def _admit(L, key, src, dst, threads, lingers, want=1):
+    return L.b200vfx_debug_pdl_admit(key, src[0], src[1], dst[0], dst[1], want, threads, 1 if lingers else 0)
+
+
+def test_pdl_admission_rule():
+    L = b200vfx.lib()
+    MB = 1 << 20
+    buf = lambda i: (0x10000000 + i * 64 * MB, 0x10000000 + i * 64 * MB + 33 * MB)       # disjoint 33 MB frames
+    capped = 148 * 4 * 256            # persistent lookup kernel: 4 CTAs x 256 threads per SM, ends on griddepcontrol.wait
+    # 1. capped (lingering) kernels: only the last 2 launches can still be running -> a pool of 3 output buffers is enough
+    key = 0x1000
+    L.b200vfx_debug_pdl_reset(key)
+    got = [_admit(L, key, buf(100 + i), buf(i % 3), capped, True) for i in range(12)]
+    assert got == [1] * 12
+    # ... a pool of 2 is not: every launch writes what the launch two before it wrote (possibly still running)
+    key = 0x1001
+    L.b200vfx_debug_pdl_reset(key)
+    got = [_admit(L, key, buf(100 + i), buf(i % 2), capped, True) for i in range(8)]
+    assert got[:2] == [1, 1] and 0 in got[2:]
+    # 2. small frames / non-lingering kernels: the last 4 launches are assumed running -> pool of 5 ok, pool of 4 not
+    small = 300 * 256
+    key = 0x1002
+    L.b200vfx_debug_pdl_reset(key)
+    assert [_admit(L, key, buf(100 + i), buf(i % 5), small, False) for i in range(15)] == [1] * 15
+    key = 0x1003
+    L.b200vfx_debug_pdl_reset(key)
+    got = [_admit(L, key, buf(100 + i), buf(i % 4), small, False) for i in range(12)]
+    assert got[:4] == [1, 1, 1, 1] and got[4] == 0
+    # 3. chained elements (input = the previous launch's output) and in-place reuse never overlap
+    key = 0x1004
+    L.b200vfx_debug_pdl_reset(key)
+    assert _admit(L, key, buf(0), buf(1), capped, True) == 1
+    assert _admit(L, key, buf(1), buf(2), capped, True) == 0          # reads what the previous launch writes
+    assert _admit(L, key, buf(5), buf(5), capped, True) == 1          # a refusal is a full barrier: the queue restarts
+    assert _admit(L, key, buf(5), buf(5), capped, True) == 0          # same frame in place again
+    # 4. a launch that does not ask for PDL is a barrier too; one that is huge (grid >> device) shortens the window to 1
+    key = 0x1005
+    L.b200vfx_debug_pdl_reset(key)
+    assert _admit(L, key, buf(0), buf(1), capped, True) == 1
+    assert _admit(L, key, buf(2), buf(3), capped, True, want=0) == 0
+    assert _admit(L, key, buf(4), buf(1), capped, True) == 1          # buf(1) was written before the barrier
+    huge = 148 * 2048 * 4
+    key = 0x1006
+    L.b200vfx_debug_pdl_reset(key)
+    assert _admit(L, key, buf(0), buf(1), huge, True) == 1
+    assert _admit(L, key, buf(2), buf(3), huge, True) == 1
+    assert _admit(L, key, buf(4), buf(1), huge, True) == 1            # two launches back: cannot still be resident
+    assert _admit(L, key, buf(6), buf(1), huge, True) == 0            # the previous launch itself
+    for k in range(0x1000, 0x1007):
+        L.b200vfx_debug_pdl_reset(k)
