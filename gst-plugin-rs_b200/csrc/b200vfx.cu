@@ -65,6 +65,7 @@ struct b200vfx_ctx {
   bool use_user_stream = false;
   cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;  // host-pointer pipeline
   std::vector<cudaEvent_t> ev_in, ev_k;
+  cudaEvent_t ev_order = nullptr;      // orders the internal pipeline stream after the context stream (mixed host/device calls)
   DevBuf stage_in, stage_out, stage_sums;
   int chunk_rows = 0;
   int sm_count = 148;
@@ -142,6 +143,17 @@ int table_built(b200vfx_ctx *c, TableSync &t, cudaStream_t st) {
 }
 int table_wait(b200vfx_ctx *c, const TableSync &t, cudaStream_t st) {
   if (t.valid && t.st != st) CU(c, cudaStreamWaitEvent(st, t.ev, 0));
+  return 0;
+}
+
+// A call that mixes host and device planes runs on the internal pipeline stream s_k, but its device planes belong to the
+// context (or user) stream: whatever was enqueued there before this call -- e.g. the element upstream that produces the
+// device frame -- must have finished before s_k touches them.
+int order_after_ctx_stream(b200vfx_ctx *c, cudaStream_t st) {
+  if (st == c->stream()) return 0;
+  if (!c->ev_order) CU(c, cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
+  CU(c, cudaEventRecord(c->ev_order, c->stream()));
+  CU(c, cudaStreamWaitEvent(st, c->ev_order, 0));
   return 0;
 }
 
@@ -262,7 +274,9 @@ int ensure_l2_set_aside(b200vfx_ctx *c, size_t want) {
 //    counts sum to less than what the device holds.  Walking back from the newest launch, the point where that sum reaches
 //    the device's thread capacity ends the list of possibly-running launches (2 launches for 4 CTAs per SM).
 //  * Anything else (small frames, non-persistent kernels) does not linger -- the wait costs ~3 us of completion latency per
-//    kernel, which small frames cannot hide: there the last 4 launches are assumed to be possibly running, as before.
+//    kernel, which small frames cannot hide.  Nothing bounds how many of those can be co-resident (they trigger at entry and
+//    complete out of order), so EVERY such launch since the last plain launch (= full barrier) counts as possibly running;
+//    the record holds kPdlQueueMax launches and a full record turns the next launch into a plain one.
 constexpr size_t kPdlQueueMax = 16;
 struct Span { uintptr_t lo, hi; };
 struct RecentLaunch { Span src, dst; long long threads; bool lingers; };
@@ -283,20 +297,28 @@ bool pdl_admit(bool want, cudaStream_t st, Span src, Span dst) {
   std::deque<RecentLaunch> &q = g_recent[st];
   bool ok = want;
   if (ok) {
-    long long newer = 0;   // threads of the launches newer than the one being examined
-    int count = 0;
-    bool all_linger = true;
-    for (auto r = q.rbegin(); r != q.rend(); ++r) {
-      if (all_linger ? newer >= g_capacity_threads : count >= 4) break;   // *r and everything older has completed
-      if (overlap(dst, r->src) || overlap(dst, r->dst) || overlap(src, r->dst)) { ok = false; break; }
-      newer += r->threads;
-      all_linger = all_linger && r->lingers;
-      count++;
+    // Walking back from the newest launch.  Launch r has provably completed when every launch newer than r lingers (those
+    // complete in launch order and hold their slots until their predecessor has completed) and together they fill the
+    // device: were r still running, none of them could have retired a CTA.  A launch that does not linger gives no
+    // such bound for anything older than itself: those stay "possibly running" until the next plain launch (= barrier).
+    long long newer = 0;       // threads of the launches newer than the one being examined
+    bool newer_linger = true;  // ... and whether all of them linger
+    size_t oldest_unknown = q.size();   // index of the oldest launch that could not be proven complete
+    for (size_t i = q.size(); i-- > 0;) {
+      const RecentLaunch &r = q[i];
+      if (!(newer_linger && newer >= g_capacity_threads)) {
+        if (overlap(dst, r.src) || overlap(dst, r.dst) || overlap(src, r.dst)) { ok = false; break; }
+        oldest_unknown = i;
+      }
+      newer += r.threads;
+      newer_linger = newer_linger && r.lingers;
     }
+    if (ok && oldest_unknown > 0 && oldest_unknown <= q.size()) q.erase(q.begin(), q.begin() + (long)std::min(oldest_unknown, q.size()));
+    // the record is bounded: when it is full the new launch becomes a plain one (a barrier), which empties it
+    if (ok && q.size() >= kPdlQueueMax) ok = false;
   }
   if (!ok) q.clear();  // a normal launch starts only after everything before it has completed
   q.push_back(RecentLaunch{src, dst, 0, false});
-  if (q.size() > kPdlQueueMax) q.pop_front();
   return ok;
 }
 void pdl_note_linger(cudaStream_t st) {   // the launch just admitted ends on griddepcontrol.wait
@@ -477,7 +499,7 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
 #define LAUNCH_PLAIN(P)                                                                                               \
   do {                                                                                                                \
     if (c->lut_kind == 3) CU(c, launch_k(c->pdl_now, colorlut_memo_apply_kernel<P>, grid, dim3(256), 0, st, c->d_memo, f.src, ss, f.dst, ds, w, h, linger));  \
-    else CU(c, launch_k(c->pdl_now, colorlut_memo1d_apply_kernel<P>, grid, dim3(256), 0, st, c->d_memo1d, f.src, ss, f.dst, ds, w, h));              \
+    else CU(c, launch_k(c->pdl_now, colorlut_memo1d_apply_kernel<P>, grid, dim3(256), 0, st, c->d_memo1d, f.src, ss, f.dst, ds, w, h, linger));      \
   } while (0)
       if (PX == 16) LAUNCH_PLAIN(16); else if (PX == 8) LAUNCH_PLAIN(8); else LAUNCH_PLAIN(4);
 #undef LAUNCH_PLAIN
@@ -763,6 +785,9 @@ int run_staged(b200vfx_ctx *c, const Staged &s, LaunchFn launch) {
   }
   const bool need_h2d = s.in_place ? true : !src_dev;
   const bool need_d2h = s.in_place ? true : !dst_dev;
+  // one plane in HBM, the other on the host: the device plane is ordered on the context stream (header contract)
+  if (!s.in_place && ((src_dev && s.src && !(s.device_addressable & 1)) || (dst_dev && !(s.device_addressable & 2))))
+    if (int rc = order_after_ctx_stream(c, c->s_k)) return rc;
   int rows = c->chunk_rows;
   if (rows <= 0) {
     // measured on B200/PCIe5 (profiles/r01_e2e_chunks.md): ~8 MB chunks win for 4K frames (4 chunks);
@@ -906,6 +931,7 @@ void b200vfx_ctx_destroy(b200vfx_ctx *c) {
   for (TableSync *t : {&c->ts_colorlut, &c->ts_hf, &c->ts_hd}) if (t->ev) cudaEventDestroy(t->ev);
   for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
+  if (c->ev_order) cudaEventDestroy(c->ev_order);
   c->stage_in.release(); c->stage_out.release(); c->stage_sums.release();
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
@@ -1274,6 +1300,11 @@ int b200vfx_blockhash_sums_batch(b200vfx_ctx *c, int fmt, int width, int height,
   for (int f = 0; f < n_frames; f++) { on_dev[f] = is_device_ptr(srcs[f]); all_dev = all_dev && on_dev[f]; }
   const bool sums_dev = is_device_ptr(sums);
   cudaStream_t st = all_dev ? c->stream() : c->s_k;
+  {
+    bool any_dev = sums_dev;
+    for (int f = 0; f < n_frames; f++) any_dev = any_dev || on_dev[f];
+    if (!all_dev && any_dev) if (int rc = order_after_ctx_stream(c, st)) return rc;   // mixed batch: device frames follow the context stream
+  }
   BlockhashFrames fr{};
   const long staged_stride = (long)((row + 15) & ~(size_t)15);
   size_t staged = 0;
@@ -1382,6 +1413,7 @@ int b200vfx_colordetect_histogram(b200vfx_ctx *c, int fmt, int width, int height
   const long long nsamples = (npix + quality - 1) / quality;
   const bool src_dev = plane_bytes == 0 || is_device_ptr(src), hist_dev = is_device_ptr(hist);
   cudaStream_t st = src_dev ? c->stream() : c->s_k;
+  if (!src_dev && hist_dev) if (int rc = order_after_ctx_stream(c, st)) return rc;   // device histogram, host frame
   const uint8_t *d_src = (const uint8_t *)src;
   if (!src_dev) {
     CU(c, c->stage_in.reserve(plane_bytes));

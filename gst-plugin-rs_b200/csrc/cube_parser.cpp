@@ -9,6 +9,8 @@
 //   * every other line is a data line of exactly three Rust-syntax f32 literals
 //   * 1D size 2..=65536, 3D size 2..=256, value count must match, domain min < max per channel
 //   * the file must be valid UTF-8 (fs::read_to_string)
+#include <locale.h>
+
 #include <cerrno>
 #include <cmath>
 #include <cstdio>
@@ -100,9 +102,13 @@ bool parse_float(sv t, float &out) {
     while (isd(j)) j++;
   }
   if (j != body.size()) return false;
+  // correctly rounded like Rust's dec2flt -- and, like it, independent of the process locale: a GTK / GStreamer
+  // application that called setlocale(LC_ALL, "") under de_DE would make plain strtof stop at the '.'
+  static const locale_t c_locale = newlocale(LC_ALL_MASK, "C", (locale_t)0);
   const std::string z(t);
-  out = std::strtof(z.c_str(), nullptr);  // correctly rounded, like Rust's dec2flt
-  return true;
+  char *end = nullptr;
+  out = c_locale ? strtof_l(z.c_str(), &end, c_locale) : std::strtof(z.c_str(), &end);
+  return end == z.c_str() + z.size();   // the grammar check above already accepted the whole token
 }
 
 // <usize as FromStr>: '+'? digits+, overflow rejected

@@ -170,21 +170,25 @@ __global__ void __launch_bounds__(256) colorlut_memo_apply_kernel(const uint32_t
   if (linger) pdl_wait_prior();   // capped grids only (large frames): see pdl_admit in b200vfx.cu
 }
 
-// 1D LUT: three 256-byte tables in shared memory
+// 1D LUT: three 256-byte tables in shared memory.  Item-persistent like the 3D kernel above (item = row x chunk of
+// 8 warps x 32*PX pixels): any 1-D grid covers any frame, whether it was flattened to one long row or not.
 template <int PX>
 __global__ void __launch_bounds__(256) colorlut_memo1d_apply_kernel(const uint8_t *__restrict__ memo1d,
                                                                     const uint8_t *__restrict__ src, long sstride,
                                                                     uint8_t *__restrict__ dst, long dstride,
-                                                                    int width, int height) {
+                                                                    int width, int height, int linger) {
   pdl_trigger();
   __shared__ uint8_t tab[768];
   for (int i = threadIdx.x; i < 768 / 4; i += blockDim.x)
     reinterpret_cast<uint32_t *>(tab)[i] = __ldg(reinterpret_cast<const uint32_t *>(memo1d) + i);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int x0 = (blockIdx.x * (blockDim.x >> 5) + warp) * (32 * PX) + lane;
-  if (x0 - lane >= width) return;
-  for (int row = blockIdx.y; row < height; row += gridDim.y) {
+  const int chunks_x = (width + 8 * 32 * PX - 1) / (8 * 32 * PX);
+  const long long items = (long long)chunks_x * height;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int row = (int)(item / chunks_x), cx = (int)(item - (long long)row * chunks_x);
+    const int x0 = (cx * 8 + warp) * (32 * PX) + lane;
+    if (x0 - lane >= width) continue;
     const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)row * sstride);
     uint32_t *d = reinterpret_cast<uint32_t *>(dst + (size_t)row * dstride);
     uint32_t px[PX];
@@ -196,6 +200,7 @@ __global__ void __launch_bounds__(256) colorlut_memo1d_apply_kernel(const uint8_
       if (x0 + 32 * k < width) st_stream_u32(d + x0 + 32 * k, r | (g << 8) | (b << 16) | (px[k] & 0xFF000000u));
     }
   }
+  if (linger) pdl_wait_prior();
 }
 
 // generic byte-addressed fallback for rows that are not 4-byte aligned

@@ -103,6 +103,10 @@ __device__ __forceinline__ void peer_exit(const PeerSet &ps, uint64_t deadline, 
     if (t < ps.world && t != ps.rank) {
       if (ok) st_release_sys(ps.flags[t] + PF_DONE + ps.rank, ps.epoch);
       if (!wait_epoch(mine + PF_DONE + t, ps.epoch, deadline)) atomicExch(mine + PF_ERR, ps.epoch);
+      // the polls are relaxed (an acquire per poll would invalidate L1 under the table gathers); ONE acquire fence
+      // after the last wait, just before the kernel ends, makes the post-condition formal: everything the peers
+      // stored before publishing DONE happens-before whatever follows this kernel on the stream
+      fence_acq_rel_sys();
     }
   }
 }

@@ -1,0 +1,79 @@
+"""GPU tests added in round 2: the round-1 review findings (1D LUT geometry, mixed host/device ordering) and the new kernels."""
+import numpy as np
+import pytest
+
+import b200vfx
+import oracle_binding as orc
+from b200vfx import synth
+
+pytestmark = pytest.mark.gpu
+NT = 8
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = b200vfx.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("w,h,pad", [(1920, 1080, 0), (3840, 2160, 0), (1918, 1080, 0), (1919, 1081, 12), (2562, 1440, 0)])
+@pytest.mark.parametrize("stream_path", [0, -1])
+def test_colorlut_1d_device_frames_any_size(ctx, w, h, pad, stream_path):
+    """1D LUT on device frames beyond 592*256*8 pixels: every pixel must be written (the non-TMA kernel is item-persistent),
+    with stream_path = 0 and with widths that are not a multiple of 4 (rows then are not flattened / not 16-byte aligned)"""
+    torch = pytest.importorskip("torch")
+    cube = orc.cube_parse(synth.cube_text_1d(1024, 2.0))
+    ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.set_option("stream_path", stream_path)
+    try:
+        stride = 4 * w + pad
+        frame = synth.frame_noise("RGBA", w, h, 0x1D + w, stride=stride)
+        exp = orc.colorlut_apply(cube, "RGBA", w, h, frame, threads=NT)
+        d_src = torch.from_numpy(frame).cuda()
+        for px in (4, 8, 16):
+            ctx.set_option("memo_px", px)
+            d_dst = torch.full_like(d_src, 0xA5)
+            ctx.colorlut_process("RGBA", w, h, d_src, stride, d_dst, stride)
+            torch.cuda.synchronize()
+            got = d_dst.cpu().numpy()
+            assert (got[:, :4 * w] == exp[:, :4 * w]).all(), (w, h, px)
+            assert (got[:, 4 * w:] == 0xA5).all()          # padding untouched
+    finally:
+        ctx.set_option("stream_path", -1)
+        ctx.set_option("memo_px", 8)
+
+
+def test_mixed_host_device_calls_follow_the_context_stream():
+    """a device frame produced asynchronously on the context stream and consumed by a call whose OTHER plane is host memory
+    (which runs on the library's internal stream) must be ordered after its producer"""
+    torch = pytest.importorskip("torch")
+    w, h = 3840, 2160
+    frame = synth.frame_noise("BGRx", w, h, 321)
+    fo = dict(hue_shift=33.0)
+    step1 = orc.hsvfilter("BGRx", w, h, frame.copy(), threads=NT, **fo)
+    dkw = dict(hue_ref=120.0, hue_var=60.0, saturation_ref=0.6, saturation_var=0.4, value_ref=0.6, value_var=0.4)
+    exp = orc.hsvdetector("BGRx", "RGBA", w, h, step1, hue_ref=120.0, hue_var=60.0, sat_ref=0.6, sat_var=0.4, val_ref=0.6, val_var=0.4, threads=NT)
+    exp_sums = orc.blockhash_sums("RGBA", w, h, exp)
+    with b200vfx.Context(0) as ctx:
+        s = torch.cuda.Stream()
+        ctx.set_stream(s.cuda_stream)
+        ctx.set_option("hsv_memo", 0)      # the slow direct kernel: the producer is certainly still running when the consumer is enqueued
+        for rep in range(3):
+            with torch.cuda.stream(s):
+                d = torch.from_numpy(frame).cuda(non_blocking=False)
+            for _ in range(2):             # queue some work in front of the producer
+                ctx.hsvfilter_process("BGRx", w, h, torch.from_numpy(frame).cuda(), 4 * w, hue_shift=1.0)
+            ctx.hsvfilter_process("BGRx", w, h, d, 4 * w, **fo)                                  # device, in place, async on s
+            out = np.zeros((h, 4 * w), np.uint8)
+            ctx.hsvdetector_process("BGRx", "RGBA", w, h, d, 4 * w, out, 4 * w, **dkw)          # device src, HOST dst
+            assert (out == exp).all(), rep
+            # blockhash batch mixing a device frame that is still being produced with a host frame
+            with torch.cuda.stream(s):
+                dd = torch.zeros((h, 4 * w), dtype=torch.uint8, device="cuda")
+            ctx.hsvdetector_process("BGRx", "RGBA", w, h, d, 4 * w, dd, 4 * w, **dkw)            # device -> device, async on s
+            sums = np.zeros(128, np.uint32)
+            ctx.blockhash_sums_batch("RGBA", w, h, [dd, exp], [4 * w, 4 * w], sums)
+            assert (sums[:64] == exp_sums).all() and (sums[64:] == exp_sums).all(), rep
+            s.synchronize()

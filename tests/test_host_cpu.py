@@ -114,6 +114,30 @@ def test_product_parser_invalid_utf8_and_missing_file(tmp_path):
     L.b200vfx_cube_free(vals)
 
 
+def test_product_parser_is_locale_independent():
+    """Rust's str::parse::<f32> ignores the process locale; so must the product parser (strtof is LC_NUMERIC-dependent)"""
+    import locale
+    text = "LUT_1D_SIZE 2\n0.25 0.5 0.75\n1.0 1e0 1.5e-1\n"
+    ref = b200vfx.cube_parse(text)
+    old = locale.setlocale(locale.LC_NUMERIC)
+    tried = []
+    try:
+        for name in ("de_DE.UTF-8", "de_DE.utf8", "fr_FR.UTF-8", "fr_FR.utf8", "de_DE", "fr_FR", "ru_RU.UTF-8", "nl_NL.UTF-8"):
+            try:
+                locale.setlocale(locale.LC_NUMERIC, name)
+            except locale.Error:
+                continue
+            tried.append(name)
+            got = b200vfx.cube_parse(text)
+            assert got[0] == ref[0] and got[1] == ref[1] and np.array_equal(np.asarray(got[2]), np.asarray(ref[2])), name
+    finally:
+        locale.setlocale(locale.LC_NUMERIC, old)
+    # the container may ship no comma-decimal locale: then only the "C" path ran (values checked against the KATs elsewhere)
+    assert np.allclose(np.asarray(ref[2]).reshape(-1)[:3], [0.25, 0.5, 0.75])
+    if not tried:
+        pytest.skip("no comma-decimal locale installed in this image")
+
+
 def test_blockhash_bits_and_distance_host_side():
     rng = np.random.default_rng(3)
     for _ in range(20):
@@ -227,15 +251,31 @@ def test_pdl_admission_rule():
     L.b200vfx_debug_pdl_reset(key)
     got = [_admit(L, key, buf(100 + i), buf(i % 2), capped, True) for i in range(8)]
     assert got[:2] == [1, 1] and 0 in got[2:]
-    # 2. small frames / non-lingering kernels: the last 4 launches are assumed running -> pool of 5 ok, pool of 4 not
+    # 2. small frames / non-lingering kernels: nothing bounds how many are co-resident, so every launch since the last
+    #    barrier counts as running -> reusing ANY buffer of the chain is refused (and the refusal is the barrier) ...
     small = 300 * 256
-    key = 0x1002
-    L.b200vfx_debug_pdl_reset(key)
-    assert [_admit(L, key, buf(100 + i), buf(i % 5), small, False) for i in range(15)] == [1] * 15
+    for pool in (4, 5, 9):
+        key = 0x1002
+        L.b200vfx_debug_pdl_reset(key)
+        got = [_admit(L, key, buf(100 + i), buf(i % pool), small, False) for i in range(3 * pool)]
+        assert got == [1] * pool + ([0] + [1] * (pool - 1)) * 2, (pool, got)
+    #    ... and with all-distinct buffers the bounded record forces a plain launch when it is full (16 launches)
     key = 0x1003
     L.b200vfx_debug_pdl_reset(key)
-    got = [_admit(L, key, buf(100 + i), buf(i % 4), small, False) for i in range(12)]
-    assert got[:4] == [1, 1, 1, 1] and got[4] == 0
+    got = [_admit(L, key, buf(100 + i), buf(200 + i), small, False) for i in range(40)]
+    assert got[:16] == [1] * 16 and got[16] == 0 and got[17:32] == [1] * 15 and got[32] == 0   # the barrier launch is entry 1 of the new record
+    #    a lingering stream never fills the record (completed launches are forgotten)
+    key = 0x1007
+    L.b200vfx_debug_pdl_reset(key)
+    assert [_admit(L, key, buf(100 + i), buf(200 + i), capped, True) for i in range(64)] == [1] * 64
+    #    one non-lingering launch inside a lingering stream removes the occupancy bound for everything behind it
+    key = 0x1008
+    L.b200vfx_debug_pdl_reset(key)
+    assert _admit(L, key, buf(0), buf(1), capped, True) == 1
+    assert _admit(L, key, buf(2), buf(3), small, False) == 1
+    assert _admit(L, key, buf(4), buf(5), capped, True) == 1
+    assert _admit(L, key, buf(6), buf(7), capped, True) == 1
+    assert _admit(L, key, buf(8), buf(1), capped, True) == 0          # 4 launches back, but the chain is not all-lingering
     # 3. chained elements (input = the previous launch's output) and in-place reuse never overlap
     key = 0x1004
     L.b200vfx_debug_pdl_reset(key)
@@ -256,5 +296,5 @@ def test_pdl_admission_rule():
     assert _admit(L, key, buf(2), buf(3), huge, True) == 1
     assert _admit(L, key, buf(4), buf(1), huge, True) == 1            # two launches back: cannot still be resident
     assert _admit(L, key, buf(6), buf(1), huge, True) == 0            # the previous launch itself
-    for k in range(0x1000, 0x1007):
+    for k in range(0x1000, 0x1009):
         L.b200vfx_debug_pdl_reset(k)
