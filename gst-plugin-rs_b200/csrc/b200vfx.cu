@@ -88,6 +88,7 @@ struct b200vfx_ctx {
   int memo_ctas = 4;     // CTAs per SM of the persistent table-lookup kernels: 4 x 256 threads = half the thread slots, so the next
                          // frame's kernel (PDL) is resident beside this one (profiles/r01_memo_ctas_experiment.jsonl)
   int memo_tile = 0;     // 4-byte-pixel table lookups through memo_tile_kernel (per-tile shared-memory copy of the colour sub-cube)
+  int memo_tile_small = 256;   // ... tiles whose colour box has at most this many entries gather directly (already coherent)
   int cd_cluster = 2;    // colordetect: CTAs per cluster merging their shared-memory histograms (1, 2, 4, 8)
   int peer_timeout_ms = 2000;  // deadline of the cross-GPU waits in the tile-gather kernel
   std::string err;
@@ -479,8 +480,9 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
     int w = f.width, h = f.height;
     long ss = f.sstride, ds = f.dstride;
     if (c->memo_tile && c->lut_kind == 3 && (w % 4) == 0 && aligned(f.src, ss, 16) && aligned(f.dst, ds, 16)) {
-      dim3 grid((unsigned)ceil_div(w, kTileW), (unsigned)ceil_div(h, kTileH));
-      CU(c, launch_k(c->pdl_now, memo_tile_kernel<0, false>, grid, dim3(256), 0, st, c->d_memo, f.src, ss, f.dst, ds, w, h));
+      const long long ntiles = (long long)ceil_div(w, kTileW) * ceil_div(h, kTileH);
+      dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(ntiles, (long long)c->sm_count * 3)));   // persistent
+      CU(c, launch_k(c->pdl_now, memo_tile_kernel<0, false>, grid, dim3(256), 0, st, c->d_memo, f.src, ss, f.dst, ds, w, h, c->memo_tile_small));
       c->launches++;
       CU(c, cudaGetLastError());
       return 0;
@@ -543,18 +545,29 @@ bool hsv_memo_decide(int option, bool key_same, uint64_t &px_seen, uint64_t npx,
   return ready || option == 1 || px_seen >= (1ull << 24);
 }
 
+constexpr int kHsvDirectPx = 4;   // independent pixels per thread of hsv_direct_map_kernel
+
 template <int BPP, int COFF, bool BGR>
 void launch_hsvfilter_t(const HsvFilterSettings &s, const uint32_t *memo, uint8_t *data, long stride, int w, int h,
                         cudaStream_t st, int sm_count) {
   const bool al = BPP == 4 && aligned(data, stride, 4);
+  const int cls = hsvf_shift_class(s.hue_shift);
   if (memo) {
     dim3 grid((unsigned)ceil_div(w, 256), grid_rows(h));
-    if (al) hsvfilter_kernel<BPP, COFF, BGR, true, true><<<grid, 256, 0, st>>>(s, memo, data, stride, w, h);
-    else hsvfilter_kernel<BPP, COFF, BGR, false, true><<<grid, 256, 0, st>>>(s, memo, data, stride, w, h);
+    if (al) hsvfilter_kernel<BPP, COFF, BGR, true, true><<<grid, 256, 0, st>>>(s, cls, memo, data, stride, w, h);
+    else hsvfilter_kernel<BPP, COFF, BGR, false, true><<<grid, 256, 0, st>>>(s, cls, memo, data, stride, w, h);
+  } else if (al) {   // 4-byte pixels: lane-consecutive map kernel, kHsvDirectPx independent pixels per thread
+    int ww = w, hh = h;
+    if (stride == 4L * w && (long long)w * h < (1LL << 28)) { ww = w * h; hh = 1; }
+    const long long items = (long long)ceil_div(ww, 8 * 32 * kHsvDirectPx) * hh;
+    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(items, (long long)sm_count * 8)));
+    if (cls) hsv_direct_map_kernel<HsvFilterDirectOp<BPP == 4 ? COFF : 0, BGR, 1>, kHsvDirectPx><<<grid, 256, 0, st>>>(
+        HsvFilterDirectOp<BPP == 4 ? COFF : 0, BGR, 1>{s, 1.0f}, data, stride, data, stride, ww, hh);
+    else hsv_direct_map_kernel<HsvFilterDirectOp<BPP == 4 ? COFF : 0, BGR, 0>, kHsvDirectPx><<<grid, 256, 0, st>>>(
+        HsvFilterDirectOp<BPP == 4 ? COFF : 0, BGR, 0>{s, 1.0f}, data, stride, data, stride, ww, hh);
   } else {
     dim3 grid((unsigned)ceil_div(w, 256), grid_rows_persistent(ceil_div(w, 256), h, sm_count));
-    if (al) hsvfilter_kernel<BPP, COFF, BGR, true, false><<<grid, 256, 0, st>>>(s, nullptr, data, stride, w, h);
-    else hsvfilter_kernel<BPP, COFF, BGR, false, false><<<grid, 256, 0, st>>>(s, nullptr, data, stride, w, h);
+    hsvfilter_kernel<BPP, COFF, BGR, false, false><<<grid, 256, 0, st>>>(s, cls, nullptr, data, stride, w, h);
   }
 }
 
@@ -571,7 +584,7 @@ int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings 
       if (int rc = ensure_l2_set_aside(c, (size_t)72 << 20)) return rc;
       if (!c->d_hf_memo) CU(c, cudaMalloc(&c->d_hf_memo, sizeof(uint32_t) << 24));
       pdl_admit(false, st, Span{0, 0}, Span{0, 0});  // plain launch
-      hsvfilter_memo_build_kernel<<<(1u << 24) / 256, 256, 0, st>>>(s, c->d_hf_memo);
+      hsvfilter_memo_build_kernel<<<(unsigned)c->sm_count * 8, 256, 0, st>>>(s, hsvf_shift_class(s.hue_shift), c->d_hf_memo);
       c->launches++;
       CU(c, cudaGetLastError());
       c->hf_ready = true;
@@ -587,8 +600,9 @@ int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings 
     const Span sp = span_of(data, stride, (size_t)w * 4, h);
     const bool pdl = pdl_admit(c->pdl && !built_now, st, sp, sp);
     if (c->memo_tile && (w % 4) == 0 && aligned(data, stride, 16)) {
-      dim3 tgrid((unsigned)ceil_div(w, kTileW), (unsigned)ceil_div(h, kTileH));
-#define LT(CO, BG) CU(c, launch_k(pdl, memo_tile_kernel<CO, BG>, tgrid, dim3(256), 0, st, memo, (const uint8_t *)data, stride, data, stride, w, h))
+      const long long ntiles = (long long)ceil_div(w, kTileW) * ceil_div(h, kTileH);
+      dim3 tgrid((unsigned)std::max<long long>(1, std::min<long long>(ntiles, (long long)c->sm_count * 3)));
+#define LT(CO, BG) CU(c, launch_k(pdl, memo_tile_kernel<CO, BG>, tgrid, dim3(256), 0, st, memo, (const uint8_t *)data, stride, data, stride, w, h, c->memo_tile_small))
       if (fi.coff == 0) { if (fi.bgr) LT(0, true); else LT(0, false); }
       else { if (fi.bgr) LT(1, true); else LT(1, false); }
 #undef LT
@@ -636,16 +650,26 @@ template <int IBPP, int ICOFF, bool IBGR>
 int launch_hsvdetector_t(b200vfx_ctx *c, const FmtInfo &fo, const HsvDetectSettings &s, const uint32_t *bitmap, bool pdl,
                          const Frame &f, cudaStream_t st) {
   const bool al = aligned(f.dst, f.dstride, 4) && (IBPP == 3 || aligned(f.src, f.sstride, 4));
+  const int cls = hsvf_shift_class(180.0f - s.hue_ref);
   const int gx = ceil_div(f.width, 256);
   dim3 grid((unsigned)gx, bitmap ? grid_rows(f.height) : grid_rows_persistent(gx, f.height, c->sm_count));
 #define L(OC, OB)                                                                                                          \
   do {                                                                                                                     \
     if (bitmap) {                                                                                                          \
-      if (al) CU(c, launch_k(pdl, hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, true, true>, grid, dim3(256), 0, st, s, bitmap, f.src, f.sstride, f.dst, f.dstride, f.width, f.height)); \
-      else CU(c, launch_k(pdl, hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, false, true>, grid, dim3(256), 0, st, s, bitmap, f.src, f.sstride, f.dst, f.dstride, f.width, f.height)); \
+      if (al) CU(c, launch_k(pdl, hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, true, true>, grid, dim3(256), 0, st, s, cls, bitmap, f.src, f.sstride, f.dst, f.dstride, f.width, f.height)); \
+      else CU(c, launch_k(pdl, hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, false, true>, grid, dim3(256), 0, st, s, cls, bitmap, f.src, f.sstride, f.dst, f.dstride, f.width, f.height)); \
     } else {                                                                                                               \
-      if (al) hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, true, false><<<grid, 256, 0, st>>>(s, nullptr, f.src, f.sstride, f.dst, f.dstride, f.width, f.height); \
-      else hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, false, false><<<grid, 256, 0, st>>>(s, nullptr, f.src, f.sstride, f.dst, f.dstride, f.width, f.height);  \
+      if (al && IBPP == 4) {                                                                                               \
+        int ww = f.width, hh = f.height;                                                                                   \
+        if (f.sstride == 4L * ww && f.dstride == 4L * ww && (long long)ww * hh < (1LL << 28)) { ww = ww * hh; hh = 1; }    \
+        const long long items = (long long)ceil_div(ww, 8 * 32 * kHsvDirectPx) * hh;                                       \
+        dim3 g2((unsigned)std::max<long long>(1, std::min<long long>(items, (long long)c->sm_count * 8)));                 \
+        if (cls) hsv_direct_map_kernel<HsvDetectDirectOp<IBPP == 4 ? ICOFF : 0, IBGR, OC, OB, 1>, kHsvDirectPx><<<g2, 256, 0, st>>>( \
+            HsvDetectDirectOp<IBPP == 4 ? ICOFF : 0, IBGR, OC, OB, 1>{s, 1.0f}, f.src, f.sstride, f.dst, f.dstride, ww, hh);     \
+        else hsv_direct_map_kernel<HsvDetectDirectOp<IBPP == 4 ? ICOFF : 0, IBGR, OC, OB, 0>, kHsvDirectPx><<<g2, 256, 0, st>>>( \
+            HsvDetectDirectOp<IBPP == 4 ? ICOFF : 0, IBGR, OC, OB, 0>{s, 1.0f}, f.src, f.sstride, f.dst, f.dstride, ww, hh);     \
+      } else if (al) hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, true, false><<<grid, 256, 0, st>>>(s, cls, nullptr, f.src, f.sstride, f.dst, f.dstride, f.width, f.height); \
+      else hsvdetector_kernel<IBPP, ICOFF, IBGR, OC, OB, false, false><<<grid, 256, 0, st>>>(s, cls, nullptr, f.src, f.sstride, f.dst, f.dstride, f.width, f.height);  \
     }                                                                                                                      \
   } while (0)
   if (fo.coff == 0) { if (fo.bgr) L(0, true); else L(0, false); }
@@ -667,7 +691,7 @@ int launch_hsvdetector(b200vfx_ctx *c, const FmtInfo &fi, const FmtInfo &fo, con
     if (!c->hd_ready) {
       if (!c->d_hd_bitmap) CU(c, cudaMalloc(&c->d_hd_bitmap, (1u << 24) / 8));
       pdl_admit(false, st, Span{0, 0}, Span{0, 0});
-      hsvdetector_bitmap_build_kernel<<<(1u << 24) / 256, 256, 0, st>>>(s, c->d_hd_bitmap);
+      hsvdetector_bitmap_build_kernel<<<1024, 256, 0, st>>>(s, hsvf_shift_class(180.0f - s.hue_ref), c->d_hd_bitmap);
       c->launches++;
       CU(c, cudaGetLastError());
       c->hd_ready = true;
@@ -978,6 +1002,7 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "zero_copy") { c->zero_copy = value; c->zc_calls = 0; c->zc_best_ms[0] = c->zc_best_ms[1] = 1e30; }
   else if (n == "blockhash_tma") c->blockhash_tma = value != 0;
   else if (n == "memo_tile") c->memo_tile = value != 0;
+  else if (n == "memo_tile_small") c->memo_tile_small = std::max(0, value);
   else if (n == "memo_ctas") c->memo_ctas = std::max(2, std::min(8, value));
   else if (n == "cd_cluster") c->cd_cluster = (value == 1 || value == 2 || value == 4 || value == 8) ? value : 2;
   else if (n == "l2_persist") c->l2_persist = value;

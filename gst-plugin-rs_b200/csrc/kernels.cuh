@@ -233,29 +233,32 @@ __global__ void colorlut_memo_apply_bytes_kernel(const uint32_t *__restrict__ me
 //   hsvfilter   : u32[2^24]  answer table  memo[r|g<<8|b<<16] = r'|g'<<8|b'<<16   (64 MiB, L2 resident)
 //   hsvdetector : 2^24-bit hit bitmap (2 MiB)
 // with the exact per-pixel evaluator below and the frame kernel becomes a table lookup (bit-exact by construction).
-__global__ void __launch_bounds__(256) hsvfilter_memo_build_kernel(HsvFilterSettings st, uint32_t *__restrict__ memo) {
-  __shared__ float d255[256];
-  fill_d255(d255);
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned r = idx & 255u, g = (idx >> 8) & 255u, b = idx >> 16;
-  hsvfilter_px(st, d255, r, g, b);
-  memo[memo_index(idx)] = r | (g << 8) | (b << 16);
+__global__ void __launch_bounds__(256) hsvfilter_memo_build_kernel(HsvFilterSettings st, int cls, uint32_t *__restrict__ memo) {
+  __shared__ HsvTables T;
+  fill_hsv_tables(&T, &st);
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < (1u << 24); idx += gridDim.x * blockDim.x) {
+    unsigned r4, g4, b4;
+    bytes_x4(idx, r4, g4, b4);
+    memo[memo_index(idx)] = hsvf_filter_px(&T, &st, cls, r4, g4, b4, 1.0f);
+  }
 }
 
-__global__ void __launch_bounds__(256) hsvdetector_bitmap_build_kernel(HsvDetectSettings st, uint32_t *__restrict__ bitmap) {
-  __shared__ float d255[256];
-  fill_d255(d255);
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;  // 32 consecutive colours per warp -> one bitmap word
-  const bool hit = hsvdetect_px(st, d255, idx & 255u, (idx >> 8) & 255u, idx >> 16);
-  const unsigned word = __ballot_sync(0xFFFFFFFFu, hit);
-  if ((threadIdx.x & 31) == 0) bitmap[idx >> 5] = word;
+__global__ void __launch_bounds__(256) hsvdetector_bitmap_build_kernel(HsvDetectSettings st, int cls, uint32_t *__restrict__ bitmap) {
+  __shared__ HsvTables T;
+  fill_hsv_tables(&T);
+  // 32 consecutive colours per warp -> one bitmap word; the grid-stride keeps whole warps together (2^24 % (grid*256) == 0)
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < (1u << 24); idx += gridDim.x * blockDim.x) {
+    const bool hit = hsvdetect_px(st, &T, cls, idx & 255u, (idx >> 8) & 255u, idx >> 16);
+    const unsigned word = __ballot_sync(0xFFFFFFFFu, hit);
+    if ((threadIdx.x & 31) == 0) bitmap[idx >> 5] = word;
+  }
 }
 
 template <int BPP, int COFF, bool BGR, bool ALIGNED, bool MEMO>
-__global__ void __launch_bounds__(256) hsvfilter_kernel(HsvFilterSettings st, const uint32_t *__restrict__ memo,
+__global__ void __launch_bounds__(256) hsvfilter_kernel(HsvFilterSettings st, int cls, const uint32_t *__restrict__ memo,
                                                         uint8_t *__restrict__ data, long stride, int width, int height) {
-  __shared__ float d255[256];
-  if (!MEMO) fill_d255(d255);
+  __shared__ HsvTables T;
+  if (!MEMO) fill_hsv_tables(&T, &st);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= width) return;
   for (int row = blockIdx.y; row < height; row += gridDim.y) {
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(256) hsvfilter_kernel(HsvFilterSettings st, co
       const uint32_t v = __ldg(memo + memo_index(r | (g << 8) | (b << 16)));
       r = v & 255u; g = (v >> 8) & 255u; b = (v >> 16) & 255u;
     } else {
-      hsvfilter_px(st, d255, r, g, b);
+      hsvfilter_px(st, &T, cls, r, g, b);
     }
     c0 = BGR ? b : r; c1 = g; c2 = BGR ? r : b;
     if (BPP == 4 && ALIGNED) {
@@ -287,12 +290,12 @@ __global__ void __launch_bounds__(256) hsvfilter_kernel(HsvFilterSettings st, co
 
 // IBPP/ICOFF/IBGR describe the input pixel; OCOFF/OBGR the 4-byte output pixel (alpha at 3 if OCOFF==0 else 0)
 template <int IBPP, int ICOFF, bool IBGR, int OCOFF, bool OBGR, bool ALIGNED, bool MEMO>
-__global__ void __launch_bounds__(256) hsvdetector_kernel(HsvDetectSettings st, const uint32_t *__restrict__ bitmap,
+__global__ void __launch_bounds__(256) hsvdetector_kernel(HsvDetectSettings st, int cls, const uint32_t *__restrict__ bitmap,
                                                           const uint8_t *__restrict__ src, long sstride,
                                                           uint8_t *__restrict__ dst, long dstride, int width, int height) {
   if (MEMO) pdl_trigger();
-  __shared__ float d255[256];
-  if (!MEMO) fill_d255(d255);
+  __shared__ HsvTables T;
+  if (!MEMO) fill_hsv_tables(&T);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= width) return;
   for (int row = blockIdx.y; row < height; row += gridDim.y) {
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(256) hsvdetector_kernel(HsvDetectSettings st, 
       const uint32_t idx = r | (g << 8) | (b << 16);
       hit = (__ldg(bitmap + (idx >> 5)) >> (idx & 31u)) & 1u;
     } else {
-      hit = hsvdetect_px(st, d255, r, g, b);
+      hit = hsvdetect_px(st, &T, cls, r, g, b);
     }
     const unsigned a = hit ? 255u : 0u;
     const unsigned o0 = OBGR ? b : r, o1 = g, o2 = OBGR ? r : b;
@@ -379,6 +382,70 @@ __global__ void __launch_bounds__(256) map_u32_kernel(Op op, const uint8_t *__re
       if (x0 + 32 * k < width) st_stream_u32(d + x0 + 32 * k, o[k]);
   }
   if (linger) pdl_wait_prior();
+}
+
+// --------------------------------------------------------------------------------------------
+// DIRECT hsvfilter / hsvdetector on 4-byte pixels (what frames get while properties are being animated and no
+// answer table can pay for itself): the map_u32_kernel thread mapping with the exact branch-free arithmetic of
+// hsv_fast.cuh and its 2 KB of shared-memory tables.  Issue-bound (~100 instructions per pixel): PX independent
+// pixels per thread give the scheduler ILP across the dependent FMA chains.
+// --------------------------------------------------------------------------------------------
+template <int COFF, bool BGR, int CLS>   // CLS = hsvf_shift_class (0: proven fast code, 1: general code), fixed per launch
+struct HsvFilterDirectOp {
+  HsvFilterSettings st;
+  float one;   // 1.0f, opaque to the compiler: keeps the adds that hsv_fast.cuh routes to the FMA pipe as FFMAs
+  static constexpr int cls = CLS;
+  __device__ __forceinline__ const HsvFilterParams *filter_params() const { return &st; }
+  __device__ __forceinline__ uint32_t operator()(const HsvTables *T, uint32_t px) const {
+    const uint32_t c = (px >> (8 * COFF)) & 0x00FFFFFFu;
+    unsigned c0, c1, c2;
+    bytes_x4(c, c0, c1, c2);
+    uint32_t v = hsvf_filter_px(T, &st, cls, BGR ? c2 : c0, c1, BGR ? c0 : c2, one);   // r | g<<8 | b<<16
+    if (BGR) v = swap_c0_c2(v);
+    const uint32_t keep = COFF ? (px & 0x000000FFu) : (px & 0xFF000000u);        // x / alpha byte untouched
+    return keep | (v << (8 * COFF));
+  }
+};
+template <int ICOFF, bool IBGR, int OCOFF, bool OBGR, int CLS>
+struct HsvDetectDirectOp {
+  HsvDetectSettings st;
+  float one;
+  static constexpr int cls = CLS;
+  __device__ __forceinline__ const HsvFilterParams *filter_params() const { return nullptr; }
+  __device__ __forceinline__ uint32_t operator()(const HsvTables *T, uint32_t px) const {
+    const uint32_t c = (px >> (8 * ICOFF)) & 0x00FFFFFFu;
+    unsigned c0, c1, c2;
+    bytes_x4(c, c0, c1, c2);
+    const bool hit = hsvf_detect_px(T, &st, cls, IBGR ? c2 : c0, c1, IBGR ? c0 : c2, one) != 0;
+    const uint32_t oc = (IBGR == OBGR) ? c : swap_c0_c2(c);
+    const uint32_t a = hit ? (OCOFF ? 0x000000FFu : 0xFF000000u) : 0u;
+    return (oc << (8 * OCOFF)) | a;
+  }
+};
+
+template <typename Op, int PX>
+__global__ void __launch_bounds__(256) hsv_direct_map_kernel(Op op, const uint8_t *__restrict__ src, long sstride,
+                                                             uint8_t *__restrict__ dst, long dstride, int width, int height) {
+  __shared__ HsvTables T;
+  fill_hsv_tables(&T, op.filter_params());
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunks_x = (width + 8 * 32 * PX - 1) / (8 * 32 * PX);
+  const long long items = (long long)chunks_x * height;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int row = (int)(item / chunks_x), cx = (int)(item - (long long)row * chunks_x);
+    const int x0 = (cx * 8 + warp) * (32 * PX) + lane;
+    if (x0 - lane >= width) continue;
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)row * sstride);
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst + (size_t)row * dstride);
+    uint32_t px[PX], o[PX];
+#pragma unroll
+    for (int k = 0; k < PX; k++) px[k] = (x0 + 32 * k < width) ? ld_stream_u32(s + x0 + 32 * k) : 0u;
+#pragma unroll
+    for (int k = 0; k < PX; k++) o[k] = op(&T, px[k]);
+#pragma unroll
+    for (int k = 0; k < PX; k++)
+      if (x0 + 32 * k < width) st_stream_u32(d + x0 + 32 * k, o[k]);
+  }
 }
 
 // --------------------------------------------------------------------------------------------

@@ -126,6 +126,19 @@ def main():
                 t = timeit(lambda i: ctx.hsvdetector_process("RGB", "ARGB", w, h, fr[i % 4], 3 * w, out[i % 4], 4 * w, **kw), max(args.iters // 3, 5))
                 report("hsvdetector_rgb_argb_" + tag_m, t, w * h * 7, content="noise", frame="%dx%d" % (w, h))
         ctx.set_option("hsv_memo", -1)
+    if want("hsvanim"):
+        # animated properties (a GstController changing hue-shift on every frame): no answer table survives, every frame
+        # takes the direct kernel -- default policy (hsv_memo = -1), per-frame distinct settings
+        ctx.set_option("hsv_memo", -1)
+        for cname in ("ramps", "noise", "natural"):
+            fr = [torch.from_numpy(contents[cname](i)).cuda() for i in range(RING)]
+            t = timeit(lambda i: ctx.hsvfilter_process("RGBA", W, H, fr[i % RING], 4 * W, hue_shift=0.37 * (i % 900) - 120.0, saturation_mul=1.1), args.iters)
+            report("hsvfilter_rgba_animated_hue_shift", t, 2 * W * H * 4, content=cname, frame="3840x2160")
+            out = [torch.empty_like(f) for f in fr]
+            t = timeit(lambda i: ctx.hsvdetector_process("BGRx", "RGBA", W, H, fr[i % RING], 4 * W, out[i % RING], 4 * W, hue_ref=0.5 * (i % 700), hue_var=30.0,
+                                                         saturation_ref=0.8, saturation_var=0.2, value_ref=0.8, value_var=0.2), args.iters)
+            report("hsvdetector_bgrx_rgba_animated_hue_ref", t, 2 * W * H * 4, content=cname, frame="3840x2160")
+            del fr, out
     if want("videofx"):
         frames, _ = ring_of(contents["noise"])
         sums = torch.zeros(64, dtype=torch.int32, device="cuda")

@@ -19,11 +19,15 @@ ap.add_argument("--lut", type=int, default=33)
 ap.add_argument("--launches", type=int, default=6)
 ap.add_argument("--quality", type=int, default=1)
 ap.add_argument("--memo-tile", type=int, default=0)
+ap.add_argument("--opt", action="append", default=[], help="name=value context option, repeatable (e.g. hsv_memo=0)")
 a = ap.parse_args()
 W, H = 3840, 2160
 ctx = b200vfx.Context(0)
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 ctx.set_option("memo_tile", a.memo_tile)
+for kv in a.opt:
+    name, val = kv.split("=")
+    ctx.set_option(name, int(val))
 
 
 def frame(fmt, w, h, i):

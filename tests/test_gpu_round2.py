@@ -77,3 +77,69 @@ def test_mixed_host_device_calls_follow_the_context_stream():
             ctx.blockhash_sums_batch("RGBA", w, h, [dd, exp], [4 * w, 4 * w], sums)
             assert (sums[:64] == exp_sums).all() and (sums[64:] == exp_sums).all(), rep
             s.synchronize()
+
+
+# ---- direct (non-memoised) hsv kernels: the branch-free arithmetic of hsv_fast.cuh on the GPU ------------------------
+from test_hsv_fast_model import FILTER_SETTINGS, DETECT_SETTINGS, all_colors_frame   # noqa: E402
+
+
+@pytest.mark.parametrize("st", FILTER_SETTINGS)
+def test_hsvfilter_direct_kernel_all_colors_all_setting_classes(ctx, st):
+    """every 24-bit colour through the direct kernel (hsv_memo = 0) == oracle, for ordinary settings and for the ones that
+    select the general code (NaN / inf / huge / near-denormal hue-shift)"""
+    torch = pytest.importorskip("torch")
+    ctx.set_option("hsv_memo", 0)
+    try:
+        frame = all_colors_frame()
+        kw = dict(hue_shift=st[0], sat_mul=st[1], sat_off=st[2], val_mul=st[3], val_off=st[4])
+        exp = orc.hsvfilter("RGBx", 4096, 4096, frame.copy(), threads=NT, **kw)
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        d = torch.from_numpy(frame).cuda()
+        ctx.hsvfilter_process("RGBx", 4096, 4096, d, 4 * 4096, hue_shift=st[0], saturation_mul=st[1], saturation_off=st[2],
+                              value_mul=st[3], value_off=st[4])
+        torch.cuda.synchronize()
+        assert (d.cpu().numpy() == exp).all(), st
+    finally:
+        ctx.set_option("hsv_memo", -1)
+
+
+@pytest.mark.parametrize("st", DETECT_SETTINGS)
+@pytest.mark.parametrize("ifmt,ofmt", [("RGBx", "RGBA"), ("xBGR", "ARGB")])
+def test_hsvdetector_direct_kernel_all_colors(ctx, st, ifmt, ofmt):
+    torch = pytest.importorskip("torch")
+    ctx.set_option("hsv_memo", 0)
+    try:
+        frame = all_colors_frame()
+        if ifmt == "xBGR":
+            frame = np.ascontiguousarray(frame.reshape(-1, 4)[:, ::-1]).reshape(4096, -1)   # x,B,G,R <- R,G,B,x reversed
+        exp = orc.hsvdetector(ifmt, ofmt, 4096, 4096, frame, hue_ref=st[0], hue_var=st[1], sat_ref=st[2], sat_var=st[3],
+                              val_ref=st[4], val_var=st[5], threads=NT)
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        d = torch.from_numpy(frame).cuda()
+        o = torch.zeros_like(d)
+        ctx.hsvdetector_process(ifmt, ofmt, 4096, 4096, d, 4 * 4096, o, 4 * 4096, hue_ref=st[0], hue_var=st[1],
+                                saturation_ref=st[2], saturation_var=st[3], value_ref=st[4], value_var=st[5])
+        torch.cuda.synchronize()
+        assert (o.cpu().numpy() == exp).all(), st
+    finally:
+        ctx.set_option("hsv_memo", -1)
+
+
+@pytest.mark.parametrize("fmt", ["RGB", "BGR", "ARGB", "BGRx"])
+def test_hsvfilter_direct_kernel_other_formats_and_strides(ctx, fmt):
+    """3-byte pixels and unaligned rows take the one-pixel-per-thread kernel with the same arithmetic"""
+    ctx.set_option("hsv_memo", 0)
+    try:
+        bpp = 3 if fmt in ("RGB", "BGR") else 4
+        for (w, h, pad, off) in ((641, 37, 5, 0), (1280, 64, 0, 0), (333, 17, 3, 1)):
+            stride = ((w * bpp + 3) // 4) * 4 + pad
+            base = synth.frame_noise(fmt, w, h, 0xF00 + w, stride=stride)
+            buf = np.zeros(stride * h + 8, np.uint8)
+            view = buf[off:off + stride * h].reshape(h, stride)
+            view[:] = base
+            exp = orc.hsvfilter(fmt, w, h, base.copy(), hue_shift=200.0, sat_mul=1.2, val_off=-0.05, threads=NT)
+            ctx.hsvfilter_process(fmt, w, h, view, stride, hue_shift=200.0, saturation_mul=1.2, value_off=-0.05)
+            assert (view[:, :w * bpp] == exp[:, :w * bpp]).all(), (fmt, w, h)
+            assert (view[:, w * bpp:] == base[:, w * bpp:]).all()
+    finally:
+        ctx.set_option("hsv_memo", -1)
