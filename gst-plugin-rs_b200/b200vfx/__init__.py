@@ -19,11 +19,13 @@ HEADER = os.path.join(REPO_ROOT, "include", "b200vfx.h")
 FMT = {"RGBx": 0, "xRGB": 1, "BGRx": 2, "xBGR": 3, "RGBA": 4, "ARGB": 5, "BGRA": 6, "ABGR": 7,
        "RGB": 8, "BGR": 9, "RGBA64_LE": 10, "RGBA64_BE": 11, "I420": 12, "A420": 13}
 
+HASH_ALGO = {"mean": 0, "gradient": 1, "vertgradient": 2, "doublegradient": 3, "blockhash": 4}
+
 OK, ERR_INVALID, ERR_CUDA, ERR_NOT_NEGOTIATED, ERR_UNSUPPORTED, ERR_PARSE, ERR_IO = 0, -1, -2, -3, -4, -5, -6
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-SOURCES = ["csrc/b200vfx.cu", "csrc/cube_parser.cpp", "csrc/elements.cpp", "csrc/colordetect_host.cpp"]
+SOURCES = ["csrc/b200vfx.cu", "csrc/cube_parser.cpp", "csrc/elements.cpp", "csrc/colordetect_host.cpp", "csrc/hash_host.cpp"]
 
 
 class B200VfxError(RuntimeError):
@@ -97,6 +99,13 @@ def lib() -> C.CDLL:
         "b200vfx_blockhash_sums_batch": ([vp, ci, ci, ci, ci, C.POINTER(vp), C.POINTER(ci), ci, ci, vp], ci),
         "b200vfx_blockhash_bits": ([vp, ci, ci, ci, ci, vp], None),
         "b200vfx_hash_distance": ([vp, vp, ci], ci),
+        "b200vfx_hash_image": ([vp, ci, ci, ci, ci, vp, ci, vp, C.POINTER(ci)], ci),
+        "b200vfx_blockhash_sums_f32": ([vp, ci, ci, ci, vp, ci, ci, ci, vp], ci),
+        "b200vfx_blockhash_bits_f32": ([vp, ci, ci, ci, ci, vp], None),
+        "b200vfx_luma_resize": ([vp, ci, ci, ci, vp, ci, ci, ci, vp], ci),
+        "b200vfx_hash_resize_dims": ([ci, C.POINTER(ci), C.POINTER(ci)], ci),
+        "b200vfx_debug_resize_taps": ([ci, ci, ci, C.POINTER(ci), f32p, ci], ci),
+        "b200vfx_hash_bits_from_luma": ([ci, vp, ci, ci, vp], ci),
         "b200vfx_colordetect_histogram": ([vp, ci, ci, ci, vp, ci, ci, vp], ci),
         "b200vfx_colordetect_palette": ([vp, ci, vp, ci, C.POINTER(ci)], ci),
         "b200vfx_css_color_similar": ([cu, cu, cu], C.c_char_p),
@@ -283,6 +292,24 @@ class Context:
     def blockhash_sums(self, fmt, width, height, src, stride, sums, hw=8, hh=8):
         self._chk(lib().b200vfx_blockhash_sums(self._h, FMT[fmt], width, height, _ptr(src), stride, hw, hh, _ptr(sums)))
 
+    def hash_image(self, algo, fmt, width, height, src, stride):
+        """-> numpy uint8 array of 0/1 bits (64, or 40 for doublegradient); algo: name or number (videocompare hash-algo)"""
+        import numpy as np
+        bits = np.zeros(64, np.uint8)
+        n = C.c_int()
+        self._chk(lib().b200vfx_hash_image(self._h, HASH_ALGO.get(algo, algo), FMT[fmt], width, height, _ptr(src), stride,
+                                           bits.ctypes.data, C.byref(n)))
+        return bits[:n.value].copy()
+
+    def blockhash_sums_f32(self, fmt, width, height, src, stride, sums, hw=8, hh=8):
+        self._chk(lib().b200vfx_blockhash_sums_f32(self._h, FMT[fmt], width, height, _ptr(src), stride, hw, hh, _ptr(sums)))
+
+    def luma_resize(self, fmt, width, height, src, stride, nw, nh):
+        import numpy as np
+        out = np.zeros((nh, nw), np.uint8)
+        self._chk(lib().b200vfx_luma_resize(self._h, FMT[fmt], width, height, _ptr(src), stride, nw, nh, out.ctypes.data))
+        return out
+
     def device_alloc(self, nbytes) -> int:
         p = lib().b200vfx_device_alloc(self._h, nbytes)
         if not p:
@@ -330,6 +357,30 @@ def blockhash_bits(sums, width, height, hw=8, hh=8):
     bits = np.zeros(hw * hh, np.uint8)
     lib().b200vfx_blockhash_bits(s.ctypes.data, hw, hh, width, height, bits.ctypes.data)
     return bits
+
+
+def blockhash_bits_f32(sums, width, height, hw=8, hh=8):
+    import numpy as np
+    s = np.ascontiguousarray(sums, np.float32)
+    bits = np.zeros(hw * hh, np.uint8)
+    lib().b200vfx_blockhash_bits_f32(s.ctypes.data, hw, hh, width, height, bits.ctypes.data)
+    return bits
+
+
+def hash_bits_from_luma(algo, luma):
+    import numpy as np
+    l = np.ascontiguousarray(luma, np.uint8)
+    bits = np.zeros(96, np.uint8)
+    n = lib().b200vfx_hash_bits_from_luma(HASH_ALGO.get(algo, algo), l.ctypes.data, l.shape[1], l.shape[0], bits.ctypes.data)
+    return bits[:n].copy()
+
+
+def hash_resize_dims(algo):
+    nw, nh = C.c_int(), C.c_int()
+    rc = lib().b200vfx_hash_resize_dims(HASH_ALGO.get(algo, algo), C.byref(nw), C.byref(nh))
+    if rc != 0:
+        raise B200VfxError(rc, "blockhash does not resize")
+    return nw.value, nh.value
 
 
 def hash_distance(a, b) -> int:

@@ -26,6 +26,8 @@
 #include "tile_gather.cuh"
 #include "colordetect.cuh"
 #include "memo_tile.cuh"
+#include "hash_kernels.cuh"
+#include "hash_host.h"
 
 using namespace b200vfx;
 
@@ -92,6 +94,9 @@ struct b200vfx_ctx {
   int cd_cluster = 2;    // colordetect: CTAs per cluster merging their shared-memory histograms (1, 2, 4, 8)
   int peer_timeout_ms = 2000;  // deadline of the cross-GPU waits in the tile-gather kernel
   std::string err;
+  // videocompare: Lanczos3 tap tables per (source length, output length), computed on the host once and kept on the device
+  struct TapsDev { float *taps = nullptr; int2 *meta = nullptr; int max_taps = 0; };
+  std::map<std::pair<int, int>, TapsDev> taps_cache;
 
   // colorlut state (State{lut}, colorlut/imp.rs:50-53)
   bool have_lut = false;
@@ -956,6 +961,7 @@ void b200vfx_ctx_destroy(b200vfx_ctx *c) {
   for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
   if (c->ev_order) cudaEventDestroy(c->ev_order);
+  for (auto &kv : c->taps_cache) { cudaFree(kv.second.taps); cudaFree(kv.second.meta); }
   c->stage_in.release(); c->stage_out.release(); c->stage_sums.release();
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
@@ -1389,29 +1395,184 @@ int b200vfx_blockhash_sums(b200vfx_ctx *c, int fmt, int width, int height, const
 }
 
 void b200vfx_blockhash_bits(const uint32_t *sums, int hw, int hh, int width, int height, uint8_t *bits_out) {
-  // image_hasher 3.1.1 blockhash bit rule (recalled; parity unpinned -- SURVEY A.7): four bands,
-  // band median = element len/2 of the sorted band, bit = v > m || (v == m && m > half).
-  const int n = hw * hh, band = n / 4;
-  if (band <= 0) { for (int i = 0; i < n; i++) bits_out[i] = 0; return; }
+  // image_hasher 3.1.1 alg/blockhash.rs gen_hash! (recalled; parity unpinned -- SURVEY A.7): groups of `hash width * 4`
+  // blocks (4 rows of the hash grid: two groups for the 8x8 hash), group median = element len/2 of the sorted group,
+  // bit = v > m || (v == m && m > 255 * 3 * block_area / 2).
+  const int n = hw * hh, group = hw * 4;
+  if (group <= 0) return;
   const uint32_t half = (uint32_t)(((uint64_t)765 * (uint64_t)(width / hw) * (uint64_t)(height / hh)) / 2);
-  std::vector<uint32_t> tmp((size_t)band);
-  int b0 = 0;
-  for (; b0 + band <= n; b0 += band) {
-    std::copy(sums + b0, sums + b0 + band, tmp.begin());
-    std::nth_element(tmp.begin(), tmp.begin() + band / 2, tmp.end());
-    const uint32_t m = tmp[(size_t)band / 2];
-    for (int i = 0; i < band; i++) {
-      const uint32_t v = sums[b0 + i];
-      bits_out[b0 + i] = (uint8_t)(v > m || (v == m && m > half));
+  std::vector<uint32_t> tmp;
+  for (int g0 = 0; g0 < n; g0 += group) {
+    const int len = std::min(group, n - g0);
+    tmp.assign(sums + g0, sums + g0 + len);
+    std::nth_element(tmp.begin(), tmp.begin() + len / 2, tmp.end());
+    const uint32_t m = tmp[(size_t)len / 2];
+    for (int i = 0; i < len; i++) {
+      const uint32_t v = sums[g0 + i];
+      bits_out[g0 + i] = (uint8_t)(v > m || (v == m && m > half));
     }
   }
-  for (; b0 < n; b0++) bits_out[b0] = 0;
 }
 
 int b200vfx_hash_distance(const uint8_t *a, const uint8_t *b, int nbits) {
   int d = 0;
   for (int i = 0; i < nbits; i++) d += (a[i] != 0) != (b[i] != 0);
   return d;
+}
+
+// ---- videocompare: the other hash algorithms and blockhash on sizes that are not multiples of the hash grid -------------
+namespace {
+// stages a host plane on the device (whole plane, one copy) or passes a device plane through; returns the stream to use
+int stage_plane(b200vfx_ctx *c, const void *src, int stride, size_t row_bytes, int height, const uint8_t **d_src, long *d_stride,
+                cudaStream_t *st) {
+  if (is_device_ptr(src)) { *d_src = (const uint8_t *)src; *d_stride = stride; *st = c->stream(); return 0; }
+  const long ds = (long)((row_bytes + 15) & ~(size_t)15);
+  CU(c, c->stage_in.reserve((size_t)ds * height));
+  *st = c->s_k;
+  if ((size_t)stride == row_bytes && (size_t)ds == row_bytes) CU(c, cudaMemcpyAsync(c->stage_in.p, src, row_bytes * (size_t)height, cudaMemcpyHostToDevice, *st));
+  else CU(c, cudaMemcpy2DAsync(c->stage_in.p, (size_t)ds, src, (size_t)stride, row_bytes, (size_t)height, cudaMemcpyHostToDevice, *st));
+  *d_src = c->stage_in.p; *d_stride = ds;
+  return 0;
+}
+}  // namespace
+
+int b200vfx_luma_resize(b200vfx_ctx *c, int fmt, int width, int height, const void *src, int stride, int nw, int nh, uint8_t *out) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (fmt != B200VFX_FORMAT_RGB && fmt != B200VFX_FORMAT_RGBA) return fail(c, B200VFX_ERR_UNSUPPORTED, "videocompare: format %d is not RGB / RGBA", fmt);
+  if (!out || nw <= 0 || nh <= 0 || nw * nh > 4096) return fail(c, B200VFX_ERR_INVALID, "luma_resize: bad output size");
+  const int bpp = fmt == B200VFX_FORMAT_RGB ? 3 : 4;
+  const size_t row = (size_t)width * bpp;
+  if (int rc = check_frame(c, width, height, src, stride, row, nullptr, 0, 0)) return rc;
+  if (width <= 0 || height <= 0) return fail(c, B200VFX_ERR_INVALID, "luma_resize: empty frame");
+  DeviceGuard g(c->device);
+  const uint8_t *d_src; long d_stride; cudaStream_t st;
+  if (int rc = stage_plane(c, src, stride, row, height, &d_src, &d_stride, &st)) return rc;
+  pdl_admit(false, st, Span{0, 0}, Span{0, 0});
+  const bool same = nw == width && nh == height;
+  // scratch: [tmp f32 width*nh][out nw*nh]
+  const size_t n_tmp = same ? 0 : (size_t)width * nh;
+  const size_t off_out = (n_tmp * 4 + 15) & ~(size_t)15, total = off_out + (size_t)nw * nh;
+  CU(c, c->stage_sums.reserve(total + 64));
+  uint8_t *base = c->stage_sums.p;
+  uint8_t *d_out = base + off_out;
+  if (same) {
+    const int n = width * height;
+    if (bpp == 4) luma_copy_kernel<4><<<ceil_div(n, 256), 256, 0, st>>>(d_src, d_stride, width, height, d_out);
+    else luma_copy_kernel<3><<<ceil_div(n, 256), 256, 0, st>>>(d_src, d_stride, width, height, d_out);
+    c->launches++;
+  } else {
+    auto taps_for = [&](int in_len, int out_len, b200vfx_ctx::TapsDev *out_t) -> int {
+      auto it = c->taps_cache.find({in_len, out_len});
+      if (it == c->taps_cache.end()) {
+        if (c->taps_cache.size() >= 16) {   // bounded: a caps change brings new sizes
+          CU(c, cudaDeviceSynchronize());
+          for (auto &kv : c->taps_cache) { cudaFree(kv.second.taps); cudaFree(kv.second.meta); }
+          c->taps_cache.clear();
+        }
+        const ResizeTaps t = make_resize_taps(in_len, out_len);
+        std::vector<int2> meta((size_t)out_len);
+        for (int i = 0; i < out_len; i++) meta[(size_t)i] = make_int2(t.left[(size_t)i], t.count[(size_t)i]);
+        b200vfx_ctx::TapsDev d;
+        d.max_taps = t.max_taps;
+        CU(c, cudaMalloc(&d.taps, t.taps.size() * sizeof(float)));
+        CU(c, cudaMalloc(&d.meta, meta.size() * sizeof(int2)));
+        CU(c, cudaMemcpy(d.taps, t.taps.data(), t.taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(c, cudaMemcpy(d.meta, meta.data(), meta.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        it = c->taps_cache.emplace(std::make_pair(in_len, out_len), d).first;
+      }
+      *out_t = it->second;
+      return 0;
+    };
+    b200vfx_ctx::TapsDev tv, th;
+    if (int rc = taps_for(height, nh, &tv)) return rc;
+    if (int rc = taps_for(width, nw, &th)) return rc;
+    float *d_tmp = (float *)base;
+    dim3 grid((unsigned)ceil_div(width, 128), (unsigned)nh);
+    const bool al = bpp == 4 && aligned(d_src, d_stride, 4);
+    if (al) luma_vresize_kernel<4><<<grid, 128, 0, st>>>(d_src, d_stride, width, tv.taps, tv.meta, tv.max_taps, d_tmp);
+    else if (bpp == 4) luma_vresize_bytes_kernel<4><<<grid, 128, 0, st>>>(d_src, d_stride, width, tv.taps, tv.meta, tv.max_taps, d_tmp);
+    else luma_vresize_kernel<3><<<grid, 128, 0, st>>>(d_src, d_stride, width, tv.taps, tv.meta, tv.max_taps, d_tmp);
+    luma_hresize_kernel<<<ceil_div(nw * nh, 32), 32, 0, st>>>(d_tmp, width, nw, nh, th.taps, th.meta, th.max_taps, d_out);
+    c->launches += 2;
+  }
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(out, d_out, (size_t)nw * nh, cudaMemcpyDefault, st));
+  CU(c, cudaStreamSynchronize(st));
+  pdl_forget(st);
+  return 0;
+}
+
+int b200vfx_blockhash_sums_f32(b200vfx_ctx *c, int fmt, int width, int height, const void *src, int stride, int hw, int hh, float *sums) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (fmt != B200VFX_FORMAT_RGB && fmt != B200VFX_FORMAT_RGBA) return fail(c, B200VFX_ERR_UNSUPPORTED, "videocompare: format %d is not RGB / RGBA", fmt);
+  if (hw <= 0 || hh <= 0 || hw * hh > 4096 || !sums) return fail(c, B200VFX_ERR_INVALID, "blockhash: bad hash size");
+  const int bpp = fmt == B200VFX_FORMAT_RGB ? 3 : 4;
+  const size_t row = (size_t)width * bpp;
+  if (int rc = check_frame(c, width, height, src, stride, row, nullptr, 0, 0)) return rc;
+  // block sizes of at most one pixel make the reference's `x + 1. % block_width` weights genuinely fractional: such
+  // frames (narrower or lower than the hash grid) are not served
+  if (width <= hw || height <= hh)
+    return fail(c, B200VFX_ERR_UNSUPPORTED, "blockhash: a %dx%d frame is not larger than the %dx%d hash grid", width, height, hw, hh);
+  DeviceGuard g(c->device);
+  const uint8_t *d_src; long d_stride; cudaStream_t st;
+  if (int rc = stage_plane(c, src, stride, row, height, &d_src, &d_stride, &st)) return rc;
+  pdl_admit(false, st, Span{0, 0}, Span{0, 0});
+  const float bwf = (float)width / (float)hw, bhf = (float)height / (float)hh;   // one IEEE division each, as the reference
+  const int n = hw * hh;
+  CU(c, c->stage_sums.reserve((size_t)n * 4));
+  std::vector<float> host((size_t)n);
+  const double max_block = (std::ceil((double)bwf) + 1.0) * (std::ceil((double)bhf) + 1.0) * 765.0;
+  if (max_block < 16777216.0) {   // every partial sum is an integer below 2^24: f32 accumulation is exact, any order
+    uint32_t *d_u = (uint32_t *)c->stage_sums.p;
+    CU(c, cudaMemsetAsync(d_u, 0, (size_t)n * 4, st));
+    const int rows_per_cta = std::max(1, ceil_div(height, c->sm_count * 4));
+    const unsigned grid = (unsigned)ceil_div(height, rows_per_cta);
+    if (bpp == 4) blockhash_frac_kernel<4><<<grid, 256, (size_t)n * 4, st>>>(d_src, d_stride, width, height, hw, hh, bwf, bhf, rows_per_cta, d_u);
+    else blockhash_frac_kernel<3><<<grid, 256, (size_t)n * 4, st>>>(d_src, d_stride, width, height, hw, hh, bwf, bhf, rows_per_cta, d_u);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    std::vector<uint32_t> hu((size_t)n);
+    CU(c, cudaMemcpyAsync(hu.data(), d_u, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    for (int i = 0; i < n; i++) host[(size_t)i] = (float)hu[(size_t)i];
+  } else {                        // sums leave the exact range: replay the raster-order chain per block
+    float *d_f = (float *)c->stage_sums.p;
+    if (bpp == 4) blockhash_seq_kernel<4><<<(unsigned)n, 32, 0, st>>>(d_src, d_stride, width, height, hw, hh, bwf, bhf, d_f);
+    else blockhash_seq_kernel<3><<<(unsigned)n, 32, 0, st>>>(d_src, d_stride, width, height, hw, hh, bwf, bhf, d_f);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(host.data(), d_f, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+  }
+  pdl_forget(st);
+  if (is_device_ptr(sums)) CU(c, cudaMemcpy(sums, host.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+  else std::memcpy(sums, host.data(), (size_t)n * 4);
+  return 0;
+}
+
+int b200vfx_hash_image(b200vfx_ctx *c, int algo, int fmt, int width, int height, const void *src, int stride, uint8_t *bits_out,
+                       int *n_bits) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (!bits_out || !n_bits) return fail(c, B200VFX_ERR_INVALID, "hash_image: null output");
+  if (algo == B200VFX_HASH_BLOCKHASH) {
+    if (width > 0 && height > 0 && width % 8 == 0 && height % 8 == 0) {   // integer fast path
+      uint32_t sums[64];
+      if (int rc = b200vfx_blockhash_sums(c, fmt, width, height, src, stride, 8, 8, sums)) return rc;
+      b200vfx_blockhash_bits(sums, 8, 8, width, height, bits_out);
+    } else {
+      float sums[64];
+      if (int rc = b200vfx_blockhash_sums_f32(c, fmt, width, height, src, stride, 8, 8, sums)) return rc;
+      b200vfx_blockhash_bits_f32(sums, 8, 8, width, height, bits_out);
+    }
+    *n_bits = 64;
+    return 0;
+  }
+  int nw = 0, nh = 0;
+  if (b200vfx_hash_resize_dims(algo, &nw, &nh)) return fail(c, B200VFX_ERR_INVALID, "unknown hash algorithm %d", algo);
+  uint8_t luma[96];
+  if (int rc = b200vfx_luma_resize(c, fmt, width, height, src, stride, nw, nh, luma)) return rc;
+  *n_bits = b200vfx_hash_bits_from_luma(algo, luma, nw, nh, bits_out);
+  return 0;
 }
 
 // ---- colordetect ----------------------------------------------------------------------------------

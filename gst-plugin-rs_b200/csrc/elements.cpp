@@ -268,14 +268,12 @@ struct VideoCompare : b200gst_element {  // video/videofx/src/videocompare/imp.r
     pads.erase(std::find(pads.begin(), pads.end(), id));
     return 0;
   }
-  int hash(const b200gst_video_frame &fr, std::vector<uint8_t> &bits) {
-    if ((int)values["hash-algo"].d != 4)
-      return fail(B200GST_FLOW_ERROR, "hash-algo: only blockhash is implemented on the B200 path (SURVEY 8(f) row 3)");
-    uint32_t sums[64];
-    if (b200vfx_blockhash_sums(ctx, fr.format, fr.width, fr.height, fr.data[0], fr.stride[0], 8, 8, sums) != 0)
+  int hash(const b200gst_video_frame &fr, std::vector<uint8_t> &bits) {   // HasherEngine::hash_image, hashed_image.rs:24-64
+    bits.assign(B200VFX_HASH_MAX_BITS, 0);
+    int n = 0;
+    if (b200vfx_hash_image(ctx, (int)values["hash-algo"].d, fr.format, fr.width, fr.height, fr.data[0], fr.stride[0], bits.data(), &n) != 0)
       return ctx_error(B200GST_FLOW_ERROR);
-    bits.assign(64, 0);
-    b200vfx_blockhash_bits(sums, 8, 8, fr.width, fr.height, bits.data());
+    bits.resize((size_t)n);
     return 0;
   }
   int aggregate(const b200gst_video_frame *frames, const int *pad_ids, int n, int64_t running_time, b200gst_video_frame *out) {
@@ -311,7 +309,8 @@ struct VideoCompare : b200gst_element {  // video/videofx/src/videocompare/imp.r
     std::vector<std::pair<int, double>> distances;
     bool same_fmt = true;
     for (auto &o : others) same_fmt = same_fmt && o.second->format == ref->format;
-    if ((int)values["hash-algo"].d == 4 && same_fmt && !others.empty() && others.size() + 1 <= B200VFX_BLOCKHASH_MAX_FRAMES) {
+    if ((int)values["hash-algo"].d == 4 && same_fmt && !others.empty() && others.size() + 1 <= B200VFX_BLOCKHASH_MAX_FRAMES &&
+        ref->width % 8 == 0 && ref->height % 8 == 0) {
       // one launch hashes the reference frame and every other pad's frame
       const int nf = (int)others.size() + 1;
       const void *srcs[B200VFX_BLOCKHASH_MAX_FRAMES];
@@ -332,7 +331,7 @@ struct VideoCompare : b200gst_element {  // video/videofx/src/videocompare/imp.r
       if (int rc = hash(*ref, ref_bits)) return rc;
       for (auto &o : others) {
         if (int rc = hash(*o.second, bits)) return rc;
-        distances.push_back({o.first, (double)b200vfx_hash_distance(ref_bits.data(), bits.data(), 64)});
+        distances.push_back({o.first, (double)b200vfx_hash_distance(ref_bits.data(), bits.data(), (int)std::min(ref_bits.size(), bits.size()))});
       }
     }
     const double thr = values["max-dist-threshold"].d;

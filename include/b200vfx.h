@@ -172,10 +172,24 @@ int b200vfx_roundmask_generate(b200vfx_ctx *ctx, int width, int height, int stri
                                unsigned border_radius_px, void *a8_out);
 
 /* ---- videocompare -------------------------------------------------------
- * HasherEngine::hash_image for HashAlg::Blockhash (video/videofx/src/videocompare/
- * hashed_image.rs:24-64,110-130 -> image_hasher 3.1.1): the hw*hh u32 block sums of
- * (A==0 ? 765 : R+G+B).  fmt: RGB or RGBA.  Requires width%hw==0 && height%hh==0
- * (image_hasher's integer fast path).  `sums` may be a host or device pointer. */
+ * HasherEngine::hash_image (video/videofx/src/videocompare/hashed_image.rs:24-64,110-130 -> image_hasher 3.1.1,
+ * image 0.25.10: third-party crates, restated as recalled -- bit patterns are parity-unpinned; the reference's tests pin
+ * only `distance 0 for identical frames` and `> 0 for snow vs red`, tests/videocompare.rs:57-139).
+ * All five values of the `hash-algo` property (GstVideoCompareHashAlgorithm, videocompare/mod.rs:57-92): */
+typedef enum {
+  B200VFX_HASH_MEAN = 0,
+  B200VFX_HASH_GRADIENT = 1,
+  B200VFX_HASH_VERTGRADIENT = 2,
+  B200VFX_HASH_DOUBLEGRADIENT = 3,
+  B200VFX_HASH_BLOCKHASH = 4
+} b200vfx_hash_algo;
+#define B200VFX_HASH_MAX_BITS 64
+/* one frame -> hash bits (bytes of 0/1; 64 bits, 40 for doublegradient), any frame size larger than 8x8.
+ * fmt: RGB or RGBA; src host or device.  Synchronous. */
+int b200vfx_hash_image(b200vfx_ctx *ctx, int algo, int fmt, int width, int height, const void *src, int stride,
+                       uint8_t *bits_out, int *n_bits);
+/* HashAlg::Blockhash, integer fast path (width % hw == 0 && height % hh == 0): the hw*hh u32 block sums of
+ * (A==0 ? 765 : R+G+B).  `sums` may be a host or device pointer. */
 int b200vfx_blockhash_sums(b200vfx_ctx *ctx, int fmt, int width, int height, const void *src,
                            int stride, int hw, int hh, uint32_t *sums);
 /* VideoCompare::aggregate_frames (videocompare/imp.rs:297-353) hashes the reference pad's frame and then every other
@@ -184,10 +198,22 @@ int b200vfx_blockhash_sums(b200vfx_ctx *ctx, int fmt, int width, int height, con
 #define B200VFX_BLOCKHASH_MAX_FRAMES 8
 int b200vfx_blockhash_sums_batch(b200vfx_ctx *ctx, int fmt, int width, int height, int n_frames,
                                  const void *const *srcs, const int *strides, int hw, int hh, uint32_t *sums);
-/* median/bit rule + Hamming distance (host side, tiny): bits_out hw*hh bytes of 0/1 */
+/* HashAlg::Blockhash for every other frame size (blockhash_slow): f32 block sums, block index = floor(x / (W/hw)) with
+ * the reference's f32 division, accumulated in raster order (exact integers below 2^24; a sequential kernel beyond). */
+int b200vfx_blockhash_sums_f32(b200vfx_ctx *ctx, int fmt, int width, int height, const void *src, int stride, int hw,
+                               int hh, float *sums);
+/* median/bit rules (gen_hash!) + Hamming distance (host side, tiny): bits_out hw*hh bytes of 0/1 */
 void b200vfx_blockhash_bits(const uint32_t *sums, int hw, int hh, int width, int height,
                             uint8_t *bits_out);
+void b200vfx_blockhash_bits_f32(const float *sums, int hw, int hh, int width, int height, uint8_t *bits_out);
 int b200vfx_hash_distance(const uint8_t *bits_a, const uint8_t *bits_b, int nbits);
+/* Mean / Gradient / VertGradient / DoubleGradient: image::imageops::grayscale + resize(FilterType::Lanczos3) of the frame
+ * to nw x nh luma bytes (row-major) on the GPU, then the bit rule on the host.
+ * b200vfx_hash_resize_dims: HashAlg::resize_dimensions for the 8x8 hash -> (8,8) (9,8) (8,9) (5,5). */
+int b200vfx_luma_resize(b200vfx_ctx *ctx, int fmt, int width, int height, const void *src, int stride, int nw, int nh,
+                        uint8_t *out);
+int b200vfx_hash_resize_dims(int algo, int *nw, int *nh);
+int b200vfx_hash_bits_from_luma(int algo, const uint8_t *luma, int nw, int nh, uint8_t *bits);
 
 /* ---- colordetect --------------------------------------
  * ColorDetect::detect_color (video/videofx/src/colordetect/imp.rs:57-86) = color_thief::get_palette(plane 0,
@@ -245,6 +271,9 @@ int b200vfx_colorlut_process_tile_gather(b200vfx_ctx *ctx, int fmt, int width, i
 int b200vfx_debug_pdl_admit(void *stream_key, uintptr_t src_lo, uintptr_t src_hi, uintptr_t dst_lo, uintptr_t dst_hi,
                             int want_pdl, long long threads, int lingers);
 void b200vfx_debug_pdl_reset(void *stream_key);
+/* the normalised Lanczos3 tap weights image::imageops::resize uses for output sample `out` when in_len samples become
+ * out_len (host computation behind b200vfx_luma_resize); returns the number of taps written to ws, < 0 on error */
+int b200vfx_debug_resize_taps(int in_len, int out_len, int out, int *left, float *ws, int cap);
 
 #ifdef __cplusplus
 }

@@ -612,20 +612,21 @@ static int cmp_u32(const void *a, const void *b) {
 }
 void orc_blockhash_bits(const uint32_t *sums, int hw, int hh, int width, int height,
                         uint8_t *bits_out) {
-  /* recalled from image_hasher 3.1.1 alg/blockhash.rs (parity unpinned):
-   * 4 horizontal bands; per band m = sorted[len/2];
-   * bit = block > m || (block == m && m > half_block_value),
-   * half_block_value = 765 * bw * bh / 2. */
-  const int n = hw * hh, band = n / 4;
+  /* recalled from image_hasher 3.1.1 alg/blockhash.rs gen_hash! (parity unpinned):
+   * groups of `hash width * 4` blocks (= 4 rows of the hash grid: two groups for the 8x8 hash); per group
+   * m = sorted[len/2]; bit = block > m || (block == m && m > cmp_factor),
+   * cmp_factor = 255 * 3 * bw * bh / 2 (integer). */
+  const int n = hw * hh, group = hw * 4;
   const uint32_t half = (uint32_t)(((uint64_t)765 * (uint64_t)(width / hw) * (uint64_t)(height / hh)) / 2);
-  uint32_t *scratch = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(band > 0 ? band : 1));
-  for (int b0 = 0; band > 0 && b0 + band <= n; b0 += band) {
-    memcpy(scratch, sums + b0, sizeof(uint32_t) * (size_t)band);
-    qsort(scratch, (size_t)band, sizeof(uint32_t), cmp_u32);
-    uint32_t m = scratch[band / 2];
-    for (int i = 0; i < band; i++) {
-      uint32_t v = sums[b0 + i];
-      bits_out[b0 + i] = (uint8_t)(v > m || (v == m && m > half));
+  uint32_t *scratch = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(group > 0 ? group : 1));
+  for (int g0 = 0; group > 0 && g0 < n; g0 += group) {
+    const int len = (n - g0 < group) ? n - g0 : group;
+    memcpy(scratch, sums + g0, sizeof(uint32_t) * (size_t)len);
+    qsort(scratch, (size_t)len, sizeof(uint32_t), cmp_u32);
+    uint32_t m = scratch[len / 2];
+    for (int i = 0; i < len; i++) {
+      uint32_t v = sums[g0 + i];
+      bits_out[g0 + i] = (uint8_t)(v > m || (v == m && m > half));
     }
   }
   free(scratch);

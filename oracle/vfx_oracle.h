@@ -88,6 +88,16 @@ void orc_blockhash_bits(const uint32_t *sums, int hw, int hh, int width,
                         int height, uint8_t *bits_out);
 int orc_hamming(const uint8_t *a, const uint8_t *b, int n);
 
+/* ---- videocompare, the other HashAlg values and the non-divisible blockhash path (vfx_oracle_hash.c; third-party
+ * image_hasher 3.1.1 + image 0.25.10 restated as recalled: PARITY UNPINNED) ----------------------------------------
+ * algo: 0 mean, 1 gradient, 2 vertgradient, 3 doublegradient.  fmt: ORC_FMT_RGB / ORC_FMT_RGBA. */
+int orc_resize_taps(int in_len, int out_len, int out, int *left_out, float *ws, int cap);
+int orc_luma_resize(int fmt, int width, int height, const uint8_t *src, int stride, int nw, int nh, uint8_t *out);
+void orc_hash_resize_dims(int algo, int *nw, int *nh);
+int orc_hash_bits_from_luma(int algo, const uint8_t *luma, int nw, int nh, uint8_t *bits);
+int orc_blockhash_sums_f32(int fmt, int width, int height, const uint8_t *src, int stride, int hw, int hh, float *blocks);
+void orc_blockhash_bits_f32(const float *blocks, int hw, int hh, int width, int height, uint8_t *bits_out);
+
 /* ---- roundedcorners mask (video/videofx/src/border/imp.rs:57-180) ---------
  * A8 plane, `stride` bytes per row, rows [0,height); rows up to
  * round_up_2(height) are zero-filled like the reference's pre-zeroed memory.

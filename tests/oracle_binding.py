@@ -20,8 +20,8 @@ FMT = {"RGBx": 0, "xRGB": 1, "BGRx": 2, "xBGR": 3, "RGBA": 4, "ARGB": 5, "BGRA":
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(ORACLE_DIR, "vfx_oracle.c")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("vfx_oracle.c", "vfx_oracle_hash.c", "vfx_oracle.h")]
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
     return LIB_PATH
 
@@ -49,6 +49,13 @@ def lib() -> C.CDLL:
                                             u32p, C.c_int]
         _lib.orc_blockhash_bits.argtypes = [u32p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         _lib.orc_hamming.argtypes = [u8p, u8p, C.c_int]
+        _lib.orc_luma_resize.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.orc_hash_resize_dims.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        _lib.orc_hash_resize_dims.restype = None
+        _lib.orc_hash_bits_from_luma.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        _lib.orc_blockhash_sums_f32.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.orc_blockhash_bits_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.orc_blockhash_bits_f32.restype = None
         _lib.orc_roundmask.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p]
         _lib.orc_colordetect_histogram.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib.orc_colordetect_palette.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -205,3 +212,44 @@ def colordetect_palette(hist: np.ndarray, max_colors=2):
 
 def css_similar(r, g, b) -> str:
     return lib().orc_css_similar(int(r), int(g), int(b)).decode()
+
+
+HASH_ALGO = {"mean": 0, "gradient": 1, "vertgradient": 2, "doublegradient": 3, "blockhash": 4}
+
+
+def luma_resize(fmt, width, height, frame, nw, nh) -> np.ndarray:
+    """image::imageops::grayscale + resize(Lanczos3) as recalled (vfx_oracle_hash.c): nh x nw luma bytes"""
+    f = np.ascontiguousarray(frame)
+    out = np.zeros((nh, nw), np.uint8)
+    rc = lib().orc_luma_resize(FMT[fmt], width, height, f.ctypes.data, f.shape[1], nw, nh, out.ctypes.data)
+    assert rc == 0, rc
+    return out
+
+
+def hash_image(algo, fmt, width, height, frame) -> np.ndarray:
+    """HasherEngine::hash_image for any of the five algorithms and any frame size: array of 0/1 bits"""
+    a = HASH_ALGO.get(algo, algo)
+    f = np.ascontiguousarray(frame)
+    if a == 4:
+        if width % 8 == 0 and height % 8 == 0:
+            return blockhash_bits(blockhash_sums(fmt, width, height, f), width, height)
+        sums = np.zeros(64, np.float32)
+        rc = lib().orc_blockhash_sums_f32(FMT[fmt], width, height, f.ctypes.data, f.shape[1], 8, 8, sums.ctypes.data)
+        assert rc == 0, rc
+        bits = np.zeros(64, np.uint8)
+        lib().orc_blockhash_bits_f32(sums.ctypes.data, 8, 8, width, height, bits.ctypes.data)
+        return bits
+    nw, nh = C.c_int(), C.c_int()
+    lib().orc_hash_resize_dims(a, C.byref(nw), C.byref(nh))
+    luma = luma_resize(fmt, width, height, f, nw.value, nh.value)
+    bits = np.zeros(96, np.uint8)
+    n = lib().orc_hash_bits_from_luma(a, luma.ctypes.data, nw.value, nh.value, bits.ctypes.data)
+    return bits[:n].copy()
+
+
+def blockhash_sums_f32(fmt, width, height, frame) -> np.ndarray:
+    f = np.ascontiguousarray(frame)
+    sums = np.zeros(64, np.float32)
+    rc = lib().orc_blockhash_sums_f32(FMT[fmt], width, height, f.ctypes.data, f.shape[1], 8, 8, sums.ctypes.data)
+    assert rc == 0, rc
+    return sums

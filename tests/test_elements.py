@@ -191,8 +191,21 @@ def test_videocompare_red_vs_red_posts_message_and_snow_does_not():
     small = synth.frame_solid("RGBA", 160, 120)
     assert vc.aggregate_frames([fr(red), gst.frame("RGBA", 160, 120, [small], [640])], [ref, other]) == gst.FLOW_NOT_NEGOTIATED
     assert vc.aggregate_frames([fr(red2)], [other]) == gst.FLOW_OK and vc.pop_message() is None   # reference pad has no buffer
-    vc.set_property("hash-algo", "mean")
-    assert vc.aggregate_frames([fr(red), fr(red2)], [ref, other]) == gst.FLOW_ERROR
+    # every value of hash-algo (GstVideoCompareHashAlgorithm, videocompare/mod.rs:57-92) hashes: identical frames -> distance 0
+    # -> message; snow vs red -> distance > 0 -> none at threshold 0.  Also on a size that is not a multiple of 8.
+    vc.set_property("max-dist-threshold", 0)
+    for algo in ("mean", "gradient", "vertgradient", "doublegradient", "blockhash"):
+        vc.set_property("hash-algo", algo)
+        assert vc.aggregate_frames([fr(red), fr(red2)], [ref, other]) == gst.FLOW_OK, algo
+        m = vc.pop_message()
+        assert m is not None and "distance\\=(double)0" in m, algo
+        assert vc.aggregate_frames([fr(red), fr(snow)], [ref, other]) == gst.FLOW_OK
+        assert vc.pop_message() is None, algo
+        w2, h2 = 333, 241
+        r2, s2 = synth.frame_solid("RGBA", w2, h2), synth.frame_noise("RGBA", w2, h2, 9)
+        f2 = lambda a: gst.frame("RGBA", w2, h2, [a], [4 * w2])
+        assert vc.aggregate_frames([f2(r2), f2(r2.copy())], [ref, other]) == gst.FLOW_OK and vc.pop_message() is not None, algo
+        assert vc.aggregate_frames([f2(r2), f2(s2)], [ref, other]) == gst.FLOW_OK and vc.pop_message() is None, algo
     vc.stop()
 
 
