@@ -38,6 +38,17 @@ METRIC = "colorlut_4k_rgba_frames_per_sec"
 WORKLOAD = "colorlut 33^3 .cube on 3840x2160 RGBA synthetic stream (frames A ramps / B noise alternating)"
 
 
+def workload_config(gop, n_gpus, mode):
+    """the `config` object of the JSON line -- IDENTICAL for the GPU arm and the reference arm (the driver compares them)"""
+    return {"workload": WORKLOAD, "lut": "33^3 mix .cube", "frame": "3840x2160 RGBA stride 15360",
+            "frames_per_step": gop * n_gpus, "ring_frames": RING,
+            "l2": "inputs larger than L2 (%d in + %d out frames = %d MB ring, no flush)" % (RING, RING, 2 * RING * FRAME_BYTES // 1000000),
+            "colorlut_mode": "memo" if mode == 0 else "direct",
+            "sharding": "row tiles, rank r owns rows [r*H/N,(r+1)*H/N) of every frame, tiles of N consecutive frames stacked per launch; "
+                        "no data-path collective: `value` at N > 1 is REPLICA (weak) scaling of the per-GPU kernel, the tiled-frame "
+                        "reassembly numbers are under roofline.multi_gpu"}
+
+
 def host_threads():
     """threads the CPU arm may use: the cgroup CPU quota of this container (cpu.max), not the host's core count --
     oversubscribing the quota makes the OpenMP loop slower (measured: 128 threads 10 fps, 32 threads 47 fps)"""
@@ -57,8 +68,12 @@ def ncu_traffic_bytes(mode):
     if mode != 0:
         return None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return int(json.load(f)["dominant_kernel"]["mix_ramps_noise_cold"])
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            p = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(p):
+                with open(p) as f:
+                    return int(json.load(f)["dominant_kernel"]["mix_ramps_noise_cold"])
+        return None
     except Exception:
         return None
 
@@ -171,7 +186,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "lut": "33^3 mix .cube", "frame": "3840x2160 RGBA", "step": "1 frame per step"},
+            "config": workload_config(args.gop, args.gpus, args.mode),
+            "sample_frames_per_step": 1,   # a step of this arm is a bounded sample of the workload: one full 4K frame (A/B alternating)
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": "%d full 4K frames, C restatement of colorlut/imp.rs:267-294 row-parallel over %d threads "
                                        "(the Rust reference cannot be built here)" % (args.steps, threads)},
@@ -224,6 +240,95 @@ def emit(line):
     else:
         sys.stdout.flush()
         os.write(_JSON_FD, data)
+
+
+def gpu_numa_node(index):
+    """NUMA node of GPU `index` (sysfs through its PCI bus id), -1 if unknown"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        for cand in (bus.lower(), bus.lower()[4:]):
+            path = "/sys/bus/pci/devices/%s/numa_node" % cand
+            if os.path.exists(path):
+                return int(open(path).read().strip())
+    except Exception:
+        pass
+    return -1
+
+
+def config5_leg(torch, dist, np, synth, b200vfx, rank, N, local):
+    """BASELINE config 5 in front of the driver: colorlut 65^3 on ONE 7680x4320 RGBA frame row-tiled over the N ranks and
+    reassembled on every GPU, two ways -- (a) tile kernel + in-place ncclAllGather, (b) the fused kernel that stores its
+    results into every rank's frame buffer over NVLink (b200vfx_colorlut_process_tile_gather).  Parity: rank 0's
+    reassembled frame of the fused path == CPU oracle, outside the timed loops.  Device time per frame, max over ranks."""
+    import oracle_binding as orc
+    from b200vfx import sharding
+    W, H = 7680, 4320
+    rows = H // N
+    r0 = rank * rows
+    text = synth.cube_text_3d(65, "mix")
+    ctx = b200vfx.Context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.set_option("peer_timeout_ms", 5000)
+    k, s_, v, sc, of = b200vfx.cube_parse(text)
+    ctx.colorlut_set_lut(k, s_, v, sc, of)
+    frames = [synth.frame_natural("RGBA", W, H, 0x5EED0005), synth.frame_noise("RGBA", W, H, 0x5EED0005)]
+    tiles = [torch.from_numpy(np.ascontiguousarray(f[r0:r0 + rows])).cuda() for f in frames]
+    pf = sharding.PeerFrames(ctx, dist, H, 4 * W, nbuf=2)
+    res = {"workload": "colorlut 65^3 on 7680x4320 RGBA, %d rows per GPU, whole frame reassembled on every GPU" % rows,
+           "frame_bytes": 4 * W * H, "received_bytes_per_gpu": 4 * W * rows * (N - 1)}
+    # ---- parity (one frame, both contents), rank 0 checks the whole reassembled frame against the oracle
+    parity = True
+    for i in range(2):
+        kbuf = pf.process(W, tiles[i], 4 * W)
+        got = torch.as_tensor(pf.frame(kbuf), device="cuda").clone()
+        torch.cuda.synchronize()
+        if rank == 0:
+            cube = orc.cube_parse(text)
+            exp = orc.colorlut_apply(cube, "RGBA", W, H, frames[i], threads=host_threads())
+            parity = parity and bool((got.cpu().numpy() == exp).all())
+    res["fused_timeouts"] = int(pf.status())
+    flag = torch.tensor([1 if parity else 0], dtype=torch.int32, device="cuda")
+    dist.broadcast(flag, 0)
+    res["parity"] = bool(flag.item()) and res["fused_timeouts"] == 0
+    res["parity_checked"] = "rank 0: reassembled frame of the fused path == CPU oracle, 2 frames (natural, noise)"
+    # ---- timing
+    full = torch.empty((H, 4 * W), dtype=torch.uint8, device="cuda")
+
+    def k_only(i):
+        ctx.colorlut_process("RGBA", W, rows, tiles[i % 2], 4 * W, full[r0:r0 + rows], 4 * W)
+
+    def k_nccl(i):
+        slot = full[r0:r0 + rows]
+        ctx.colorlut_process("RGBA", W, rows, tiles[i % 2], 4 * W, slot, 4 * W)
+        dist.all_gather_into_tensor(full.view(-1), slot.reshape(-1))
+
+    def k_fused(i):
+        pf.process(W, tiles[i % 2], 4 * W)
+
+    for name, fn in (("tile_kernel_us", k_only), ("kernel_plus_nccl_us", k_nccl), ("fused_tile_gather_us", k_fused)):
+        for i in range(6):
+            fn(i)
+        torch.cuda.synchronize(); dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(40):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([a.elapsed_time(b) * 1e3 / 40], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        res[name] = float(tt.item())
+    res["fused_timeouts"] = int(pf.status())
+    for name in ("kernel_plus_nccl", "fused_tile_gather"):
+        res[name + "_rx_GBps_per_gpu"] = res["received_bytes_per_gpu"] / (res[name + "_us"] * 1e-6) / 1e9
+    res["nvlink_reference"] = "measured peer copy 770 GB/s per direction per GPU (B200_PROFILING.md); 900 nominal"
+    res["fused_frac_of_770"] = res["fused_tile_gather_rx_GBps_per_gpu"] / 770.0
+    pf.close()
+    ctx.close()
+    return res
 
 
 # --------------------------------------------------------------------------------------------------
@@ -325,13 +430,13 @@ def main():
     breakdown = {}
     if N == 1:
         # "natural" (ramps +- 3 of sensor-like noise, not part of `value`) is reported next to the two contents the workload names
-        nat_in = [torch.from_numpy(synth.frame_natural("RGBA", W4K, H4K, 0x5EED0020 + i, amp=3)).cuda() for i in range(4)]
-        nat_out = [torch.empty_like(t_) for t_ in nat_in]
-        for name in ("ramps", "noise", "natural"):
+        for name in ("ramps", "noise", "natural", "natural_pm8"):
             idx = [i for i in range(RING) if kinds[i] == name]
-            if name == "natural":
+            if name.startswith("natural"):
+                amp = 3 if name == "natural" else 8
+                nat_in = [torch.from_numpy(synth.frame_natural("RGBA", W4K, H4K, 0x5EED0020 + 16 * amp + i, amp=amp)).cuda() for i in range(4)]
                 base_n = len(d_in)
-                d_in.extend(nat_in); d_out.extend(nat_out)
+                d_in.extend(nat_in); d_out.extend([torch.empty_like(t_) for t_ in nat_in])
                 idx = list(range(base_n, base_n + 4))
             def run_kind():
                 for i in range(args.gop):
@@ -367,6 +472,7 @@ def main():
             gop_host()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        dt_local = dt
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -386,6 +492,8 @@ def main():
             for _ in range(3):
                 both()
             torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()          # all ranks copy at the same time: the ceiling under the same contention as e2e
             tp = time.perf_counter()
             for _ in range(20):
                 both()
@@ -394,12 +502,27 @@ def main():
             pcie = {"frames_per_s_ceiling_per_gpu": 1.0 / tp, "GBps_each_way": FRAME_BYTES / tp / 1e9}
         except Exception:
             pcie = None
+        per_rank = None
+        if dist is not None:
+            mine = {"rank": rank, "gpu": local, "gpu_numa_node": gpu_numa_node(local), "cpus_bound": len(os.sched_getaffinity(0)),
+                    "frames_per_s": e2e_gop * e2e_steps / dt_local, "pcie_concurrent_memcpy": pcie}
+            per_rank = [None] * N
+            dist.all_gather_object(per_rank, mine)
         e2e = {"value": e2e_gop * e2e_steps * N / dt, "unit": "frames/s",
                "h2d_bytes_per_step": FRAME_BYTES * e2e_gop, "d2h_bytes_per_step": FRAME_BYTES * e2e_gop,
                "frames_per_step": e2e_gop, "steps": e2e_steps, "ms_per_frame": 1e3 * dt / (e2e_gop * e2e_steps),
                "host_buffers": "pinned", "checksum": chk, "pcie_concurrent_memcpy": pcie,
                "transfer": "zero-copy: the kernel bulk-loads (cp.async.bulk) the frame from pinned host memory over PCIe and "
                            "bulk-stores the result back; h2d/d2h bytes cross PCIe inside the timed call"}
+        if per_rank is not None and all(p and p.get("pcie_concurrent_memcpy") for p in per_rank):
+            # the host-side ceiling of this leg, measured in the same run: every rank's pinned copies in both directions at
+            # once, all ranks simultaneously (each rank measured it while the others did the same) -- e2e cannot beat the sum
+            ceil = sum(p["pcie_concurrent_memcpy"]["frames_per_s_ceiling_per_gpu"] for p in per_rank)
+            e2e["host_ceiling"] = {"frames_per_s": ceil, "GBps_each_way_all_ranks": ceil * FRAME_BYTES / 1e9,
+                                   "e2e_frac_of_ceiling": e2e["value"] / ceil if ceil > 0 else None,
+                                   "note": "sum over ranks of plain pinned cudaMemcpyAsync H2D+D2H run concurrently on all ranks: the "
+                                           "host DMA path (one root complex / NUMA node shared by the GPUs), not a kernel, bounds e2e at N > 1"}
+            e2e["per_rank"] = per_rank
 
     # ---- optional all-gather reassembly (config 5 style), reported separately ---------------------
     allgather = None
@@ -455,6 +578,13 @@ def main():
             except Exception as exc:   # the reassembly comparison is informative only; never lose the bench line over it
                 allgather["fused_error"] = str(exc)[:200]
 
+    multi = None
+    if dist is not None and os.environ.get("B200VFX_BENCH_CONFIG5", "1") != "0" and H4K * 2 % N == 0:
+        try:
+            multi = config5_leg(torch, dist, np, synth, b200vfx, rank, N, local)
+        except Exception as exc:   # informative leg: never lose the bench line over it
+            multi = {"error": str(exc)[:300]}
+
     cpu = None
     if rank == 0 and N == 1 and not args.no_cpu:
         cpu = cpu_baseline_sample(np, synth)
@@ -464,10 +594,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 (f32 LUT arithmetic)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "lut": "33^3 mix .cube", "frame": "3840x2160 RGBA stride 15360",
-                       "frames_per_step": args.gop * N, "ring_frames": RING, "l2": "inputs larger than L2 (%d in + %d out frames = %d MB ring, no flush)" % (RING, RING, 2 * RING * FRAME_BYTES // 1000000),
-                       "colorlut_mode": "memo" if args.mode == 0 else "direct",
-                       "sharding": "row tiles, rank r owns rows [r*H/N,(r+1)*H/N) of every frame; no data-path collective"},
+            "config": workload_config(args.gop, N, args.mode),
             "gpu_launches": total_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_bytes(args.mode), "kernel": "colorlut_memo_apply_kernel<8>" if args.mode == 0 else "colorlut_direct_kernel<0,true>",
@@ -481,6 +608,8 @@ def main():
             line["cpu_baseline"] = cpu
         if allgather is not None:
             line["allgather"] = allgather
+        if multi is not None:
+            line["roofline"]["multi_gpu"] = multi
         emit(line)
     ctx.close()
     if dist is not None:

@@ -92,6 +92,11 @@ def lib() -> C.CDLL:
         "b200vfx_colorlut_clear": ([vp], ci),
         "b200vfx_colorlut_set_mode": ([vp, ci], ci),
         "b200vfx_colorlut_process": ([vp, ci, ci, ci, vp, ci, vp, ci], ci),
+        "b200vfx_colorlut_process_fmt": ([vp, ci, ci, ci, ci, vp, ci, vp, ci], ci),
+        "b200vfx_convert_packed": ([vp, ci, ci, ci, ci, vp, ci, vp, ci], ci),
+        "b200vfx_convert_to_planar": ([vp, ci, ci, ci, ci, vp, ci, C.POINTER(vp), C.POINTER(ci), ci], ci),
+        "b200vfx_convert_from_planar": ([vp, ci, ci, ci, ci, C.POINTER(vp), C.POINTER(ci), vp, ci, ci], ci),
+        "b200vfx_a420_append": ([vp, ci, ci, C.POINTER(vp), C.POINTER(ci), vp, ci, C.POINTER(vp), C.POINTER(ci)], ci),
         "b200vfx_hsvfilter_process": ([vp, ci, ci, ci, vp, ci] + [cf] * 5, ci),
         "b200vfx_hsvdetector_process": ([vp, ci, ci, ci, ci, vp, ci, vp, ci] + [cf] * 6, ci),
         "b200vfx_roundmask_generate": ([vp, ci, ci, ci, cu, vp], ci),
@@ -274,6 +279,32 @@ class Context:
                                                              world, rank, fa, frame_stride, frame_row0, ga, epoch))
 
     # hsv ----------------------------------------------------------------------------------
+    def colorlut_process_fmt(self, in_fmt, out_fmt, width, height, src, sstride, dst, dstride):
+        self._chk(lib().b200vfx_colorlut_process_fmt(self._h, FMT[in_fmt], FMT[out_fmt], width, height, _ptr(src), sstride,
+                                                     _ptr(dst), dstride))
+
+    def convert_packed(self, src_fmt, dst_fmt, width, height, src, sstride, dst, dstride):
+        self._chk(lib().b200vfx_convert_packed(self._h, FMT[src_fmt], FMT[dst_fmt], width, height, _ptr(src), sstride,
+                                               _ptr(dst), dstride))
+
+    @staticmethod
+    def _planes(planes, strides):
+        n = len(planes)
+        return (C.c_void_p * n)(*[_ptr(p) for p in planes]), (C.c_int * n)(*strides)
+
+    def convert_to_planar(self, src_fmt, dst_fmt, width, height, src, sstride, planes, strides, matrix=0):
+        pp, ss = self._planes(planes, strides)
+        self._chk(lib().b200vfx_convert_to_planar(self._h, FMT[src_fmt], FMT[dst_fmt], width, height, _ptr(src), sstride, pp, ss, matrix))
+
+    def convert_from_planar(self, src_fmt, dst_fmt, width, height, planes, strides, dst, dstride, matrix=0):
+        pp, ss = self._planes(planes, strides)
+        self._chk(lib().b200vfx_convert_from_planar(self._h, FMT[src_fmt], FMT[dst_fmt], width, height, pp, ss, _ptr(dst), dstride, matrix))
+
+    def a420_append(self, width, height, i420_planes, i420_strides, a8, a8_stride, out_planes, out_strides):
+        ip, istr = self._planes(i420_planes, i420_strides)
+        op, ostr = self._planes(out_planes, out_strides)
+        self._chk(lib().b200vfx_a420_append(self._h, width, height, ip, istr, _ptr(a8), a8_stride, op, ostr))
+
     def hsvfilter_process(self, fmt, width, height, data, stride, hue_shift=0.0, saturation_mul=1.0,
                           saturation_off=0.0, value_mul=1.0, value_off=0.0):
         self._chk(lib().b200vfx_hsvfilter_process(self._h, FMT[fmt], width, height, _ptr(data), stride, hue_shift,

@@ -27,6 +27,7 @@
 #include "colordetect.cuh"
 #include "memo_tile.cuh"
 #include "hash_kernels.cuh"
+#include "convert.cuh"
 #include "hash_host.h"
 
 using namespace b200vfx;
@@ -1418,6 +1419,263 @@ int b200vfx_hash_distance(const uint8_t *a, const uint8_t *b, int nbits) {
   int d = 0;
   for (int i = 0; i < nbits; i++) d += (a[i] != 0) != (b[i] != 0);
   return d;
+}
+
+// ---- format conversion: what `videoconvert` does either side of these elements, on the device ------
+namespace {
+bool packed_fmt(int fmt, PackedFmt *o) {
+  switch (fmt) {
+    case B200VFX_FORMAT_RGBX: *o = {4, 0, 1, 2, -1}; return true;
+    case B200VFX_FORMAT_RGBA: *o = {4, 0, 1, 2, 3}; return true;
+    case B200VFX_FORMAT_XRGB: *o = {4, 1, 2, 3, -1}; return true;
+    case B200VFX_FORMAT_ARGB: *o = {4, 1, 2, 3, 0}; return true;
+    case B200VFX_FORMAT_BGRX: *o = {4, 2, 1, 0, -1}; return true;
+    case B200VFX_FORMAT_BGRA: *o = {4, 2, 1, 0, 3}; return true;
+    case B200VFX_FORMAT_XBGR: *o = {4, 3, 2, 1, -1}; return true;
+    case B200VFX_FORMAT_ABGR: *o = {4, 3, 2, 1, 0}; return true;
+    case B200VFX_FORMAT_RGB: *o = {3, 0, 1, 2, -1}; return true;
+    case B200VFX_FORMAT_BGR: *o = {3, 2, 1, 0, -1}; return true;
+    default: return false;
+  }
+}
+// PRMT selector turning a 4-byte `sf` pixel into a 4-byte `df` pixel; source bytes 4-7 read 0xFF
+uint32_t swizzle_selector(const PackedFmt &sf, const PackedFmt &df) {
+  uint32_t nib[4] = {4, 4, 4, 4};
+  nib[df.r] = (uint32_t)sf.r; nib[df.g] = (uint32_t)sf.g; nib[df.b] = (uint32_t)sf.b;
+  const int fourth = 6 - df.r - df.g - df.b;
+  nib[fourth] = (df.a >= 0 && sf.a >= 0) ? (uint32_t)sf.a : 4u;   // alpha only when both sides have one; else 255
+  return nib[0] | (nib[1] << 4) | (nib[2] << 8) | (nib[3] << 12);
+}
+YuvMatrix yuv_matrix(int matrix, int height) {
+  // limited-range BT.601 (SD) / BT.709 (HD), 8-bit fixed point x 256; matrix: 0 = by height like GStreamer's default
+  // colorimetry (<= 576 lines: bt601), 601, 709
+  const bool hd = matrix == 709 || (matrix == 0 && height > 576);
+  const double kr = hd ? 0.2126 : 0.299, kb = hd ? 0.0722 : 0.114, kg = 1.0 - kr - kb;
+  const double sy = 219.0 / 255.0, sc = 224.0 / 255.0;
+  auto q = [](double v) { return (int)std::lrint(v * 256.0); };
+  YuvMatrix m;
+  m.yr = q(kr * sy); m.yg = q(kg * sy); m.yb = q(kb * sy);
+  m.ur = q(-kr / (2.0 * (1.0 - kb)) * sc); m.ug = q(-kg / (2.0 * (1.0 - kb)) * sc); m.ub = q(0.5 * sc);
+  m.vr = q(0.5 * sc); m.vg = q(-kg / (2.0 * (1.0 - kr)) * sc); m.vb = q(-kb / (2.0 * (1.0 - kr)) * sc);
+  m.ry = m.gy = m.by = q(1.0 / sy);
+  m.rv = q(2.0 * (1.0 - kr) / sc);
+  m.gu = q(-2.0 * (1.0 - kb) * kb / kg / sc); m.gv = q(-2.0 * (1.0 - kr) * kr / kg / sc);
+  m.bu = q(2.0 * (1.0 - kb) / sc);
+  return m;
+}
+struct PlaneSet { const uint8_t *p[4]; long stride[4]; size_t row[4]; int rows[4]; int n; };
+// I420 / A420 plane geometry
+void planar_geometry(int fmt, int w, int h, PlaneSet *ps) {
+  ps->n = fmt == B200VFX_FORMAT_A420 ? 4 : 3;
+  ps->row[0] = (size_t)w; ps->rows[0] = h;
+  ps->row[1] = ps->row[2] = (size_t)((w + 1) / 2); ps->rows[1] = ps->rows[2] = (h + 1) / 2;
+  ps->row[3] = (size_t)w; ps->rows[3] = h;
+}
+}  // namespace
+
+// ColorLut::transform_frame with the neighbouring videoconverts folded in: any 4-byte 8-bit RGB format in, any out
+int b200vfx_colorlut_process_fmt(b200vfx_ctx *c, int in_fmt, int out_fmt, int width, int height, const void *src, int src_stride,
+                                 void *dst, int dst_stride) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (in_fmt == B200VFX_FORMAT_RGBA && out_fmt == B200VFX_FORMAT_RGBA)
+    return b200vfx_colorlut_process(c, in_fmt, width, height, src, src_stride, dst, dst_stride);
+  if (!c->have_lut) return fail(c, B200VFX_ERR_NOT_NEGOTIATED, "No LUT configured");  // imp.rs:210-213
+  PackedFmt sf, df;
+  if (!packed_fmt(in_fmt, &sf) || !packed_fmt(out_fmt, &df) || sf.bpp != 4 || df.bpp != 4)
+    return fail(c, B200VFX_ERR_UNSUPPORTED, "colorlut (fused convert): formats %d -> %d are not both 4-byte 8-bit RGB formats", in_fmt, out_fmt);
+  const size_t row = (size_t)width * 4;
+  if (int rc = check_frame(c, width, height, src, src_stride, row, dst, dst_stride, row)) return rc;
+  if (width == 0 || height == 0) return 0;
+  DeviceGuard g(c->device);
+  ColorLutFmtOp op;
+  op.in_sel = (uint32_t)sf.r | ((uint32_t)sf.g << 4) | ((uint32_t)sf.b << 8) | (4u << 12);
+  {
+    uint32_t nib[4];
+    nib[df.r] = 0; nib[df.g] = 1; nib[df.b] = 2;
+    const int fourth = 6 - df.r - df.g - df.b, src_fourth = 6 - sf.r - sf.g - sf.b;
+    nib[fourth] = 4u + (uint32_t)src_fourth;                       // the source pixel's 4th byte ...
+    op.out_sel = nib[0] | (nib[1] << 4) | (nib[2] << 8) | (nib[3] << 12);
+    op.src_or = (sf.a >= 0 && df.a >= 0) ? 0u : (0xFFu << (8 * src_fourth));   // ... forced to 255 unless alpha -> alpha
+  }
+  Staged s{(const uint8_t *)src, src_stride, row, (uint8_t *)dst, dst_stride, row, height, false};
+  return run_staged(c, s, [&](const uint8_t *ds, long dss, uint8_t *dd, long dds, int, int rows, cudaStream_t st) {
+    if (!(aligned(ds, dss, 4) && aligned(dd, dds, 4))) return fail(c, B200VFX_ERR_UNSUPPORTED, "colorlut (fused convert): rows must be 4-byte aligned");
+    const bool tables_ready = c->d_axis8 != nullptr && c->memo_ready;
+    const bool pdl = pdl_admit(c->pdl && tables_ready, st, span_of(ds, dss, row, rows), span_of(dd, dds, row, rows));
+    if (int rc = build_axis(c, st)) return rc;
+    if (int rc = ensure_colorlut_memo(c, lut_dev(c), st)) return rc;
+    op.memo = c->lut_kind == 3 ? c->d_memo : nullptr;
+    op.memo1d = c->d_memo1d;
+    int ww = width, hh = rows;
+    if (dss == 4L * width && dds == 4L * width && (long long)width * rows < (1LL << 28)) { ww = width * rows; hh = 1; }
+    const long long items = (long long)ceil_div(ww, 8 * 32 * kMapPx) * hh, cap = (long long)c->sm_count * c->memo_ctas;
+    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(items, cap)));
+    const int linger = (pdl && items > cap) ? 1 : 0;
+    if (linger) pdl_note_linger(st);
+    CU(c, launch_k(pdl, map_u32_kernel<ColorLutFmtOp, kMapPx>, grid, dim3(256), 0, st, op, ds, dss, dd, dds, ww, hh, linger));
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return 0;
+  });
+}
+
+int b200vfx_convert_packed(b200vfx_ctx *c, int src_fmt, int dst_fmt, int width, int height, const void *src, int src_stride,
+                           void *dst, int dst_stride) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  PackedFmt sf, df;
+  if (!packed_fmt(src_fmt, &sf) || !packed_fmt(dst_fmt, &df))
+    return fail(c, B200VFX_ERR_UNSUPPORTED, "convert: formats %d -> %d are not both packed 8-bit RGB formats", src_fmt, dst_fmt);
+  const size_t irow = (size_t)width * sf.bpp, orow = (size_t)width * df.bpp;
+  if (int rc = check_frame(c, width, height, src, src_stride, irow, dst, dst_stride, orow)) return rc;
+  if (width == 0 || height == 0) return 0;
+  DeviceGuard g(c->device);
+  Staged s{(const uint8_t *)src, src_stride, irow, (uint8_t *)dst, dst_stride, orow, height, false};
+  return run_staged(c, s, [&](const uint8_t *ds, long dss, uint8_t *dd, long dds, int, int rows, cudaStream_t st) {
+    const bool pdl = pdl_admit(c->pdl && sf.bpp == 4 && df.bpp == 4, st, span_of(ds, dss, irow, rows), span_of(dd, dds, orow, rows));
+    if (sf.bpp == 4 && df.bpp == 4) {
+      const int vec = (width % 4) == 0 && aligned(ds, dss, 16) && aligned(dd, dds, 16);
+      const int gx = ceil_div(vec ? width / 4 : width, 256);
+      dim3 grid((unsigned)gx, grid_rows_persistent(gx, rows, c->sm_count));
+      CU(c, launch_k(pdl, swizzle44_kernel, grid, dim3(256), 0, st, ds, dss, dd, dds, width, rows, swizzle_selector(sf, df), vec));
+    } else {
+      const int gx = ceil_div(width, 256);
+      dim3 grid((unsigned)gx, grid_rows_persistent(gx, rows, c->sm_count));
+      swizzle_generic_kernel<<<grid, 256, 0, st>>>(ds, dss, sf, dd, dds, df, width, rows);
+    }
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return 0;
+  });
+}
+
+namespace {
+// planar frames: every plane in HBM (kernel enqueued on the context stream) or every plane on the host (staged, synchronous)
+int planes_location(b200vfx_ctx *c, const void *const *planes, int n, const void *packed, bool *on_device) {
+  int dev = 0;
+  for (int i = 0; i < n; i++) dev += is_device_ptr(planes[i]) ? 1 : 0;
+  const bool pd = is_device_ptr(packed);
+  if (!((dev == n && pd) || (dev == 0 && !pd))) return fail(c, B200VFX_ERR_INVALID, "convert: planes must be all device or all host memory");
+  *on_device = pd;
+  return 0;
+}
+}  // namespace
+
+int b200vfx_convert_to_planar(b200vfx_ctx *c, int src_fmt, int dst_fmt, int width, int height, const void *src, int src_stride,
+                              void *const *planes, const int *strides, int matrix) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  PackedFmt sf;
+  if (!packed_fmt(src_fmt, &sf) || (dst_fmt != B200VFX_FORMAT_I420 && dst_fmt != B200VFX_FORMAT_A420))
+    return fail(c, B200VFX_ERR_UNSUPPORTED, "convert: %d -> %d is not packed RGB -> I420 / A420", src_fmt, dst_fmt);
+  if (!planes || !strides || (matrix != 0 && matrix != 601 && matrix != 709)) return fail(c, B200VFX_ERR_INVALID, "convert: bad argument");
+  if (width <= 0 || height <= 0) return fail(c, B200VFX_ERR_INVALID, "convert: empty frame");
+  PlaneSet ps;
+  planar_geometry(dst_fmt, width, height, &ps);
+  const size_t irow = (size_t)width * sf.bpp;
+  if (!src || src_stride < 0 || (size_t)src_stride < irow) return fail(c, B200VFX_ERR_INVALID, "convert: bad source plane");
+  for (int i = 0; i < ps.n; i++)
+    if (!planes[i] || strides[i] < 0 || (size_t)strides[i] < ps.row[i]) return fail(c, B200VFX_ERR_INVALID, "convert: bad plane %d", i);
+  DeviceGuard g(c->device);
+  bool dev;
+  if (int rc = planes_location(c, (const void *const *)planes, ps.n, src, &dev)) return rc;
+  const YuvMatrix m = yuv_matrix(matrix, height);
+  cudaStream_t st = dev ? c->stream() : c->s_k;
+  const uint8_t *d_src = (const uint8_t *)src;
+  long d_ss = src_stride;
+  uint8_t *dp[4] = {nullptr, nullptr, nullptr, nullptr};
+  long dstr[4] = {0, 0, 0, 0};
+  if (dev) { for (int i = 0; i < ps.n; i++) { dp[i] = (uint8_t *)planes[i]; dstr[i] = strides[i]; } }
+  else {
+    CU(c, c->stage_in.reserve((size_t)src_stride * height));
+    CU(c, cudaMemcpyAsync(c->stage_in.p, src, (size_t)src_stride * (height - 1) + irow, cudaMemcpyHostToDevice, st));
+    d_src = c->stage_in.p;
+    size_t total = 0;
+    for (int i = 0; i < ps.n; i++) total += (size_t)strides[i] * ps.rows[i];
+    CU(c, c->stage_out.reserve(total));
+    size_t off = 0;
+    for (int i = 0; i < ps.n; i++) { dp[i] = c->stage_out.p + off; dstr[i] = strides[i]; off += (size_t)strides[i] * ps.rows[i]; }
+  }
+  pdl_admit(false, st, Span{0, 0}, Span{0, 0});
+  dim3 block(32, 8), grid((unsigned)ceil_div((width + 1) / 2, 32), (unsigned)ceil_div((height + 1) / 2, 8));
+  rgb_to_i420_kernel<<<grid, block, 0, st>>>(d_src, d_ss, sf, width, height, m, dp[0], dstr[0], dp[1], dstr[1], dp[2], dstr[2],
+                                             ps.n == 4 ? dp[3] : nullptr, dstr[3]);
+  c->launches++;
+  CU(c, cudaGetLastError());
+  if (!dev) {
+    for (int i = 0; i < ps.n; i++)
+      CU(c, cudaMemcpy2DAsync(planes[i], (size_t)strides[i], dp[i], (size_t)dstr[i], ps.row[i], (size_t)ps.rows[i], cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    pdl_forget(st);
+  }
+  return 0;
+}
+
+int b200vfx_convert_from_planar(b200vfx_ctx *c, int src_fmt, int dst_fmt, int width, int height, const void *const *planes,
+                                const int *strides, void *dst, int dst_stride, int matrix) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  PackedFmt df;
+  if (!packed_fmt(dst_fmt, &df) || (src_fmt != B200VFX_FORMAT_I420 && src_fmt != B200VFX_FORMAT_A420))
+    return fail(c, B200VFX_ERR_UNSUPPORTED, "convert: %d -> %d is not I420 / A420 -> packed RGB", src_fmt, dst_fmt);
+  if (!planes || !strides || (matrix != 0 && matrix != 601 && matrix != 709)) return fail(c, B200VFX_ERR_INVALID, "convert: bad argument");
+  if (width <= 0 || height <= 0) return fail(c, B200VFX_ERR_INVALID, "convert: empty frame");
+  PlaneSet ps;
+  planar_geometry(src_fmt, width, height, &ps);
+  const size_t orow = (size_t)width * df.bpp;
+  if (!dst || dst_stride < 0 || (size_t)dst_stride < orow) return fail(c, B200VFX_ERR_INVALID, "convert: bad destination plane");
+  for (int i = 0; i < ps.n; i++)
+    if (!planes[i] || strides[i] < 0 || (size_t)strides[i] < ps.row[i]) return fail(c, B200VFX_ERR_INVALID, "convert: bad plane %d", i);
+  DeviceGuard g(c->device);
+  bool dev;
+  if (int rc = planes_location(c, planes, ps.n, dst, &dev)) return rc;
+  const YuvMatrix m = yuv_matrix(matrix, height);
+  cudaStream_t st = dev ? c->stream() : c->s_k;
+  const uint8_t *sp[4] = {nullptr, nullptr, nullptr, nullptr};
+  long sstr[4] = {0, 0, 0, 0};
+  uint8_t *d_dst = (uint8_t *)dst;
+  if (dev) { for (int i = 0; i < ps.n; i++) { sp[i] = (const uint8_t *)planes[i]; sstr[i] = strides[i]; } }
+  else {
+    size_t total = 0;
+    for (int i = 0; i < ps.n; i++) total += (size_t)strides[i] * ps.rows[i];
+    CU(c, c->stage_in.reserve(total));
+    size_t off = 0;
+    for (int i = 0; i < ps.n; i++) {
+      CU(c, cudaMemcpy2DAsync(c->stage_in.p + off, (size_t)strides[i], planes[i], (size_t)strides[i], ps.row[i], (size_t)ps.rows[i], cudaMemcpyHostToDevice, st));
+      sp[i] = c->stage_in.p + off; sstr[i] = strides[i]; off += (size_t)strides[i] * ps.rows[i];
+    }
+    CU(c, c->stage_out.reserve((size_t)dst_stride * height));
+    d_dst = c->stage_out.p;
+  }
+  pdl_admit(false, st, Span{0, 0}, Span{0, 0});
+  const int gx = ceil_div(width, 256);
+  dim3 grid((unsigned)gx, grid_rows_persistent(gx, height, c->sm_count));
+  i420_to_rgb_kernel<<<grid, 256, 0, st>>>(sp[0], sstr[0], sp[1], sstr[1], sp[2], sstr[2], ps.n == 4 ? sp[3] : nullptr, sstr[3], width, height, m,
+                                           d_dst, dst_stride, df);
+  c->launches++;
+  CU(c, cudaGetLastError());
+  if (!dev) {
+    CU(c, cudaMemcpy2DAsync(dst, (size_t)dst_stride, d_dst, (size_t)dst_stride, orow, (size_t)height, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    pdl_forget(st);
+  }
+  return 0;
+}
+
+// RoundedCorners::prepare_output_buffer (border/imp.rs:482-559) for a device-resident pipeline: the reference appends the
+// shared alpha GstMemory to the I420 buffer; device frames are plain plane pointers, so A420 = the three I420 planes + the
+// mask plane copied into the output frame (device-to-device, asynchronous on the context stream)
+int b200vfx_a420_append(b200vfx_ctx *c, int width, int height, const void *const *i420_planes, const int *i420_strides, const void *a8,
+                        int a8_stride, void *const *out_planes, const int *out_strides) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (!i420_planes || !i420_strides || !a8 || !out_planes || !out_strides || width <= 0 || height <= 0)
+    return fail(c, B200VFX_ERR_INVALID, "a420_append: bad argument");
+  PlaneSet ps;
+  planar_geometry(B200VFX_FORMAT_A420, width, height, &ps);
+  for (int i = 0; i < 4; i++) {
+    const void *sp = i < 3 ? i420_planes[i] : a8;
+    const int ss = i < 3 ? i420_strides[i] : a8_stride;
+    if (out_planes[i] == sp) continue;   // plane shared with the input frame: nothing to copy
+    if (int rc = b200vfx_copy_plane(c, out_planes[i], out_strides[i], sp, ss, ps.row[i], ps.rows[i])) return rc;
+  }
+  return 0;
 }
 
 // ---- videocompare: the other hash algorithms and blockhash on sizes that are not multiples of the hash grid -------------

@@ -43,6 +43,18 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 #ifndef B200VFX_EXP_NO_TAIL_WAIT   // timing experiment only
 #define B200VFX_EXP_NO_TAIL_WAIT 0
 #endif
+// (row, chunk) of a work item of the persistent kernels.  Packed frames are flattened to ONE row by the launchers, so the
+// common case needs no division at all; otherwise a 32-bit division serves every frame below 2^31 items.  (The generic
+// 64-bit division is a ~100-instruction subroutine call -- per item and thread it cost 10-25 instructions per pixel.)
+__device__ __forceinline__ void item_row_chunk(long long item, int chunks_x, int height, int &row, int &cx) {
+  if (height == 1) { row = 0; cx = (int)item; }
+  else if (item < (1LL << 31)) {
+    const unsigned it = (unsigned)item, r = it / (unsigned)chunks_x;
+    row = (int)r; cx = (int)(it - r * (unsigned)chunks_x);
+  } else {
+    row = (int)(item / chunks_x); cx = (int)(item - (long long)row * chunks_x);
+  }
+}
 __device__ __forceinline__ void pdl_wait_prior() {
 #if !B200VFX_EXP_NO_TAIL_WAIT
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -153,7 +165,8 @@ __global__ void __launch_bounds__(256) colorlut_memo_apply_kernel(const uint32_t
   const int chunks_x = (width + 8 * 32 * PX - 1) / (8 * 32 * PX);
   const long long items = (long long)chunks_x * height;
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-    const int row = (int)(item / chunks_x), cx = (int)(item - (long long)row * chunks_x);
+    int row, cx;
+    item_row_chunk(item, chunks_x, height, row, cx);
     const int x0 = (cx * 8 + warp) * (32 * PX) + lane;
     if (x0 - lane >= width) continue;
     const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)row * sstride);
@@ -186,7 +199,8 @@ __global__ void __launch_bounds__(256) colorlut_memo1d_apply_kernel(const uint8_
   const int chunks_x = (width + 8 * 32 * PX - 1) / (8 * 32 * PX);
   const long long items = (long long)chunks_x * height;
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-    const int row = (int)(item / chunks_x), cx = (int)(item - (long long)row * chunks_x);
+    int row, cx;
+    item_row_chunk(item, chunks_x, height, row, cx);
     const int x0 = (cx * 8 + warp) * (32 * PX) + lane;
     if (x0 - lane >= width) continue;
     const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)row * sstride);
@@ -358,6 +372,24 @@ struct HsvDetectBitmapOp {  // bitmap bit index = r | g<<8 | b<<16
   }
 };
 
+// colorlut on any 4-byte 8-bit format, input and output byte orders independent: the byte permutation a `videoconvert`
+// either side of the element would do is folded into the lookup kernel's load and store (one PRMT each).
+//   in_sel : source pixel -> (r, g, b, 0) table key;   out_sel: {table value (bytes 0-2), source pixel | 0xFF.. (bytes 4-7)}
+//   -> destination pixel; or_mask sets the 4th byte to 255 when the source has no alpha to copy.
+struct ColorLutFmtOp {
+  const uint32_t *memo;      // 3D: 2^24 answers, or nullptr
+  const uint8_t *memo1d;     // 1D: 3 x 256 answers
+  uint32_t in_sel, out_sel, src_or;
+  __device__ __forceinline__ uint32_t operator()(uint32_t px) const {
+    const uint32_t c = __byte_perm(px, 0u, in_sel);
+    uint32_t v;
+    if (memo) v = __ldg(memo + memo_index(c));
+    else v = (uint32_t)__ldg(memo1d + (c & 255u)) | ((uint32_t)__ldg(memo1d + 256 + ((c >> 8) & 255u)) << 8) |
+             ((uint32_t)__ldg(memo1d + 512 + (c >> 16)) << 16);
+    return __byte_perm(v, px | src_or, out_sel);
+  }
+};
+
 template <typename Op, int PX>
 __global__ void __launch_bounds__(256) map_u32_kernel(Op op, const uint8_t *__restrict__ src, long sstride,
                                                       uint8_t *__restrict__ dst, long dstride, int width, int height,
@@ -367,7 +399,8 @@ __global__ void __launch_bounds__(256) map_u32_kernel(Op op, const uint8_t *__re
   const int chunks_x = (width + 8 * 32 * PX - 1) / (8 * 32 * PX);   // persistent like colorlut_memo_apply_kernel
   const long long items = (long long)chunks_x * height;
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-    const int row = (int)(item / chunks_x), cx = (int)(item - (long long)row * chunks_x);
+    int row, cx;
+    item_row_chunk(item, chunks_x, height, row, cx);
     const int x0 = (cx * 8 + warp) * (32 * PX) + lane;
     if (x0 - lane >= width) continue;
     const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)row * sstride);
@@ -435,7 +468,8 @@ __global__ void __launch_bounds__(256) hsv_direct_map_kernel(Op op, const uint8_
   // the kernel is issue-bound with 64 resident warps per SM, the extra registers and moves cost more than the
   // exposed load latency they hide)
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-    const int row = (int)(item / chunks_x), cx = (int)(item - (long long)row * chunks_x);
+    int row, cx;
+    item_row_chunk(item, chunks_x, height, row, cx);
     const int x0 = (cx * 8 + warp) * (32 * PX) + lane;
     if (x0 - lane >= width) continue;
     const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)row * sstride);

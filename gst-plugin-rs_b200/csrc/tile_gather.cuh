@@ -138,8 +138,9 @@ __global__ void __launch_bounds__(256) colorlut_tile_gather_kernel(const uint32_
   const long long nwork = (long long)cx * rows;
   uint32_t *xp = strip[warp];
   for (long long c = blockIdx.x; go && c < nwork; c += gridDim.x) {
-    const int row = (int)(c / cx);
-    const int xw = ((int)(c % cx) * 8 + warp) * (32 * PX);   // first pixel of this warp's strip
+    int row, ci;
+    item_row_chunk(c, cx, rows, row, ci);
+    const int xw = (ci * 8 + warp) * (32 * PX);   // first pixel of this warp's strip
     if (xw >= width) continue;
     const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)row * sstride);
     const size_t drow = (size_t)dst_offset + (size_t)row * dstride;

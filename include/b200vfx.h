@@ -149,6 +149,31 @@ int b200vfx_colorlut_set_mode(b200vfx_ctx *ctx, int mode);
 int b200vfx_colorlut_process(b200vfx_ctx *ctx, int fmt, int width, int height, const void *src,
                              int src_stride, void *dst, int dst_stride);
 
+/* ColorLut::transform_frame with the videoconverts that surround colorlut in real pipelines (colorlut/imp.rs:18 doc
+ * pipeline) folded into the kernel's load and store: in_fmt / out_fmt are any of the eight 4-byte 8-bit RGB formats
+ * (RGBx xRGB BGRx xBGR RGBA ARGB BGRA ABGR), independently.  Colour bytes go through the LUT; the 4th byte is copied
+ * when both formats carry alpha and written as 255 otherwise.  Same answers as convert -> colorlut -> convert. */
+int b200vfx_colorlut_process_fmt(b200vfx_ctx *ctx, int in_fmt, int out_fmt, int width, int height, const void *src,
+                                 int src_stride, void *dst, int dst_stride);
+
+/* ---- format conversion (the `videoconvert` either side of these elements, kept on the device) ----
+ * b200vfx_convert_packed: any of the ten packed 8-bit RGB formats to any other -- a byte permutation, exact.  A missing
+ * alpha / padding byte is written as 255.  Host or device pointers (device: asynchronous on the context stream).
+ * b200vfx_convert_to_planar / _from_planar: packed RGB <-> I420 / A420 (planes Y, U, V[, A]; SURVEY App. E geometry).
+ * GStreamer's converter is not part of the reference tree: the arithmetic is specified in csrc/convert.cuh (8-bit fixed
+ * point, limited range, BT.601 for <= 576 lines else BT.709 when matrix == 0; 601 / 709 force one) and its parity with
+ * `videoconvert` is UNPINNED.  Planes must be all host or all device memory.
+ * b200vfx_a420_append: RoundedCorners::prepare_output_buffer (border/imp.rs:482-559) for device frames: I420 planes + the
+ * A8 mask -> the four planes of an A420 frame (planes that are shared with the input are not copied). */
+int b200vfx_convert_packed(b200vfx_ctx *ctx, int src_fmt, int dst_fmt, int width, int height, const void *src,
+                           int src_stride, void *dst, int dst_stride);
+int b200vfx_convert_to_planar(b200vfx_ctx *ctx, int src_fmt, int dst_fmt, int width, int height, const void *src,
+                              int src_stride, void *const *planes, const int *strides, int matrix);
+int b200vfx_convert_from_planar(b200vfx_ctx *ctx, int src_fmt, int dst_fmt, int width, int height,
+                                const void *const *planes, const int *strides, void *dst, int dst_stride, int matrix);
+int b200vfx_a420_append(b200vfx_ctx *ctx, int width, int height, const void *const *i420_planes, const int *i420_strides,
+                        const void *a8, int a8_stride, void *const *out_planes, const int *out_strides);
+
 /* ---- hsvfilter ----------------------------------------------------------
  * HsvFilter::transform_frame_ip + hsv_filter (video/hsv/src/hsvfilter/imp.rs:76-120,323-376).
  * In place.  Settings by value = the per-frame snapshot of imp.rs:85.
