@@ -70,6 +70,7 @@ struct b200vfx_ctx {
   std::vector<cudaEvent_t> ev_in, ev_k;
   cudaEvent_t ev_order = nullptr;      // orders the internal pipeline stream after the context stream (mixed host/device calls)
   DevBuf stage_in, stage_out, stage_sums;
+  DevBuf reduce_scratch;               // single-launch reductions: [0,64) two grid counters (kept zero between launches), then partials
   int chunk_rows = 0;
   int sm_count = 148;
   int l2_persist = 0;        // 1 = mark the 2^24-entry answer tables as L2-persisting (access-policy window per launch +
@@ -91,7 +92,6 @@ struct b200vfx_ctx {
   int memo_ctas = 4;     // CTAs per SM of the persistent table-lookup kernels: 4 x 256 threads = half the thread slots, so the next
                          // frame's kernel (PDL) is resident beside this one (profiles/r01_memo_ctas_experiment.jsonl)
   int memo_tile = 0;     // 4-byte-pixel table lookups through memo_tile_kernel (per-tile shared-memory copy of the colour sub-cube)
-  int memo_tile_small = 256;   // ... tiles whose colour box has at most this many entries gather directly (already coherent)
   int cd_cluster = 2;    // colordetect: CTAs per cluster merging their shared-memory histograms (1, 2, 4, 8)
   int peer_timeout_ms = 2000;  // deadline of the cross-GPU waits in the tile-gather kernel
   std::string err;
@@ -216,6 +216,7 @@ LutDev lut_dev(const b200vfx_ctx *c) {
   L.axis_len = 256;
   L.size = c->lut_size; L.kind = c->lut_kind;
   L.ident_domain = 1;
+  L.neg_zero = -0.0f;
   for (int i = 0; i < 3; i++) {
     L.scale[i] = c->scale[i]; L.offset[i] = c->offset[i];
     if (!(c->scale[i] == 1.0f && c->offset[i] == 0.0f)) L.ident_domain = 0;   // -0.0 == 0.0: the default domain yields offset -0.0
@@ -486,9 +487,8 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
     int w = f.width, h = f.height;
     long ss = f.sstride, ds = f.dstride;
     if (c->memo_tile && c->lut_kind == 3 && (w % 4) == 0 && aligned(f.src, ss, 16) && aligned(f.dst, ds, 16)) {
-      const long long ntiles = (long long)ceil_div(w, kTileW) * ceil_div(h, kTileH);
-      dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(ntiles, (long long)c->sm_count * 3)));   // persistent
-      CU(c, launch_k(c->pdl_now, memo_tile_kernel<0, false>, grid, dim3(256), 0, st, c->d_memo, f.src, ss, f.dst, ds, w, h, c->memo_tile_small));
+      dim3 grid((unsigned)ceil_div(w, kTileW), (unsigned)ceil_div(h, kTileH));
+      CU(c, launch_k(c->pdl_now, memo_tile_kernel<0, false>, grid, dim3(256), 0, st, c->d_memo, f.src, ss, f.dst, ds, w, h));
       c->launches++;
       CU(c, cudaGetLastError());
       return 0;
@@ -606,9 +606,8 @@ int launch_hsvfilter(b200vfx_ctx *c, const FmtInfo &fi, const HsvFilterSettings 
     const Span sp = span_of(data, stride, (size_t)w * 4, h);
     const bool pdl = pdl_admit(c->pdl && !built_now, st, sp, sp);
     if (c->memo_tile && (w % 4) == 0 && aligned(data, stride, 16)) {
-      const long long ntiles = (long long)ceil_div(w, kTileW) * ceil_div(h, kTileH);
-      dim3 tgrid((unsigned)std::max<long long>(1, std::min<long long>(ntiles, (long long)c->sm_count * 3)));
-#define LT(CO, BG) CU(c, launch_k(pdl, memo_tile_kernel<CO, BG>, tgrid, dim3(256), 0, st, memo, (const uint8_t *)data, stride, data, stride, w, h, c->memo_tile_small))
+      dim3 tgrid((unsigned)ceil_div(w, kTileW), (unsigned)ceil_div(h, kTileH));
+#define LT(CO, BG) CU(c, launch_k(pdl, memo_tile_kernel<CO, BG>, tgrid, dim3(256), 0, st, memo, (const uint8_t *)data, stride, data, stride, w, h))
       if (fi.coff == 0) { if (fi.bgr) LT(0, true); else LT(0, false); }
       else { if (fi.bgr) LT(1, true); else LT(1, false); }
 #undef LT
@@ -869,6 +868,20 @@ int run_staged(b200vfx_ctx *c, const Staged &s, LaunchFn launch) {
   return 0;
 }
 
+// scratch of the single-launch reductions: 64 bytes of grid counters (zero between launches: the kernels re-arm them) followed
+// by `bytes` of partials.  Growing the buffer synchronises first (a previous launch may still use the old one).
+int reduce_scratch(b200vfx_ctx *c, size_t bytes, unsigned **counters, uint32_t **partials) {
+  const size_t need = 64 + bytes;
+  if (need > c->reduce_scratch.cap) {
+    CU(c, cudaDeviceSynchronize());
+    CU(c, c->reduce_scratch.reserve(std::max<size_t>(need, (size_t)1 << 20)));
+    CU(c, cudaMemset(c->reduce_scratch.p, 0, 64));
+  }
+  *counters = (unsigned *)c->reduce_scratch.p;
+  if (partials) *partials = (uint32_t *)(c->reduce_scratch.p + 64);
+  return 0;
+}
+
 int check_frame(b200vfx_ctx *c, int width, int height, const void *a, long astride, size_t a_row, const void *b,
                 long bstride, size_t b_row) {
   if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
@@ -963,7 +976,7 @@ void b200vfx_ctx_destroy(b200vfx_ctx *c) {
   for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
   if (c->ev_order) cudaEventDestroy(c->ev_order);
   for (auto &kv : c->taps_cache) { cudaFree(kv.second.taps); cudaFree(kv.second.meta); }
-  c->stage_in.release(); c->stage_out.release(); c->stage_sums.release();
+  c->stage_in.release(); c->stage_out.release(); c->stage_sums.release(); c->reduce_scratch.release();
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_k) cudaStreamDestroy(c->s_k);
@@ -1009,7 +1022,6 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "zero_copy") { c->zero_copy = value; c->zc_calls = 0; c->zc_best_ms[0] = c->zc_best_ms[1] = 1e30; }
   else if (n == "blockhash_tma") c->blockhash_tma = value != 0;
   else if (n == "memo_tile") c->memo_tile = value != 0;
-  else if (n == "memo_tile_small") c->memo_tile_small = std::max(0, value);
   else if (n == "memo_ctas") c->memo_ctas = std::max(2, std::min(8, value));
   else if (n == "cd_cluster") c->cd_cluster = (value == 1 || value == 2 || value == 4 || value == 8) ? value : 2;
   else if (n == "l2_persist") c->l2_persist = value;
@@ -1373,11 +1385,12 @@ int b200vfx_blockhash_sums_batch(b200vfx_ctx *c, int fmt, int width, int height,
     dim3 g2((unsigned)hw, (unsigned)hh, (unsigned)ceil_div(bh, rows_tma));
     blockhash_sums_tma_kernel<<<g2, 128, (size_t)rows_tma * bw * 4, st>>>(fr.src[0], fr.stride[0], bw, bh, hw, rows_tma, d_sums);
   } else {
-    blockhash_zero_kernel<<<ceil_div(nbins, 256), 256, 0, st>>>(d_sums, nbins);   // PDL primary of the reduction
-    c->launches++;
-    if (vec) CU(c, launch_k(c->pdl, blockhash_sums_kernel<4, true>, grid, dim3(128), 0, st, fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums));
-    else if (bpp == 4) CU(c, launch_k(c->pdl, blockhash_sums_kernel<4, false>, grid, dim3(128), 0, st, fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums));
-    else CU(c, launch_k(c->pdl, blockhash_sums_kernel<3, false>, grid, dim3(128), 0, st, fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums));
+    uint32_t *partials = nullptr; unsigned *ticket = nullptr;
+    if (int rc = reduce_scratch(c, (size_t)nbins * zchunks * 4, &ticket, &partials)) return rc;
+    if (st != c->stream()) if (int rc = order_after_ctx_stream(c, st)) return rc;   // one launch of this context at a time uses the scratch
+    if (vec) blockhash_sums_kernel<4, true><<<grid, 128, 0, st>>>(fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums, partials, ticket);
+    else if (bpp == 4) blockhash_sums_kernel<4, false><<<grid, 128, 0, st>>>(fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums, partials, ticket);
+    else blockhash_sums_kernel<3, false><<<grid, 128, 0, st>>>(fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums, partials, ticket);
   }
   c->launches++;
   CU(c, cudaGetLastError());
@@ -1869,12 +1882,14 @@ int b200vfx_colordetect_histogram(b200vfx_ctx *c, int fmt, int width, int height
   if (!hist_dev) { CU(c, c->stage_sums.reserve(nb)); d_hist = (uint32_t *)c->stage_sums.p; }
   if (((uintptr_t)d_hist % 4) != 0) return fail(c, B200VFX_ERR_INVALID, "colordetect: histogram pointer is not 4-byte aligned");
   pdl_admit(false, st, Span{0, 0}, Span{0, 0});
-  colordetect_zero_kernel<<<kColorDetectBins / 256, 256, 0, st>>>(d_hist);   // PDL primary of the histogram kernel
-  c->launches++;
-  CU(c, cudaGetLastError());
+  unsigned *gsync = nullptr;
+  if (int rc = reduce_scratch(c, 0, &gsync, nullptr)) return rc;
+  gsync += 4;                                                     // words 4,5: colordetect's counters (word 0: blockhash ticket)
+  if (st != c->stream()) if (int rc = order_after_ctx_stream(c, st)) return rc;   // one launch of this context at a time uses the counters
+  if (nsamples <= 0) CU(c, cudaMemsetAsync(d_hist, 0, nb, st));   // nothing to count: the kernel (which zeroes the bins) does not run
   if (nsamples > 0) {
     const int mode = (bpp == 4 && quality == 1 && ((uintptr_t)d_src % 16) == 0) ? 2 : ((bpp == 4 && ((uintptr_t)d_src % 4) == 0) ? 1 : 0);
-    using KernelT = void (*)(const uint8_t *, long long, int, uint32_t *);
+    using KernelT = void (*)(const uint8_t *, long long, int, uint32_t *, unsigned *);
     static const KernelT table[5][3] = {
         {colordetect_hist_kernel<0, 0>, nullptr, nullptr},
         {colordetect_hist_kernel<1, 0>, colordetect_hist_kernel<1, 1>, colordetect_hist_kernel<1, 2>},
@@ -1920,13 +1935,11 @@ int b200vfx_colordetect_histogram(b200vfx_ctx *c, int fmt, int width, int height
     grid -= grid % cl;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kColorDetectThreads); cfg.dynamicSmemBytes = nb; cfg.stream = st;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;
-    cfg.attrs = attr; cfg.numAttrs = 2;
-    CU(c, cudaLaunchKernelEx(&cfg, k, d_src, nsamples, quality, d_hist));
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CU(c, cudaLaunchKernelEx(&cfg, k, d_src, nsamples, quality, d_hist, gsync));
     c->launches++;
     CU(c, cudaGetLastError());
   }

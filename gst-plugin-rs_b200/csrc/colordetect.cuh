@@ -18,8 +18,10 @@
 //   quality == 1, 4-byte pixels, 16-byte aligned plane: every thread streams 4 x uint4 (16 pixels, 64 KB in flight
 //     per SM -- one CTA per SM has to cover the DRAM latency alone);
 //   otherwise: lane-consecutive samples, one 4-byte (or 3 x 1-byte) load each.
-// The global histogram is zeroed by a tiny primary kernel; this kernel is its programmatic dependent (PDL) and
-// waits with griddepcontrol.wait only before its global atomics, so its launch and pixel pass overlap the zeroing.
+// ONE launch per frame: every CTA first zeroes its slice of the global histogram and arrives at a grid-wide counter; the
+// wait for that counter sits right before the global atomics, i.e. after the whole pixel pass, where it costs nothing.
+// (All CTAs of the grid are co-resident by construction -- the launcher caps the grid at the occupancy maximum -- so the
+// spin cannot deadlock.)  The last CTA to retire resets the two counters for the next launch.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -64,21 +66,23 @@ __device__ __forceinline__ void cd_count_run(uint32_t *sh_hist, uint32_t key, ui
   }
 }
 
-__global__ void colordetect_zero_kernel(uint32_t *__restrict__ hist) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < kColorDetectBins) hist[i] = 0u;
-}
-
 // MODE 0: byte loads (3-byte pixels, unaligned planes); 1: one aligned 32-bit load per sample; 2: step == 1, uint4 loads
 template <int FMT, int MODE>
 __global__ void __launch_bounds__(kColorDetectThreads, 1)
-colordetect_hist_kernel(const uint8_t *__restrict__ plane, long long nsamples, int step, uint32_t *__restrict__ hist) {
+colordetect_hist_kernel(const uint8_t *__restrict__ plane, long long nsamples, int step, uint32_t *__restrict__ hist,
+                        unsigned *__restrict__ gsync) {   // gsync[0]: CTAs that have zeroed their slice, gsync[1]: CTAs retired
   using F = CdFmt<FMT>;
   extern __shared__ __align__(16) uint32_t sh_hist[];
   for (int i = threadIdx.x; i < kColorDetectBins / 4; i += kColorDetectThreads)
     reinterpret_cast<uint4 *>(sh_hist)[i] = make_uint4(0u, 0u, 0u, 0u);
+  {  // this CTA's slice of the global histogram
+    const int per = (kColorDetectBins + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int lo = (int)blockIdx.x * per, hi = min(kColorDetectBins, lo + per);
+    for (int i = lo + (int)threadIdx.x; i < hi; i += kColorDetectThreads) hist[i] = 0u;
+  }
+  __threadfence();
   __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(gsync, 1u);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int U = 4;
   if (MODE == 2) {
@@ -146,7 +150,11 @@ colordetect_hist_kernel(const uint8_t *__restrict__ plane, long long nsamples, i
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned csize = cluster.num_blocks(), crank = cluster.block_rank();
   cluster.sync();
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // the zeroing kernel (PDL primary) has completed and is visible
+  if (threadIdx.x == 0) {   // every CTA has zeroed its slice (they did so before their pixel pass: no waiting in practice)
+    while (*(volatile unsigned *)gsync < gridDim.x) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
   // 4 consecutive bins per thread and step, read from every CTA of the cluster with ld.shared::cluster (mapa-translated
   // shared-window addresses: no generic-address loads); the reads of a step are independent of each other
   const int per4 = kColorDetectBins / 4 / (int)csize;
@@ -168,6 +176,7 @@ colordetect_hist_kernel(const uint8_t *__restrict__ plane, long long nsamples, i
     if (acc.w) atomicAdd(hist + 4 * u + 3, acc.w);
   }
   cluster.sync();  // nobody leaves while a peer may still read its copy
+  if (threadIdx.x == 0 && atomicAdd(gsync + 1, 1u) == gridDim.x - 1u) { gsync[0] = 0u; gsync[1] = 0u; }   // last CTA: re-arm
 }
 
 }  // namespace b200vfx

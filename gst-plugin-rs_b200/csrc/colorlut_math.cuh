@@ -14,9 +14,9 @@
 //
 // Packed f32x2 (Blackwell FADD2 / FMUL2 / FFMA2): the R and G channels travel as the two lanes of one 64-bit register
 // pair (the table layout puts a.rg and d.rg in adjacent registers of the 256-bit load), B stays scalar.  Packed ADDs and
-// SUBs are exact lane-wise RN operations; every multiplication whose product feeds an addition stays a scalar FMUL,
-// because ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 whatever -fmad says (tests/test_sass_lint.py keeps watch).
-// Per pixel this removes ~30 of ~160 issue slots of the RGBA64 kernel, which is issue-bound.
+// SUBs are exact lane-wise RN operations.  ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 whatever -fmad says, so the
+// products that feed an addition are written as mul2_exact (an FMA with an opaque -0.0 addend, see below) -- since round 2;
+// round 1 kept them as scalar FMULs.  tests/test_sass_lint.py keeps watch over the interpolation code.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -34,14 +34,15 @@ __device__ __forceinline__ f32x2_t sub2_rn(f32x2_t a, f32x2_t b) { f32x2_t r; as
 __device__ __forceinline__ f32x2_t add2_rd(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2_t mul2_rn(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2_t fma2_rn(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-// lane-wise a + d*t with the products rounded by scalar FMULs (never contracted)
-__device__ __forceinline__ f32x2_t lerp_pre2(f32x2_t a, f32x2_t d, float t) {
-  float dl, dh;
-  unpk2(d, dl, dh);
-  return add2_rn(a, pk2(__fmul_rn(dl, t), __fmul_rn(dh, t)));
-}
-// lane-wise a + (b - a)*t, three roundings per lane (imp.rs:528-535)
-__device__ __forceinline__ f32x2_t lerp_exact2(f32x2_t a, f32x2_t b, float t) { return lerp_pre2(a, sub2_rn(b, a), t); }
+// Packed PRODUCTS that survive ptxas: a plain mul.f32x2 whose result feeds an add.f32x2 is contracted into FFMA2 whatever
+// the flags say, which would fuse the two roundings of `a + d*t`.  fma.rn.f32x2(d, t, nz) with nz = (-0.0, -0.0) read from a
+// kernel parameter (opaque to the compiler) IS the correctly rounded product -- x*y + (-0) == RN(x*y) for every x*y,
+// signed zeros and NaN included -- and an FMA cannot be merged with the add that follows it.
+__device__ __forceinline__ f32x2_t mul2_exact(f32x2_t a, f32x2_t b, f32x2_t nz) { return fma2_rn(a, b, nz); }
+// lane-wise a + d*t, two roundings per lane: FFMA2 + FADD2
+__device__ __forceinline__ f32x2_t lerp_pre2(f32x2_t a, f32x2_t d, f32x2_t t2, f32x2_t nz) { return add2_rn(a, mul2_exact(d, t2, nz)); }
+// lane-wise a + (b - a)*t, three roundings per lane (imp.rs:528-535): FADD2 + FFMA2 + FADD2
+__device__ __forceinline__ f32x2_t lerp_exact2(f32x2_t a, f32x2_t b, f32x2_t t2, f32x2_t nz) { return lerp_pre2(a, sub2_rn(b, a), t2, nz); }
 
 struct LutDev {
   const LutPair *pair;   // 3D: size^3 x-pair entries
@@ -52,6 +53,7 @@ struct LutDev {
   int kind;              // 1 | 3
   int ident_domain;      // scale == 1 and offset == +-0 on all channels (no DOMAIN_MIN/MAX in the .cube)
   float scale[3], offset[3];
+  float neg_zero;        // -0.0f, set by the host: the opaque addend of mul2_exact
 };
 
 // f32::clamp(0,1): NaN-preserving (imp.rs:473,478)
@@ -197,16 +199,18 @@ __device__ __forceinline__ void colorlut_eval(const LutDev &L, unsigned vr, unsi
   }
   const float tx = __uint_as_float(ax.z), ty = __uint_as_float(ay.z), tz = __uint_as_float(az.z);
   if (L.kind == 3) {
-    const LutPair *base = L.pair + ax.x;
-    const PairRegs e00 = ldg256(base + ay.x + az.x);   // (x0|x1, y0, z0)
-    const PairRegs e10 = ldg256(base + ay.y + az.x);   // (x0|x1, y1, z0)
-    const PairRegs e01 = ldg256(base + ay.x + az.y);   // (x0|x1, y0, z1)
-    const PairRegs e11 = ldg256(base + ay.y + az.y);   // (x0|x1, y1, z1)
+    // 32-bit entry indices (size <= 256: index < 2^24): one IADD3 + one IMAD.WIDE per address instead of 64-bit add chains
+    const uint32_t b0 = ax.x + az.x, b1 = ax.x + az.y;
+    const PairRegs e00 = ldg256(L.pair + (b0 + ay.x));   // (x0|x1, y0, z0)
+    const PairRegs e10 = ldg256(L.pair + (b0 + ay.y));   // (x0|x1, y1, z0)
+    const PairRegs e01 = ldg256(L.pair + (b1 + ay.x));   // (x0|x1, y0, z1)
+    const PairRegs e11 = ldg256(L.pair + (b1 + ay.y));   // (x0|x1, y1, z1)
     // lerp order x (R) -> y (G) -> z (B), imp.rs:514-525.  R and G as the two lanes of a pair ...
-    const f32x2_t c00 = lerp_pre2(e00.a_rg, e00.d_rg, tx), c10 = lerp_pre2(e10.a_rg, e10.d_rg, tx);
-    const f32x2_t c01 = lerp_pre2(e01.a_rg, e01.d_rg, tx), c11 = lerp_pre2(e11.a_rg, e11.d_rg, tx);
-    const f32x2_t c0 = lerp_exact2(c00, c10, ty), c1 = lerp_exact2(c01, c11, ty);
-    quantize_round2<MAXV>(lerp_exact2(c0, c1, tz), out[0], out[1]);
+    const f32x2_t nz = pk2(L.neg_zero, L.neg_zero), tx2 = pk2(tx, tx), ty2 = pk2(ty, ty), tz2 = pk2(tz, tz);
+    const f32x2_t c00 = lerp_pre2(e00.a_rg, e00.d_rg, tx2, nz), c10 = lerp_pre2(e10.a_rg, e10.d_rg, tx2, nz);
+    const f32x2_t c01 = lerp_pre2(e01.a_rg, e01.d_rg, tx2, nz), c11 = lerp_pre2(e11.a_rg, e11.d_rg, tx2, nz);
+    const f32x2_t c0 = lerp_exact2(c00, c10, ty2, nz), c1 = lerp_exact2(c01, c11, ty2, nz);
+    quantize_round2<MAXV>(lerp_exact2(c0, c1, tz2, nz), out[0], out[1]);
     // ... B scalar
     float a, d;
     unpk2(e00.b_ad, a, d); const float b00 = lerp_pre(a, d, tx);

@@ -580,15 +580,12 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_s
 constexpr int kBlockhashMaxFrames = 8;
 struct BlockhashFrames { const uint8_t *src[kBlockhashMaxFrames]; long stride[kBlockhashMaxFrames]; };
 
-__global__ void blockhash_zero_kernel(uint32_t *__restrict__ sums, int n) {
-  pdl_trigger();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) sums[i] = 0u;
-}
-
+// ONE launch: every CTA publishes its partial sum, the last CTA to arrive (ticket) adds the partials of each bin in a
+// fixed order and writes the final sums -- no zeroing pass, no atomics on the bins, nothing to wait for.
 template <int BPP, bool VEC>
 __global__ void __launch_bounds__(128) blockhash_sums_kernel(BlockhashFrames fr, int zchunks, int bw, int bh, int hw, int hh,
-                                                             int rows_per_cta, uint32_t *__restrict__ sums) {
+                                                             int rows_per_cta, uint32_t *__restrict__ sums,
+                                                             uint32_t *__restrict__ partials, unsigned *__restrict__ ticket) {
   const int bx = blockIdx.x, by = blockIdx.y;
   const int f = (int)blockIdx.z / zchunks, chunk = (int)blockIdx.z - f * zchunks;
   const uint8_t *__restrict__ src = fr.src[f];
@@ -627,14 +624,31 @@ __global__ void __launch_bounds__(128) blockhash_sums_kernel(BlockhashFrames fr,
     }
   }
   __shared__ uint32_t wsum[4];
+  __shared__ int s_last;
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
   __syncthreads();
+  const int nbins = hw * hh;                       // per frame
+  const unsigned total = gridDim.x * gridDim.y * gridDim.z;
   if (threadIdx.x == 0) {
     uint32_t t = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += wsum[w];
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // the zeroing kernel has completed
-    atomicAdd(sums + (size_t)f * hw * hh + by * hw + bx, t);
+    // partial of (frame f, chunk, bin): chunk-major inside a frame so the final reduction reads contiguous bins
+    partials[((size_t)f * zchunks + chunk) * nbins + by * hw + bx] = t;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == total - 1u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const int nframes = (int)gridDim.z / zchunks;
+    for (int i = threadIdx.x; i < nframes * nbins; i += blockDim.x) {
+      const int ff = i / nbins, bin = i - ff * nbins;
+      uint32_t t = 0;
+      for (int c = 0; c < zchunks; c++) t += __ldcg(partials + ((size_t)ff * zchunks + c) * nbins + bin);
+      sums[i] = t;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;            // re-armed for the next launch
   }
 }
 

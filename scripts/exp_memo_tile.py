@@ -24,10 +24,6 @@ for name, gen in gens:
     for tile in (0, 1):
         ctx.set_option("memo_tile", tile)
         res["colorlut_tile%d_us" % tile] = timeit(lambda i: ctx.colorlut_process("RGBA", W, H, fr[i % 6], 4 * W, out[i % 6], 4 * W))
-    for small in (0, 64, 1024, 4096):          # direct-gather threshold of the tile kernel (default 256)
-        ctx.set_option("memo_tile_small", small)
-        res["colorlut_tile1_small%d_us" % small] = timeit(lambda i: ctx.colorlut_process("RGBA", W, H, fr[i % 6], 4 * W, out[i % 6], 4 * W))
-    ctx.set_option("memo_tile_small", 256)
     ctx.set_option("hsv_memo", 1)
     for tile in (0, 1):
         ctx.set_option("memo_tile", tile)

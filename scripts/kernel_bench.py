@@ -45,6 +45,29 @@ def timeit(fn, iters, warm=5):
     return a.elapsed_time(b) * 1e-3 / iters
 
 
+def graph_time(fn, launches=16, replays=30):
+    """device time per launch without the host enqueue: `launches` calls captured into one CUDA graph, replayed"""
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for i in range(3):
+            fn(i)
+    st.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=st):
+        for i in range(launches):
+            fn(i)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(replays):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3 / (replays * launches)
+
+
 def report(name, seconds, algo_bytes, **extra):
     gbs = algo_bytes / seconds / 1e9
     print(json.dumps({"kernel": name, "us": round(seconds * 1e6, 3), "algo_GBps": round(gbs, 1), "frac_of_measured_peak": round(gbs / PEAK, 4),
@@ -143,7 +166,27 @@ def main():
         frames, _ = ring_of(contents["noise"])
         sums = torch.zeros(64, dtype=torch.int32, device="cuda")
         t = timeit(lambda i: ctx.blockhash_sums("RGBA", W, H, frames[i % RING], 4 * W, sums), args.iters)
-        report("blockhash_sums_rgba", t, W * H * 4, content="noise", frame="3840x2160", note="one stream; config 4 = two streams")
+        report("blockhash_sums_rgba", t, W * H * 4, content="noise", frame="3840x2160", note="one stream; config 4 = two streams; per-call API loop (host enqueue included)")
+        try:   # the same launches replayed from a CUDA graph: device time only
+            cur = torch.cuda.current_stream()
+            def in_graph(fn):
+                def run(i):
+                    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+                    fn(i)
+                return run
+            t = graph_time(in_graph(lambda i: ctx.blockhash_sums("RGBA", W, H, frames[i % RING], 4 * W, sums)))
+            report("blockhash_sums_rgba", t, W * H * 4, content="noise", frame="3840x2160", note="CUDA-graph replay: device time per launch")
+            sums2g = torch.zeros(128, dtype=torch.int32, device="cuda")
+            t = graph_time(in_graph(lambda i: ctx.blockhash_sums_batch("RGBA", W, H, [frames[i % RING], frames[(i + 1) % RING]], [4 * W, 4 * W], sums2g)))
+            report("blockhash_sums_rgba_batch2", t, 2 * W * H * 4, content="noise", frame="2 x 3840x2160", note="CUDA-graph replay: device time per launch")
+            histg = torch.zeros(32768, dtype=torch.int32, device="cuda")
+            for q in (10, 1):
+                t = graph_time(in_graph(lambda i: ctx.colordetect_histogram("RGBA", W, H, frames[i % RING], 4 * W, q, histg)))
+                report("colordetect_hist_rgba", t, W * H * 4, content="noise", frame="3840x2160", quality=q, note="CUDA-graph replay: device time per launch")
+            ctx.set_stream(cur.cuda_stream)
+        except Exception as exc:
+            print(json.dumps({"graph_timing_error": str(exc)[:200]}), flush=True)
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         sums2 = torch.zeros(128, dtype=torch.int32, device="cuda")
         t = timeit(lambda i: ctx.blockhash_sums_batch("RGBA", W, H, [frames[i % RING], frames[(i + 1) % RING]], [4 * W, 4 * W], sums2), args.iters)
         report("blockhash_sums_rgba_batch2", t, 2 * W * H * 4, content="noise", frame="2 x 3840x2160", note="BASELINE config 4: both streams in one launch")

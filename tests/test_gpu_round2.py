@@ -143,3 +143,45 @@ def test_hsvfilter_direct_kernel_other_formats_and_strides(ctx, fmt):
             assert (view[:, w * bpp:] == base[:, w * bpp:]).all()
     finally:
         ctx.set_option("hsv_memo", -1)
+
+
+def test_pdl_small_frames_ring_of_three_outputs_stress(ctx):
+    """small frames (non-lingering kernels: nothing bounds how many stay co-resident) with a ring of only 3 output buffers:
+    20 000 back-to-back launches with per-frame distinct content must leave exactly the right frames in the ring -- the
+    admission rule turns every reuse of a possibly-live buffer into a plain (fully ordered) launch"""
+    torch = pytest.importorskip("torch")
+    w, h = 640, 480
+    cube = orc.cube_parse(synth.cube_text_3d(17, "mix"))
+    ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+    ctx.colorlut_set_mode(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    nin = 7
+    frames = [synth.frame_noise("RGBA", w, h, 1000 + i) for i in range(nin)]
+    exp = [orc.colorlut_apply(cube, "RGBA", w, h, f, threads=NT) for f in frames]
+    d_in = [torch.from_numpy(f).cuda() for f in frames]
+    d_out = [torch.zeros((h, 4 * w), dtype=torch.uint8, device="cuda") for _ in range(3)]
+    n = 20000
+    for i in range(n):
+        ctx.colorlut_process("RGBA", w, h, d_in[i % nin], 4 * w, d_out[i % 3], 4 * w)
+        if i % 4999 == 4998:                      # spot checks in flight: the last three launches' outputs
+            torch.cuda.synchronize()
+            for k in range(3):
+                j = i - k
+                assert (d_out[j % 3].cpu().numpy() == exp[j % nin]).all(), (i, k)
+    torch.cuda.synchronize()
+    for k in range(3):
+        j = n - 1 - k
+        assert (d_out[j % 3].cpu().numpy() == exp[j % nin]).all(), k
+    # the same with in-place hsvfilter (memoised) chained on the ring: y = f(x) then filter(y) in place, 3 buffers
+    ctx.set_option("hsv_memo", 1)
+    try:
+        flt = [orc.hsvfilter("RGBA", w, h, e.copy(), hue_shift=33.0, threads=NT) for e in exp]
+        for i in range(3000):
+            ctx.colorlut_process("RGBA", w, h, d_in[i % nin], 4 * w, d_out[i % 3], 4 * w)
+            ctx.hsvfilter_process("RGBA", w, h, d_out[i % 3], 4 * w, hue_shift=33.0)
+        torch.cuda.synchronize()
+        for k in range(3):
+            j = 2999 - k
+            assert (d_out[j % 3].cpu().numpy() == flt[j % nin]).all(), k
+    finally:
+        ctx.set_option("hsv_memo", -1)
