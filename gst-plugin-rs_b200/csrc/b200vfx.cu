@@ -91,6 +91,7 @@ struct b200vfx_ctx {
   int tg_path = 0, tg_cfg = 0, tg_ctas = 8;   // fused tile gather: 0 register path (LDG/STG), 1 TMA; variant; CTAs per SM
   int memo_ctas = 4;     // CTAs per SM of the persistent table-lookup kernels: 4 x 256 threads = half the thread slots, so the next
                          // frame's kernel (PDL) is resident beside this one (profiles/r01_memo_ctas_experiment.jsonl)
+  int rgba64_x4 = 1;     // RGBA64 + 3D LUT: 4 consecutive pixels per thread with the LUT cell cached in registers (0: one pixel per thread)
   int memo_tile = 0;     // 4-byte-pixel table lookups through memo_tile_kernel (per-tile shared-memory copy of the colour sub-cube)
   int cd_cluster = 2;    // colordetect: CTAs per cluster merging their shared-memory histograms (1, 2, 4, 8)
   int peer_timeout_ms = 2000;  // deadline of the cross-GPU waits in the tile-gather kernel
@@ -526,6 +527,16 @@ int launch_colorlut(b200vfx_ctx *c, int fmt, const Frame &f, cudaStream_t st) {
   if (((uintptr_t)f.src | (uintptr_t)f.dst) & 1u && fmt != B200VFX_FORMAT_RGBA)
     return fail(c, B200VFX_ERR_INVALID, "RGBA64 planes must be 2-byte aligned (as_slice_of::<u16>, imp.rs:323-324)");
 #define LAUNCH_DIRECT(F, A) CU(c, launch_k(c->pdl_now, colorlut_direct_kernel<F, A>, grid, dim3(256), 0, st, p, f.src, f.sstride, f.dst, f.dstride, f.width, f.height))
+  if (wide && c->lut_kind == 3 && c->rgba64_x4 && (f.width % 4) == 0 && aligned(f.src, f.sstride, 32) && aligned(f.dst, f.dstride, 32)) {
+    // four consecutive pixels per thread, LUT cell entries cached in registers (colorlut_direct64x4_kernel)
+    const int gx = ceil_div(f.width / 4, 256);
+    dim3 g4((unsigned)gx, grid_rows_persistent(gx, f.height, c->sm_count));
+    if (fmt == B200VFX_FORMAT_RGBA64_LE) CU(c, launch_k(c->pdl_now, colorlut_direct64x4_kernel<1>, g4, dim3(256), 0, st, p, f.src, f.sstride, f.dst, f.dstride, f.width, f.height));
+    else CU(c, launch_k(c->pdl_now, colorlut_direct64x4_kernel<2>, g4, dim3(256), 0, st, p, f.src, f.sstride, f.dst, f.dstride, f.width, f.height));
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return 0;
+  }
   switch (fmt) {
     case B200VFX_FORMAT_RGBA: if (al4) LAUNCH_DIRECT(0, true); else LAUNCH_DIRECT(0, false); break;
     case B200VFX_FORMAT_RGBA64_LE: if (al8) LAUNCH_DIRECT(1, true); else LAUNCH_DIRECT(1, false); break;
@@ -1022,6 +1033,7 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "zero_copy") { c->zero_copy = value; c->zc_calls = 0; c->zc_best_ms[0] = c->zc_best_ms[1] = 1e30; }
   else if (n == "blockhash_tma") c->blockhash_tma = value != 0;
   else if (n == "memo_tile") c->memo_tile = value != 0;
+  else if (n == "rgba64_x4") c->rgba64_x4 = value != 0;
   else if (n == "memo_ctas") c->memo_ctas = std::max(2, std::min(8, value));
   else if (n == "cd_cluster") c->cd_cluster = (value == 1 || value == 2 || value == 4 || value == 8) ? value : 2;
   else if (n == "l2_persist") c->l2_persist = value;

@@ -181,6 +181,48 @@ __device__ __forceinline__ void axis_entry_u16_pair(unsigned vr, unsigned vg, co
   ay = make_uint4(i0g * (unsigned)stride_g, min(i0g + 1u, m) * (unsigned)stride_g, __float_as_uint(th), 0u);
 }
 
+// ---- RGBA64, 3D LUT, consecutive pixels of one thread: the four x-pair entries of the LUT cell stay in registers and
+// are re-loaded only when the cell changes.  Measured (profiles/r02_ubench.jsonl, q1 "coherent"): four 256-bit table loads
+// per pixel cost ~40 us per 4K frame EVEN WHEN every lane of a warp reads the same entry -- 32 lanes x 32 bytes = 1 KB per
+// load instruction through the 128 B/clk L1 data path -- so on coherent content (real video: a cell spans ~120 pixels of
+// a 4K row) the RGBA64 kernel was bound by moving the same corner values over and over, not by arithmetic.
+struct CellCache {
+  PairRegs e00, e10, e01, e11;
+  uint32_t i00, i10, i01, i11;   // entry indices the registers hold (0xFFFFFFFF: nothing yet)
+};
+__device__ __forceinline__ void cell_cache_reset(CellCache &c) { c.i00 = c.i10 = c.i01 = c.i11 = 0xFFFFFFFFu; }
+
+__device__ __forceinline__ void colorlut_eval64_cached(const LutDev &L, unsigned vr, unsigned vg, unsigned vb, CellCache &c,
+                                                       unsigned out[3]) {
+  uint4 ax, ay, az;
+  const int s1 = L.size, s2 = L.size * L.size;
+  if (L.ident_domain) {
+    axis_entry_u16_pair<true>(vr, vg, L.scale, L.offset, L.size, s1, ax, ay);
+    az = axis_entry_u16<true>(vb, 1.0f, 0.0f, L.size, s2);
+  } else {
+    axis_entry_u16_pair<false>(vr, vg, L.scale, L.offset, L.size, s1, ax, ay);
+    az = axis_entry_u16<false>(vb, L.scale[2], L.offset[2], L.size, s2);
+  }
+  const float tx = __uint_as_float(ax.z), ty = __uint_as_float(ay.z), tz = __uint_as_float(az.z);
+  const uint32_t b0 = ax.x + az.x, b1 = ax.x + az.y;
+  const uint32_t i00 = b0 + ay.x, i10 = b0 + ay.y, i01 = b1 + ay.x, i11 = b1 + ay.y;
+  if (i00 != c.i00 || i10 != c.i10 || i01 != c.i01 || i11 != c.i11) {
+    c.e00 = ldg256(L.pair + i00); c.e10 = ldg256(L.pair + i10); c.e01 = ldg256(L.pair + i01); c.e11 = ldg256(L.pair + i11);
+    c.i00 = i00; c.i10 = i10; c.i01 = i01; c.i11 = i11;
+  }
+  const f32x2_t nz = pk2(L.neg_zero, L.neg_zero), tx2 = pk2(tx, tx), ty2 = pk2(ty, ty), tz2 = pk2(tz, tz);
+  const f32x2_t c00 = lerp_pre2(c.e00.a_rg, c.e00.d_rg, tx2, nz), c10 = lerp_pre2(c.e10.a_rg, c.e10.d_rg, tx2, nz);
+  const f32x2_t c01 = lerp_pre2(c.e01.a_rg, c.e01.d_rg, tx2, nz), c11 = lerp_pre2(c.e11.a_rg, c.e11.d_rg, tx2, nz);
+  const f32x2_t c0 = lerp_exact2(c00, c10, ty2, nz), c1 = lerp_exact2(c01, c11, ty2, nz);
+  quantize_round2<65535>(lerp_exact2(c0, c1, tz2, nz), out[0], out[1]);
+  float a, d;
+  unpk2(c.e00.b_ad, a, d); const float b00 = lerp_pre(a, d, tx);
+  unpk2(c.e10.b_ad, a, d); const float b10 = lerp_pre(a, d, tx);
+  unpk2(c.e01.b_ad, a, d); const float b01 = lerp_pre(a, d, tx);
+  unpk2(c.e11.b_ad, a, d); const float b11 = lerp_pre(a, d, tx);
+  out[2] = quantize_round<65535>(lerp_exact(lerp_exact(b00, b10, ty), lerp_exact(b01, b11, ty), tz));
+}
+
 // apply_1d / apply_3d for one pixel whose channel values are (vr, vg, vb); MAXV = 255 (table axis) or 65535 (inline axis)
 template <int MAXV>
 __device__ __forceinline__ void colorlut_eval(const LutDev &L, unsigned vr, unsigned vg, unsigned vb, unsigned out[3]) {

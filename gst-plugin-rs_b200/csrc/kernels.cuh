@@ -125,6 +125,45 @@ __global__ void __launch_bounds__(256) colorlut_direct_kernel(LutDev L, const ui
   }
 }
 
+// RGBA64 with a 3D LUT, vector path: a thread owns FOUR consecutive pixels (one 256-bit load, one 256-bit store: a warp moves
+// 1 KB per instruction) and keeps the LUT cell's corner entries in registers across them (colorlut_eval64_cached).
+// Needs 32-byte aligned rows and width % 4 == 0; everything else takes colorlut_direct_kernel.
+struct U256 { unsigned long long a, b, c, d; };
+__device__ __forceinline__ U256 ld_stream_256(const void *p) {
+  U256 v;
+  asm volatile("ld.global.cs.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream_256(void *p, const U256 &v) {
+  asm volatile("st.global.cs.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v.a), "l"(v.b), "l"(v.c), "l"(v.d) : "memory");
+}
+template <int FMT>   // 1 = RGBA64_LE, 2 = RGBA64_BE
+__global__ void __launch_bounds__(256) colorlut_direct64x4_kernel(LutDev L, const uint8_t *__restrict__ src, long sstride,
+                                                                  uint8_t *__restrict__ dst, long dstride, int width, int height) {
+  pdl_trigger();
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;   // group of 4 pixels
+  if (4 * g >= width) return;
+  CellCache cache;
+  cell_cache_reset(cache);
+  for (int row = blockIdx.y; row < height; row += gridDim.y) {
+    const U256 in = ld_stream_256(src + (size_t)row * sstride + (size_t)g * 32);
+    const unsigned long long w[4] = {in.a, in.b, in.c, in.d};
+    unsigned long long o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t w0 = (uint32_t)w[k], w1 = (uint32_t)(w[k] >> 32);
+      const uint32_t alpha = w1 & 0xFFFF0000u;           // alpha word copied raw, never byte-swapped (imp.rs:345,394)
+      if (FMT == 2) { w0 = __byte_perm(w0, 0, 0x2301); w1 = __byte_perm(w1, 0, 0x2301); }
+      unsigned q[3];
+      colorlut_eval64_cached(L, w0 & 0xFFFFu, w0 >> 16, w1 & 0xFFFFu, cache, q);
+      uint32_t o0 = q[0] | (q[1] << 16), o1 = q[2];
+      if (FMT == 2) { o0 = __byte_perm(o0, 0, 0x2301); o1 = __byte_perm(o1, 0, 0x2301); }
+      o[k] = (unsigned long long)o0 | ((unsigned long long)((o1 & 0xFFFFu) | alpha) << 32);
+    }
+    st_stream_256(dst + (size_t)row * dstride + (size_t)g * 32, U256{o[0], o[1], o[2], o[3]});
+  }
+}
+
 // --------------------------------------------------------------------------------------------
 // colorlut memoisation for 8-bit RGBA.  apply_1d/apply_3d are pure functions of the 24-bit
 // colour, and `location` is only mutable in READY (imp.rs:72-76), so the element evaluates

@@ -185,3 +185,46 @@ def test_pdl_small_frames_ring_of_three_outputs_stress(ctx):
             assert (d_out[j % 3].cpu().numpy() == flt[j % nin]).all(), k
     finally:
         ctx.set_option("hsv_memo", -1)
+
+
+@pytest.mark.parametrize("fmt", ["RGBA64_LE", "RGBA64_BE"])
+@pytest.mark.parametrize("lut", ["mix33", "domain17", "ident2", "mix65"])
+def test_colorlut_rgba64_four_pixels_per_thread_kernel(ctx, fmt, lut):
+    """RGBA64 + 3D LUT through colorlut_direct64x4_kernel (LUT cell cached in registers across 4 consecutive pixels, packed
+    exact products) == oracle == the one-pixel-per-thread kernel, on coherent, noisy and boundary-heavy content"""
+    torch = pytest.importorskip("torch")
+    text = {"mix33": synth.cube_text_3d(33, "mix"), "domain17": synth.cube_text_3d(17, "mix", domain=((-0.25, -0.1, 0.0), (1.5, 1.2, 1.0))),
+            "ident2": synth.cube_text_3d(2, "identity"), "mix65": synth.cube_text_3d(65, "mix")}[lut]
+    cube = orc.cube_parse(text)
+    ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    for (w, h, kind) in ((1920, 64, "ramps"), (1024, 33, "noise"), (640, 17, "natural"), (256, 256, "edges"), (1022, 5, "noise")):
+        if kind == "ramps":
+            frame = synth.frame_ramps(fmt, w, h)
+        elif kind == "natural":   # 16-bit ramps with +-200 of noise: neighbouring pixels mostly share a LUT cell, not always
+            dt = "<u2" if fmt.endswith("LE") else ">u2"
+            base = synth.frame_ramps(fmt, w, h).view(dt).astype(np.int64)
+            noise = np.random.default_rng(9).integers(-200, 201, base.shape)
+            frame = np.clip(base + noise, 0, 65535).astype(dt).view(np.uint8).reshape(h, 8 * w)
+        elif kind == "edges":   # every 16-bit channel value that sits on or next to a LUT cell boundary, plus extremes
+            v = np.array(sorted(set([0, 1, 2, 65533, 65534, 65535] + [int(round(k * 65535 / 32)) + d for k in range(33) for d in (-1, 0, 1)])), np.int64)
+            v = v[(v >= 0) & (v <= 65535)].astype(np.uint16)
+            rng = np.random.default_rng(1)
+            px = np.stack([rng.choice(v, w * h), rng.choice(v, w * h), rng.choice(v, w * h), rng.integers(0, 65536, w * h).astype(np.uint16)], axis=1)
+            frame = px.astype("<u2" if fmt.endswith("LE") else ">u2").view(np.uint8).reshape(h, 8 * w)
+        else:
+            frame = synth.frame_noise(fmt, w, h, 77 + w)
+        if frame is None:
+            continue
+        exp = orc.colorlut_apply(cube, fmt, w, h, frame, threads=NT)
+        d = torch.from_numpy(np.ascontiguousarray(frame)).cuda()
+        for x4 in (1, 0):
+            ctx.set_option("rgba64_x4", x4)
+            o = torch.zeros_like(d)
+            ctx.colorlut_process(fmt, w, h, d, 8 * w, o, 8 * w)
+            torch.cuda.synchronize()
+            assert (o.cpu().numpy() == exp).all(), (fmt, lut, w, h, kind, x4)
+        ctx.set_option("rgba64_x4", 1)
+        out = np.zeros_like(frame)
+        ctx.colorlut_process(fmt, w, h, frame, 8 * w, out, 8 * w)      # host frames (staged)
+        assert (out == exp).all(), (fmt, lut, w, h, kind, "host")
