@@ -30,7 +30,8 @@ KEYS = [
 
 
 def rep(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .ncu-rep, or the `ncu -i rep --page raw --csv` export of one (taken on the GPU box: the reports are ~12 MB each)
+    out = open(path).read() if path.endswith(".csv") else subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     if len(rows) < 3:
         print("%s: no launches" % path)

@@ -13,7 +13,7 @@ import b200vfx
 from b200vfx import synth
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--kernel", default="memo", choices=["memo", "direct", "direct64", "hsvfilter", "hsvdetector", "blockhash", "colordetect"])
+ap.add_argument("--kernel", default="memo", choices=["memo", "direct", "direct64", "hsvfilter", "hsvdetector", "blockhash", "colordetect", "hash", "fmt"])
 ap.add_argument("--content", default="ramps", choices=["ramps", "noise", "natural"])
 ap.add_argument("--lut", type=int, default=33)
 ap.add_argument("--launches", type=int, default=6)
@@ -59,6 +59,17 @@ elif a.kernel == "hsvdetector":
     for i in range(a.launches):
         ctx.hsvdetector_process("BGRx", "RGBA", w, h, fr[i % 4], 4 * w, out[i % 4], 4 * w, hue_ref=120.0, hue_var=30.0,
                                 saturation_ref=0.8, saturation_var=0.2, value_ref=0.8, value_var=0.2)
+elif a.kernel == "hash":        # videocompare mean hash: grayscale + Lanczos3 resize kernels
+    fr = [torch.from_numpy(frame("RGBA", W, H, i)).cuda() for i in range(2)]
+    for i in range(a.launches):
+        ctx.hash_image("mean", "RGBA", W, H, fr[i % 2], 4 * W)
+elif a.kernel == "fmt":         # colorlut with the surrounding converts fused in (BGRx -> RGBA)
+    k, s, v, sc, of = b200vfx.cube_parse(synth.cube_text_3d(a.lut, "mix"))
+    ctx.colorlut_set_lut(k, s, v, sc, of)
+    fr = [torch.from_numpy(frame("BGRx", W, H, i)).cuda() for i in range(4)]
+    out = [torch.empty_like(f) for f in fr]
+    for i in range(a.launches):
+        ctx.colorlut_process_fmt("BGRx", "RGBA", W, H, fr[i % 4], 4 * W, out[i % 4], 4 * W)
 elif a.kernel == "colordetect":
     fr = [torch.from_numpy(frame("RGBA", W, H, i)).cuda() for i in range(4)]
     hist = torch.zeros(32768, dtype=torch.int32, device="cuda")
