@@ -1512,7 +1512,7 @@ int b200vfx_colorlut_process_fmt(b200vfx_ctx *c, int in_fmt, int out_fmt, int wi
   if (int rc = check_frame(c, width, height, src, src_stride, row, dst, dst_stride, row)) return rc;
   if (width == 0 || height == 0) return 0;
   DeviceGuard g(c->device);
-  ColorLutFmtOp op;
+  ColorLutFmtOp<true> op;
   op.in_sel = (uint32_t)sf.r | ((uint32_t)sf.g << 4) | ((uint32_t)sf.b << 8) | (4u << 12);
   {
     uint32_t nib[4];
@@ -1537,7 +1537,11 @@ int b200vfx_colorlut_process_fmt(b200vfx_ctx *c, int in_fmt, int out_fmt, int wi
     dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(items, cap)));
     const int linger = (pdl && items > cap) ? 1 : 0;
     if (linger) pdl_note_linger(st);
-    CU(c, launch_k(pdl, map_u32_kernel<ColorLutFmtOp, kMapPx>, grid, dim3(256), 0, st, op, ds, dss, dd, dds, ww, hh, linger));
+    if (c->lut_kind == 3) CU(c, launch_k(pdl, map_u32_kernel<ColorLutFmtOp<true>, kMapPx>, grid, dim3(256), 0, st, op, ds, dss, dd, dds, ww, hh, linger));
+    else {
+      ColorLutFmtOp<false> op1{op.memo, op.memo1d, op.in_sel, op.out_sel, op.src_or};
+      CU(c, launch_k(pdl, map_u32_kernel<ColorLutFmtOp<false>, kMapPx>, grid, dim3(256), 0, st, op1, ds, dss, dd, dds, ww, hh, linger));
+    }
     c->launches++;
     CU(c, cudaGetLastError());
     return 0;

@@ -29,18 +29,35 @@ __global__ void __launch_bounds__(128) luma_vresize_kernel(const uint8_t *__rest
   const float *w = taps + (size_t)oy * max_taps;
   const uint8_t *p = src + (size_t)m.x * stride + (size_t)x * BPP;
   float t = 0.0f;
-  constexpr int U = 8;   // independent loads in flight; the accumulation itself stays strictly in source order
-  int i = 0;
-  for (; i + U <= m.y; i += U) {
-    unsigned l[U];
+  // U independent loads in flight, and the NEXT batch is requested before the current one is accumulated (there are only
+  // W x new_h threads -- ~1.6 warps per scheduler on a 4K frame -- so memory latency is hidden inside a thread or not at
+  // all); the accumulation itself stays strictly in source order
+  constexpr int U = 16;
+  auto fetch = [&](int i0, uint32_t (&raw)[U], float (&wt)[U]) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const uint8_t *q = p + (size_t)(i + u) * stride;
-      if (BPP == 4) { const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(q)); l[u] = luma_of(v & 255u, (v >> 8) & 255u, (v >> 16) & 255u); }
-      else l[u] = luma_of(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+      const uint8_t *q = p + (size_t)(i0 + u) * stride;
+      if (BPP == 4) raw[u] = __ldg(reinterpret_cast<const uint32_t *>(q));
+      else raw[u] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+      wt[u] = __ldg(w + i0 + u);
     }
+  };
+  int i = 0;
+  uint32_t cur[U], nxt[U];
+  float cw[U], nw[U];
+  if (U <= m.y) fetch(0, cur, cw);
+  for (; i + U <= m.y; i += U) {
+    const bool more = i + 2 * U <= m.y;
+    if (more) fetch(i + U, nxt, nw);
 #pragma unroll
-    for (int u = 0; u < U; u++) t = __fadd_rn(t, __fmul_rn((float)l[u], __ldg(w + i + u)));
+    for (int u = 0; u < U; u++) {
+      const unsigned l = luma_of(cur[u] & 255u, (cur[u] >> 8) & 255u, (cur[u] >> 16) & 255u);
+      t = __fadd_rn(t, __fmul_rn((float)l, cw[u]));
+    }
+    if (more) {
+#pragma unroll
+      for (int u = 0; u < U; u++) { cur[u] = nxt[u]; cw[u] = nw[u]; }
+    }
   }
   for (; i < m.y; i++) {
     const uint8_t *q = p + (size_t)i * stride;
@@ -76,7 +93,16 @@ __global__ void luma_hresize_kernel(const float *__restrict__ tmp, int width, in
   const int2 m = meta[ox];
   const float *w = taps + (size_t)ox * max_taps, *row = tmp + (size_t)oy * width + m.x;
   float t = 0.0f;
-  for (int i = 0; i < m.y; i++) t = __fadd_rn(t, __fmul_rn(__ldg(row + i), __ldg(w + i)));
+  constexpr int U = 16;   // operands of the next 16 steps are loaded before the in-order accumulation of the current 16
+  int i = 0;
+  for (; i + U <= m.y; i += U) {
+    float a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) { a[u] = __ldg(row + i + u); b[u] = __ldg(w + i + u); }
+#pragma unroll
+    for (int u = 0; u < U; u++) t = __fadd_rn(t, __fmul_rn(a[u], b[u]));
+  }
+  for (; i < m.y; i++) t = __fadd_rn(t, __fmul_rn(__ldg(row + i), __ldg(w + i)));
   t = t < 0.0f ? 0.0f : (t > 255.0f ? 255.0f : t);
   out[o] = (uint8_t)roundf(t);
 }

@@ -131,6 +131,34 @@ extern "C" {
     ) -> c_int;
     pub fn b200vfx_blockhash_bits(sums: *const u32, hw: c_int, hh: c_int, width: c_int, height: c_int, bits_out: *mut u8);
     pub fn b200vfx_hash_distance(a: *const u8, b: *const u8, nbits: c_int) -> c_int;
+    // HasherEngine::hash_image for every HashAlgorithm value (videocompare/mod.rs:57-92: mean 0, gradient 1, vertgradient 2,
+    // doublegradient 3, blockhash 4) and any frame size; bits_out: 64 bytes of 0/1, *n_bits = 64 (40 for doublegradient)
+    pub fn b200vfx_hash_image(
+        ctx: *mut b200vfx_ctx,
+        algo: c_int,
+        fmt: c_int,
+        width: c_int,
+        height: c_int,
+        src: *const c_void,
+        stride: c_int,
+        bits_out: *mut u8,
+        n_bits: *mut c_int,
+    ) -> c_int;
+
+    // the videoconvert either side of the elements, on the device (include/b200vfx.h "format conversion")
+    pub fn b200vfx_convert_packed(ctx: *mut b200vfx_ctx, src_fmt: c_int, dst_fmt: c_int, width: c_int, height: c_int,
+                                  src: *const c_void, src_stride: c_int, dst: *mut c_void, dst_stride: c_int) -> c_int;
+    pub fn b200vfx_colorlut_process_fmt(ctx: *mut b200vfx_ctx, in_fmt: c_int, out_fmt: c_int, width: c_int, height: c_int,
+                                        src: *const c_void, src_stride: c_int, dst: *mut c_void, dst_stride: c_int) -> c_int;
+    pub fn b200vfx_convert_to_planar(ctx: *mut b200vfx_ctx, src_fmt: c_int, dst_fmt: c_int, width: c_int, height: c_int,
+                                     src: *const c_void, src_stride: c_int, planes: *const *mut c_void, strides: *const c_int,
+                                     matrix: c_int) -> c_int;
+    pub fn b200vfx_convert_from_planar(ctx: *mut b200vfx_ctx, src_fmt: c_int, dst_fmt: c_int, width: c_int, height: c_int,
+                                       planes: *const *const c_void, strides: *const c_int, dst: *mut c_void, dst_stride: c_int,
+                                       matrix: c_int) -> c_int;
+    pub fn b200vfx_a420_append(ctx: *mut b200vfx_ctx, width: c_int, height: c_int, i420_planes: *const *const c_void,
+                               i420_strides: *const c_int, a8: *const c_void, a8_stride: c_int,
+                               out_planes: *const *mut c_void, out_strides: *const c_int) -> c_int;
 
     // colordetect (video/videofx/src/colordetect/imp.rs:57-86): get_palette's pixel pass on the GPU,
     // median cut + CSS name on the host

@@ -22,42 +22,42 @@ pub fn generate_alpha_mask(
     Ok(())
 }
 
-/// replaces HasherEngine::hash_image for HashAlg::Blockhash (videocompare/hashed_image.rs:24-64): no
-/// `tightly_packed_framebuffer` copy (:110-130) -- the stride is passed through.
-pub struct BlockHash(pub [u8; 64]);
+/// replaces HasherEngine::hash_image (videocompare/hashed_image.rs:24-64) for every `hash-algo` value
+/// (HashAlgorithm, videocompare/mod.rs:57-92: Mean 0, Gradient 1, VertGradient 2, DoubleGradient 3, Blockhash 4) and any
+/// frame size: no `tightly_packed_framebuffer` copy (:110-130) -- the stride is passed through.
+pub struct BlockHash(pub [u8; 64], pub usize);
 
 pub fn hash_image(
     ctx: &ffi::Ctx,
+    algo: i32,
     frame: &gst_video::VideoFrameRef<&gst::BufferRef>,
 ) -> Result<BlockHash, gst::FlowError> {
     use gst_video::prelude::*;
     let fmt = ffi::format_code(frame.format()).ok_or(gst::FlowError::NotNegotiated)?;
-    let (w, h) = (frame.width() as i32, frame.height() as i32);
-    let mut sums = [0u32; 64];
+    let mut bits = [0u8; 64];
+    let mut n_bits = 0;
     let rc = unsafe {
-        ffi::b200vfx_blockhash_sums(
+        ffi::b200vfx_hash_image(
             ctx.0,
+            algo,
             fmt,
-            w,
-            h,
+            frame.width() as i32,
+            frame.height() as i32,
             frame.plane_data(0).unwrap().as_ptr() as *const _,
             frame.plane_stride()[0],
-            8,
-            8,
-            sums.as_mut_ptr(),
+            bits.as_mut_ptr(),
+            &mut n_bits,
         )
     };
     if rc != ffi::B200VFX_OK {
         return Err(gst::FlowError::Error);
     }
-    let mut bits = [0u8; 64];
-    unsafe { ffi::b200vfx_blockhash_bits(sums.as_ptr(), 8, 8, w, h, bits.as_mut_ptr()) };
-    Ok(BlockHash(bits))
+    Ok(BlockHash(bits, n_bits as usize))
 }
 
 /// replaces HasherEngine::compare (hashed_image.rs:66-79): Hamming distance as f64
 pub fn compare(a: &BlockHash, b: &BlockHash) -> f64 {
-    unsafe { ffi::b200vfx_hash_distance(a.0.as_ptr(), b.0.as_ptr(), 64) as f64 }
+    unsafe { ffi::b200vfx_hash_distance(a.0.as_ptr(), b.0.as_ptr(), a.1.min(b.1) as i32) as f64 }
 }
 
 /// aggregate_frames (videocompare/imp.rs:297-353) hashes the reference frame and then every other pad's frame:
@@ -84,7 +84,7 @@ pub fn hash_and_compare_all(
     for i in 0..n {
         let mut bits = [0u8; 64];
         unsafe { ffi::b200vfx_blockhash_bits(sums[64 * i..].as_ptr(), 8, 8, w, h, bits.as_mut_ptr()) };
-        hashes.push(BlockHash(bits));
+        hashes.push(BlockHash(bits, 64));
     }
     Ok(hashes[1..].iter().map(|x| compare(&hashes[0], x)).collect())
 }
