@@ -579,9 +579,9 @@ void launch_hsvfilter_t(const HsvFilterSettings &s, const uint32_t *memo, uint8_
     const long long items = (long long)ceil_div(ww, 8 * 32 * kHsvDirectPx) * hh;
     dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(items, (long long)sm_count * 8)));
     if (cls) hsv_direct_map_kernel<HsvFilterDirectOp<BPP == 4 ? COFF : 0, BGR, 1>, kHsvDirectPx><<<grid, 256, 0, st>>>(
-        HsvFilterDirectOp<BPP == 4 ? COFF : 0, BGR, 1>{s, 1.0f}, data, stride, data, stride, ww, hh);
+        HsvFilterDirectOp<BPP == 4 ? COFF : 0, BGR, 1>{s, 1.0f, -0.0f}, data, stride, data, stride, ww, hh);
     else hsv_direct_map_kernel<HsvFilterDirectOp<BPP == 4 ? COFF : 0, BGR, 0>, kHsvDirectPx><<<grid, 256, 0, st>>>(
-        HsvFilterDirectOp<BPP == 4 ? COFF : 0, BGR, 0>{s, 1.0f}, data, stride, data, stride, ww, hh);
+        HsvFilterDirectOp<BPP == 4 ? COFF : 0, BGR, 0>{s, 1.0f, -0.0f}, data, stride, data, stride, ww, hh);
   } else {
     dim3 grid((unsigned)ceil_div(w, 256), grid_rows_persistent(ceil_div(w, 256), h, sm_count));
     hsvfilter_kernel<BPP, COFF, BGR, false, false><<<grid, 256, 0, st>>>(s, cls, nullptr, data, stride, w, h);

@@ -32,6 +32,9 @@ __device__ __forceinline__ void unpk2(f32x2_t v, float &lo, float &hi) { asm("mo
 __device__ __forceinline__ f32x2_t add2_rn(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2_t sub2_rn(f32x2_t a, f32x2_t b) { f32x2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2_t add2_rd(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t fma2_rd(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2_t fma2_rz(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2_t add2_rz(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2_t mul2_rn(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2_t fma2_rn(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 // Packed PRODUCTS that survive ptxas: a plain mul.f32x2 whose result feeds an add.f32x2 is contracted into FFMA2 whatever

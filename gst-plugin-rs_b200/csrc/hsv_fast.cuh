@@ -36,6 +36,8 @@
 #define HF_SUBF(a, b, one) __fmaf_rn(-(b), (one), (a))
 #define HF_ADDF_RD(a, b, one) __fmaf_rd((a), (one), (b))
 #define HF_ADD_SAT(a, b) __saturatef(__fadd_rn((a), (b)))   /* FADD.SAT: clamp to [0,1], NaN -> +0 == hsvutils::Clamp */
+#define HF_ADDF_SAT(a, b, one) __saturatef(__fmaf_rn((a), (one), (b)))   /* the same on the FMA pipe: FFMA.SAT */
+#define HF_FLOOR_UF(x, one) (__float_as_uint(__fmaf_rd((x), (one), 8388608.0f)) & 0x007FFFFFu)   /* HF_FLOOR_U on the FMA pipe */
 /* truncation of a value in [0, 256) as the low byte of val + 2^23 rounded toward zero (no F2I: XU pipe) */
 #define HF_TRUNC_MAGIC(x, one) __float_as_uint(__fmaf_rz((x), (one), 8388608.0f))
 #define HF_PERMUTE2(a, b, sel) __byte_perm((a), (b), (sel))
@@ -66,6 +68,8 @@ static inline float hf_opaque(float x) { volatile float v = x; return v; }   /* 
 #define HF_ADDF_RD(a, b, one) hf_opaque(floorf((a) * (one)) + (b))   /* only used as x + 2^23 rounded down, 0 <= x < 2^22 */
 static inline float hf_add_sat(float a, float b) { const float s = hf_opaque(a + b); return fminf(fmaxf(s, 0.0f), 1.0f); }
 #define HF_ADD_SAT(a, b) hf_add_sat((a), (b))
+#define HF_ADDF_SAT(a, b, one) hf_add_sat((a) * (one), (b))
+#define HF_FLOOR_UF(x, one) hf_floor_u((x) * (one))
 static inline uint32_t hf_trunc_magic(float x) { return 0x4B000000u | ((x != x || x <= 0.0f) ? 0u : (uint32_t)x); }
 #define HF_TRUNC_MAGIC(x, one) hf_trunc_magic((x) * (one))
 static inline uint32_t hf_permute2(uint32_t a, uint32_t b, uint32_t sel) {   /* PRMT, default mode: bytes 0-3 = a, 4-7 = b */
@@ -143,8 +147,8 @@ HF_FN struct HsvF hsvf_from_rgb(const struct HsvTables *T, unsigned r4, unsigned
   const float rem = HF_FMA(-chroma, q0, num);
   const float ratio = HF_FMA(rem, y, q0);
   float hue = HF_MUL(60.0f, HF_ADDF(ratio, add, one));
-  if (hue < 0.0f) hue = HF_ADD(hue, 360.0f);
-  if (hue >= 360.0f) hue = HF_SUB(hue, 360.0f);         // hue % 360.0 for hue in [0, 360]
+  if (hue < 0.0f) hue = HF_ADDF(hue, 360.0f, one);
+  if (hue >= 360.0f) hue = HF_ADDF(hue, -360.0f, one);  // hue % 360.0 for hue in [0, 360]
   // chroma / value: seed 255/max (within 2^-23 of 1/value); black (value == 0): seed 0 gives saturation 0 as required
   const float yv = HF_TAB(T->rdiff, mx);
   const float s0 = HF_MUL(chroma, yv);
@@ -173,10 +177,10 @@ HF_FN float hsvf_wrap360_small(float t, const float one) {
   const float a = HF_ABS(t);
   const float q = HF_SUBF(HF_ADDF_RD(HF_MUL(a, 0.0027777778f), 8388608.0f, one), 8388608.0f, one);   // floor, 0 <= x < 23
   float r = HF_FMA(-q, 360.0f, a);
-  if (r < 0.0f) r = HF_ADD(r, 360.0f);
-  if (r >= 360.0f) r = HF_SUB(r, 360.0f);
+  if (r < 0.0f) r = HF_ADDF(r, 360.0f, one);
+  if (r >= 360.0f) r = HF_ADDF(r, -360.0f, one);
   // t >= 0: r.  t < 0: fmod = -r, negative unless r == 0 -> -r + 360 = RN(360 - r) (may round to exactly 360.0)
-  if (t < 0.0f && r > 0.0f) r = HF_SUB(360.0f, r);
+  if (t < 0.0f && r > 0.0f) r = HF_SUBF(360.0f, r, one);
   return r;
 }
 HF_FN float hsvf_wrap360_general(float t) {
@@ -191,9 +195,9 @@ HF_FN uint32_t hsvf_to_rgb(const struct HsvTables *T, float h, float s, float v,
   const float c = HF_MUL(v, s);
   const float hp = general ? HF_DIV(h, 60.0f) : hsvf_div60(h);
   // sector index i = floor(hp) in 0..6; hp % 2.0 == hp - 2*(i>>1) exactly (Sterbenz).  NaN: hm = NaN, selector 7.
-  const unsigned i = HF_FLOOR_U(hp) & 7u;
+  const unsigned i = HF_FLOOR_UF(hp, one) & 7u;
   const float hm = HF_SUBF(hp, HF_U2F_SMALL(i & 6u), one);
-  const float x = HF_MUL(c, HF_SUB(1.0f, HF_ABS(HF_SUBF(hm, 1.0f, one))));
+  const float x = HF_MUL(c, HF_SUBF(1.0f, HF_ABS(HF_SUBF(hm, 1.0f, one)), one));
   const float m = HF_SUBF(v, c, one);
   // ((p + m) * 255).clamp(0,255) as u8 for p in {c, x, 0}: truncation, NaN -> 0.  0 <= p <= c and m = v - c >= 0, so
   // (p + m) * 255 lies in [0, 255.0001]: the clamp never acts and the byte is the low byte of value + 2^23 rounded
@@ -220,7 +224,7 @@ HF_FN_HD int hsvf_shift_class(float shift) {
 
 // entry of the per-launch v2 table: Clamp(value_mul * value + value_off, 0, 1), hsvutils::Clamp = max-then-min (NaN -> 0)
 HF_FN float hsvf_v2_entry(const struct HsvFilterParams *p, float value) {
-  return HF_ADD_SAT(HF_MUL(p->val_mul, value), p->val_off);
+  return HF_ADD_SAT(HF_MUL(p->val_mul, value), p->val_off);   /* table build: 256 entries per launch, pipe does not matter */
 }
 
 // hsv_filter body (hsvfilter/imp.rs:100-117).  r4,g4,b4 = 4 * byte; packed bytes r | g<<8 | b<<16 out.
@@ -229,7 +233,7 @@ HF_FN uint32_t hsvf_filter_px(const struct HsvTables *T, const struct HsvFilterP
   const struct HsvF a = hsvf_from_rgb(T, r4, g4, b4, one);
   const float t = HF_ADDF(a.h, p->hue_shift, one);
   const float h = shift_class ? hsvf_wrap360_general(t) : hsvf_wrap360_small(t, one);
-  const float s = HF_ADD_SAT(HF_MUL(p->sat_mul, a.s), p->sat_off);
+  const float s = HF_ADDF_SAT(HF_MUL(p->sat_mul, a.s), p->sat_off, one);
   const float v = HF_TAB(T->v2, a.mx4);
   return hsvf_to_rgb(T, h, s, v, shift_class, one);
 }
@@ -239,20 +243,115 @@ HF_FN int hsvf_detect_px(const struct HsvTables *T, const struct HsvDetectParams
                          unsigned b4, const float one) {
   const struct HsvF a = hsvf_from_rgb(T, r4, g4, b4, one);
   float sh = HF_ADDF(a.h, HF_SUB(180.0f, p->hue_ref), one);
-  if (sh < 0.0f) sh = HF_ADD(sh, 360.0f);
+  if (sh < 0.0f) sh = HF_ADDF(sh, 360.0f, one);
   if (ref_class) {
     sh = HF_FMOD(sh, 360.0f);
   } else {  // sh % 360 for |sh| < 8192; only |sh - 180| is consumed, so the sign of a zero result does not matter
     const float aa = HF_ABS(sh);
     const float q = HF_SUBF(HF_ADDF_RD(HF_MUL(aa, 0.0027777778f), 8388608.0f, one), 8388608.0f, one);
     float rr = HF_FMA(-q, 360.0f, aa);
-    if (rr < 0.0f) rr = HF_ADD(rr, 360.0f);
-    if (rr >= 360.0f) rr = HF_SUB(rr, 360.0f);
+    if (rr < 0.0f) rr = HF_ADDF(rr, 360.0f, one);
+    if (rr >= 360.0f) rr = HF_ADDF(rr, -360.0f, one);
     sh = (sh < 0.0f) ? -rr : rr;
   }
   return HF_ABS(HF_SUBF(sh, 180.0f, one)) <= p->hue_var && HF_ABS(HF_SUBF(a.s, p->sat_ref, one)) <= p->sat_var &&
          HF_ABS(HF_SUBF(a.v, p->val_ref, one)) <= p->val_var;
 }
+
+#ifdef __CUDACC__
+// ---- two pixels per f32x2 lane pair (device only) ----------------------------------------------------------------------
+// hsvf_filter_px for shift class 0, with every FADD / FMUL / FFMA of the scalar code issued ONCE for two pixels (FFMA2 /
+// FADD2.RM / FADD2.RZ).  Lane-wise each packed operation is the scalar operation of hsvf_filter_px -- same operands, same
+// single rounding -- so the results are identical by construction (and checked over all 2^24 colours on the GPU):
+//   a + b, a - b      : fma2(a, +-one2, b) exactly as HF_ADDF / HF_SUBF (one = 1.0f at run time)
+//   products that feed an add/sub (60*(..), a*(1/360), smul*s, v*s, c*w, (..)*255): fma2(x, y, nz2) with nz = -0.0f at run
+//                       time -- the correctly rounded product, which ptxas cannot contract with the following add
+//   products that feed FMAs only (q0 = num*y, s0 = chroma*yv, h*(1/60)): plain mul2
+//   -chroma           : vmin - value (RN is sign-symmetric; for chroma == 0 the zero's sign is immaterial, see scalar code)
+// Table look-ups, the R/G/B priority selects, the +-360 fix-ups, the two saturating adds and the byte permutes stay scalar.
+HF_FN void hsvf_filter_px2(const struct HsvTables *T, const struct HsvFilterParams *p, const unsigned r4[2], const unsigned g4[2],
+                           const unsigned b4[2], const float one, const float nzero, uint32_t out[2]) {
+  const float MAGIC = 8388608.0f;
+  const f32x2_t one2 = pk2(one, one), mone2 = pk2(-one, -one), nz2 = pk2(nzero, nzero);
+  float value[2], vmin[2], na[2], nb[2], add[2], y0[2], yv[2], vnew[2];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const float r = HF_TAB(T->d255, r4[k]), g = HF_TAB(T->d255, g4[k]), b = HF_TAB(T->d255, b4[k]);
+    const unsigned mx = max(max(r4[k], g4[k]), b4[k]), mn = min(min(r4[k], g4[k]), b4[k]);
+    value[k] = HF_TAB(T->d255, mx);
+    vmin[k] = HF_TAB(T->d255, mn);
+    const bool isr = r4[k] == mx, isg = g4[k] == mx;
+    na[k] = isr ? g : (isg ? b : r);
+    nb[k] = isr ? b : (isg ? r : g);
+    add[k] = isr ? -0.0f : (isg ? 2.0f : 4.0f);
+    y0[k] = HF_TAB(T->rdiff, mx - mn);
+    yv[k] = HF_TAB(T->rdiff, mx);
+    vnew[k] = HF_TAB(T->v2, mx);
+  }
+  const f32x2_t value2 = pk2(value[0], value[1]), vmin2 = pk2(vmin[0], vmin[1]), y02 = pk2(y0[0], y0[1]), yv2 = pk2(yv[0], yv[1]);
+  // from_rgb
+  const f32x2_t chroma2 = fma2_rn(vmin2, mone2, value2), nchroma2 = fma2_rn(value2, mone2, vmin2);
+  const f32x2_t num2 = fma2_rn(pk2(nb[0], nb[1]), mone2, pk2(na[0], na[1]));
+  const f32x2_t e2 = fma2_rn(nchroma2, y02, pk2(1.0f, 1.0f));
+  const f32x2_t y2 = fma2_rn(y02, e2, y02);
+  const f32x2_t q02 = mul2_rn(num2, y2);
+  const f32x2_t rem2 = fma2_rn(nchroma2, q02, num2);
+  const f32x2_t ratio2 = fma2_rn(rem2, y2, q02);
+  const f32x2_t hue2 = fma2_rn(pk2(60.0f, 60.0f), fma2_rn(ratio2, one2, pk2(add[0], add[1])), nz2);
+  float hue[2];
+  unpk2(hue2, hue[0], hue[1]);
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    if (hue[k] < 0.0f) hue[k] = HF_ADDF(hue[k], 360.0f, one);
+    if (hue[k] >= 360.0f) hue[k] = HF_ADDF(hue[k], -360.0f, one);
+  }
+  const f32x2_t s02 = mul2_rn(chroma2, yv2), ns02 = mul2_rn(nchroma2, yv2);
+  const f32x2_t sat2 = fma2_rn(fma2_rn(value2, ns02, chroma2), yv2, s02);
+  // hue + shift, % 360, negative fix-up
+  float t[2];
+  unpk2(fma2_rn(pk2(hue[0], hue[1]), one2, pk2(p->hue_shift, p->hue_shift)), t[0], t[1]);
+  const f32x2_t a2 = pk2(fabsf(t[0]), fabsf(t[1]));
+  const f32x2_t fl2 = fma2_rd(fma2_rn(a2, pk2(0.0027777778f, 0.0027777778f), nz2), one2, pk2(MAGIC, MAGIC));
+  const f32x2_t q2 = fma2_rn(fl2, one2, pk2(-MAGIC, -MAGIC));
+  float r[2];
+  unpk2(fma2_rn(q2, pk2(-360.0f, -360.0f), a2), r[0], r[1]);
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    if (r[k] < 0.0f) r[k] = HF_ADDF(r[k], 360.0f, one);
+    if (r[k] >= 360.0f) r[k] = HF_ADDF(r[k], -360.0f, one);
+    if (t[k] < 0.0f && r[k] > 0.0f) r[k] = HF_SUBF(360.0f, r[k], one);
+  }
+  // saturation / value
+  float sm[2];
+  unpk2(fma2_rn(pk2(p->sat_mul, p->sat_mul), sat2, nz2), sm[0], sm[1]);
+  const f32x2_t s2 = pk2(HF_ADDF_SAT(sm[0], p->sat_off, one), HF_ADDF_SAT(sm[1], p->sat_off, one));
+  const f32x2_t v2 = pk2(vnew[0], vnew[1]);
+  // to_rgb
+  const f32x2_t c2 = fma2_rn(v2, s2, nz2);
+  const f32x2_t h2 = pk2(r[0], r[1]), c60 = pk2(1.0f / 60.0f, 1.0f / 60.0f);
+  const f32x2_t q0h = mul2_rn(h2, c60);
+  const f32x2_t hp2 = fma2_rn(fma2_rn(q0h, pk2(-60.0f, -60.0f), h2), c60, q0h);
+  float yb[2];
+  unpk2(fma2_rd(hp2, one2, pk2(MAGIC, MAGIC)), yb[0], yb[1]);
+  const unsigned i0 = __float_as_uint(yb[0]) & 7u, i1 = __float_as_uint(yb[1]) & 7u;
+  const f32x2_t fk2 = fma2_rn(pk2(__uint_as_float(0x4B000000u | (i0 & 6u)), __uint_as_float(0x4B000000u | (i1 & 6u))), one2, pk2(-MAGIC, -MAGIC));
+  const f32x2_t hm2 = fma2_rn(fk2, mone2, hp2);
+  float d[2];
+  unpk2(fma2_rn(hm2, one2, pk2(-1.0f, -1.0f)), d[0], d[1]);
+  const f32x2_t w2 = fma2_rn(pk2(fabsf(d[0]), fabsf(d[1])), mone2, pk2(1.0f, 1.0f));
+  const f32x2_t x2 = fma2_rn(c2, w2, nz2);
+  const f32x2_t m2 = fma2_rn(c2, mone2, v2);
+  const f32x2_t k255 = pk2(255.0f, 255.0f), magic2 = pk2(MAGIC, MAGIC);
+  float yc[2], yx[2], ym[2];
+  unpk2(fma2_rz(fma2_rn(fma2_rn(c2, one2, m2), k255, nz2), one2, magic2), yc[0], yc[1]);
+  unpk2(fma2_rz(fma2_rn(fma2_rn(x2, one2, m2), k255, nz2), one2, magic2), yx[0], yx[1]);
+  unpk2(fma2_rz(fma2_rn(m2, k255, nz2), one2, magic2), ym[0], ym[1]);
+  const uint32_t w0 = __byte_perm(__float_as_uint(yc[0]), __float_as_uint(yx[0]), 0x7740u);
+  const uint32_t w1 = __byte_perm(__float_as_uint(yc[1]), __float_as_uint(yx[1]), 0x7740u);
+  out[0] = __byte_perm(w0, __float_as_uint(ym[0]), *(const uint32_t *)((const char *)T->sel + 4u * i0));
+  out[1] = __byte_perm(w1, __float_as_uint(ym[1]), *(const uint32_t *)((const char *)T->sel + 4u * i1));
+}
+#endif  // __CUDACC__
 
 #ifdef __cplusplus
 }  // namespace b200vfx

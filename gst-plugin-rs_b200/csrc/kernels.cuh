@@ -468,9 +468,24 @@ __global__ void __launch_bounds__(256) map_u32_kernel(Op op, const uint8_t *__re
 template <int COFF, bool BGR, int CLS>   // CLS = hsvf_shift_class (0: proven fast code, 1: general code), fixed per launch
 struct HsvFilterDirectOp {
   HsvFilterSettings st;
-  float one;   // 1.0f, opaque to the compiler: keeps the adds that hsv_fast.cuh routes to the FMA pipe as FFMAs
+  float one;     // 1.0f, opaque to the compiler: keeps the adds that hsv_fast.cuh routes to the FMA pipe as FFMAs
+  float nzero;   // -0.0f, opaque: the addend that makes a packed FMA a correctly rounded product (hsvf_filter_px2)
   static constexpr int cls = CLS;
+  static constexpr bool has_pair = CLS == 0;
   __device__ __forceinline__ const HsvFilterParams *filter_params() const { return &st; }
+  // two pixels at once, FP work in f32x2 lanes (shift class 0 only)
+  __device__ __forceinline__ void pair(const HsvTables *T, uint32_t pa, uint32_t pb, uint32_t &oa, uint32_t &ob) const {
+    const uint32_t ca = (pa >> (8 * COFF)) & 0x00FFFFFFu, cb = (pb >> (8 * COFF)) & 0x00FFFFFFu;
+    unsigned a0, a1, a2, b0, b1, b2;
+    bytes_x4(ca, a0, a1, a2);
+    bytes_x4(cb, b0, b1, b2);
+    const unsigned r4[2] = {BGR ? a2 : a0, BGR ? b2 : b0}, g4[2] = {a1, b1}, b4[2] = {BGR ? a0 : a2, BGR ? b0 : b2};
+    uint32_t v[2];
+    hsvf_filter_px2(T, &st, r4, g4, b4, one, nzero, v);
+    if (BGR) { v[0] = swap_c0_c2(v[0]); v[1] = swap_c0_c2(v[1]); }
+    oa = (COFF ? (pa & 0x000000FFu) : (pa & 0xFF000000u)) | (v[0] << (8 * COFF));
+    ob = (COFF ? (pb & 0x000000FFu) : (pb & 0xFF000000u)) | (v[1] << (8 * COFF));
+  }
   __device__ __forceinline__ uint32_t operator()(const HsvTables *T, uint32_t px) const {
     const uint32_t c = (px >> (8 * COFF)) & 0x00FFFFFFu;
     unsigned c0, c1, c2;
@@ -486,6 +501,8 @@ struct HsvDetectDirectOp {
   HsvDetectSettings st;
   float one;
   static constexpr int cls = CLS;
+  static constexpr bool has_pair = false;
+  __device__ __forceinline__ void pair(const HsvTables *, uint32_t, uint32_t, uint32_t &, uint32_t &) const {}
   __device__ __forceinline__ const HsvFilterParams *filter_params() const { return nullptr; }
   __device__ __forceinline__ uint32_t operator()(const HsvTables *T, uint32_t px) const {
     const uint32_t c = (px >> (8 * ICOFF)) & 0x00FFFFFFu;
@@ -519,8 +536,13 @@ __global__ void __launch_bounds__(256) hsv_direct_map_kernel(Op op, const uint8_
     uint32_t px[PX], o[PX];
 #pragma unroll
     for (int k = 0; k < PX; k++) px[k] = (x0 + 32 * k < width) ? ld_stream_u32(s + x0 + 32 * k) : 0u;
+    if (Op::has_pair && (PX % 2) == 0) {
 #pragma unroll
-    for (int k = 0; k < PX; k++) o[k] = op(&T, px[k]);
+      for (int k = 0; k < PX; k += 2) op.pair(&T, px[k], px[k + 1], o[k], o[k + 1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < PX; k++) o[k] = op(&T, px[k]);
+    }
 #pragma unroll
     for (int k = 0; k < PX; k++)
       if (x0 + 32 * k < width) st_stream_u32(d + x0 + 32 * k, o[k]);
