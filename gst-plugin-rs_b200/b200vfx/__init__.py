@@ -122,6 +122,8 @@ def lib() -> C.CDLL:
         "b200vfx_peer_status": ([vp, vp, C.POINTER(C.c_uint32)], ci),
         "b200vfx_colorlut_process_tile_gather": ([vp, ci, ci, ci, vp, ci, ci, ci, C.POINTER(vp), ci, ci, C.POINTER(vp),
                                                   C.c_uint32], ci),
+        "b200vfx_colorlut_process_tile_gather_mc": ([vp, ci, ci, ci, vp, ci, ci, ci, C.POINTER(vp), vp, ci, ci,
+                                                     C.POINTER(vp), C.c_uint32], ci),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(L, name)
@@ -272,11 +274,13 @@ class Context:
         return int(e.value)
 
     def colorlut_process_tile_gather(self, fmt, width, tile_rows, src, sstride, world, rank, frames, frame_stride,
-                                     frame_row0, flags, epoch):
+                                     frame_row0, flags, epoch, multicast=0):
+        """multicast: device address of an NVSwitch multicast mapping bound to every rank's frame buffer (0 = unicast)"""
         fa = (C.c_void_p * world)(*[int(x) for x in frames])
         ga = (C.c_void_p * world)(*[int(x) for x in flags])
-        self._chk(lib().b200vfx_colorlut_process_tile_gather(self._h, FMT[fmt], width, tile_rows, _ptr(src), sstride,
-                                                             world, rank, fa, frame_stride, frame_row0, ga, epoch))
+        self._chk(lib().b200vfx_colorlut_process_tile_gather_mc(self._h, FMT[fmt], width, tile_rows, _ptr(src), sstride,
+                                                                world, rank, fa, C.c_void_p(int(multicast) or None),
+                                                                frame_stride, frame_row0, ga, epoch))
 
     # hsv ----------------------------------------------------------------------------------
     def colorlut_process_fmt(self, in_fmt, out_fmt, width, height, src, sstride, dst, dstride):

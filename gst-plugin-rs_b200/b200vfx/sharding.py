@@ -69,13 +69,17 @@ class PeerFrames:
     NVLink stores).  process(tile) writes this rank's rows into buffer k = epoch % nbuf of EVERY rank; when the call
     completes on the context stream, frame(k) on this rank holds all ranks' rows."""
 
-    def __init__(self, ctx, dist, height: int, stride: int, nbuf: int = 2, align: int = 1):
+    def __init__(self, ctx, dist, height: int, stride: int, nbuf: int = 2, align: int = 1, multicast: bool = False):
         self.ctx, self.dist, self.height, self.stride, self.nbuf, self.align = ctx, dist, height, stride, nbuf, align
         self.world = dist.get_world_size() if dist is not None else 1
         self.rank = dist.get_rank() if dist is not None else 0
         self.epoch = 0
-        self._own = [ctx.peer_alloc(height * stride) for _ in range(nbuf)]
+        self.mc = [0] * nbuf         # multicast address of buffer k (0 = unicast stores to every peer)
         self._own_flags = ctx.peer_alloc(256)
+        if multicast and self.world > 1:
+            self._init_multicast()
+            return
+        self._own = [ctx.peer_alloc(height * stride) for _ in range(nbuf)]
         mine = {"frames": [h for _, h in self._own], "flags": self._own_flags[1]}
         everyone = [mine]
         if self.world > 1:
@@ -96,6 +100,34 @@ class PeerFrames:
         if self.world > 1:
             dist.barrier()
 
+    def _init_multicast(self):
+        """frame buffers from torch's symmetric memory (plumbing: cuMemCreate + cuMulticastBindMem + the handle exchange
+        between the processes); the flag blocks stay ordinary peer memory.  Raises when the fabric has no multicast."""
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        dist, nbuf = self.dist, self.nbuf
+        self._symm, self._own, self._opened = [], [], []
+        self.frames = [[0] * self.world for _ in range(nbuf)]
+        for k in range(nbuf):
+            dev = torch.cuda.current_device()
+            t = symm.empty(self.height * self.stride, dtype=torch.uint8, device=torch.device("cuda", dev))
+            h = symm.rendezvous(t, dist.group.WORLD)
+            if not h.multicast_ptr:
+                raise RuntimeError("no NVSwitch multicast on this box")
+            self._symm.append((t, h))
+            self._own.append((t.data_ptr(), None))
+            self.frames[k] = [int(p) for p in h.buffer_ptrs]
+            self.mc[k] = int(h.multicast_ptr)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, self._own_flags[1])
+        self.flags = [0] * self.world
+        for r, hdl in enumerate(everyone):
+            if r == self.rank:
+                self.flags[r] = self._own_flags[0]
+            else:
+                p = self.ctx.peer_open(hdl); self._opened.append(p); self.flags[r] = p
+        dist.barrier()
+
     def rows(self):
         return row_range(self.height, self.world, self.rank, self.align)
 
@@ -105,7 +137,7 @@ class PeerFrames:
         self.epoch += 1
         k = self.epoch % self.nbuf
         self.ctx.colorlut_process_tile_gather("RGBA", width, r1 - r0, tile, tile_stride, self.world, self.rank,
-                                              self.frames[k], self.stride, r0, self.flags, self.epoch)
+                                              self.frames[k], self.stride, r0, self.flags, self.epoch, multicast=self.mc[k])
         return k
 
     def frame(self, k: int):
@@ -125,7 +157,9 @@ class PeerFrames:
         self._opened = []
         if self.world > 1:
             self.dist.barrier()
-        for p, _ in self._own:
-            self.ctx.peer_free(p)
+        for p, h in self._own:
+            if h is not None:        # symmetric-memory buffers belong to torch
+                self.ctx.peer_free(p)
+        self._symm = []
         self.ctx.peer_free(self._own_flags[0])
         self._own = []

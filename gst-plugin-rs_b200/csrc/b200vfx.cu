@@ -2030,6 +2030,13 @@ int b200vfx_peer_status(b200vfx_ctx *c, const void *flags, uint32_t *error_epoch
 int b200vfx_colorlut_process_tile_gather(b200vfx_ctx *c, int fmt, int width, int tile_rows, const void *src,
                                          int src_stride, int world, int rank, void *const *frames, int frame_stride,
                                          int frame_row0, void *const *flags, uint32_t epoch) {
+  return b200vfx_colorlut_process_tile_gather_mc(c, fmt, width, tile_rows, src, src_stride, world, rank, frames, nullptr,
+                                                 frame_stride, frame_row0, flags, epoch);
+}
+
+int b200vfx_colorlut_process_tile_gather_mc(b200vfx_ctx *c, int fmt, int width, int tile_rows, const void *src,
+                                            int src_stride, int world, int rank, void *const *frames, void *multicast_frame,
+                                            int frame_stride, int frame_row0, void *const *flags, uint32_t epoch) {
   if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
   if (!c->have_lut) return fail(c, B200VFX_ERR_NOT_NEGOTIATED, "No LUT configured");  // imp.rs:210-213
   if (fmt != B200VFX_FORMAT_RGBA || c->mode != 0)
@@ -2069,7 +2076,12 @@ int b200vfx_colorlut_process_tile_gather(b200vfx_ctx *c, int fmt, int width, int
   }
   const bool l1d = c->lut_kind != 3;
   const bool al16 = vec && (w == 0 || (aligned(src, ss, 16)));
-  if (c->tg_path == 1 && al16) {   // TMA: one bulk store per destination out of the shared-memory tile
+  if (multicast_frame) {   // multimem.st moves 16 bytes: the vector path only
+    if (!vec || (uintptr_t)multicast_frame % 16)
+      return fail(c, B200VFX_ERR_UNSUPPORTED, "tile gather: the multicast path needs width %% 4 == 0 and 16-byte aligned frames");
+    ps.mc = (uint8_t *)multicast_frame;
+  }
+  if (c->tg_path == 1 && al16 && !ps.mc) {   // TMA: one bulk store per destination out of the shared-memory tile
     if (int rc = launch_tile_gather_tma(c, l1d, (const uint8_t *)src, ss, ps, ds, doff, 4 * w, h, st)) return rc;
   } else {
     constexpr int PX = 8;

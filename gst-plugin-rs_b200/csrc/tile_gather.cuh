@@ -30,6 +30,7 @@ enum : int { PF_READY = 0, PF_DONE = 16, PF_COUNT = 32, PF_ERR = 33, PF_WORDS = 
 struct PeerSet {
   uint8_t *frame[kMaxPeers];    // whole-frame buffer of every rank, as addressable from THIS device
   uint32_t *flags[kMaxPeers];   // PF_WORDS u32 per rank
+  uint8_t *mc;                  // optional: ONE NVSwitch multicast address bound to the frame buffer of every rank
   int world, rank;
   uint32_t epoch;               // > 0, the same on every rank for one frame, increasing
   uint32_t timeout_ms;
@@ -62,6 +63,11 @@ __device__ __forceinline__ bool wait_epoch(const uint32_t *p, uint32_t epoch, ui
 
 __device__ __forceinline__ void st_v4(uint8_t *p, uint4 v) {
   asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// store through a multicast mapping: the switch replicates the 16 bytes into the bound buffer of every GPU
+__device__ __forceinline__ void st_mc_v4(uint8_t *p, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
 }
 __device__ __forceinline__ void st_u32(uint8_t *p, uint32_t v) {
   asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -164,6 +170,14 @@ __global__ void __launch_bounds__(256) colorlut_tile_gather_kernel(const uint32_
       uint4 v[PX / 4];
 #pragma unroll
       for (int j = 0; j < PX / 4; j++) v[j] = *reinterpret_cast<const uint4 *>(xp + 4 * (lane + 32 * j));
+      if (ps.mc) {   // one store leaves the GPU, the switch fans it out: egress = the tile, not (world - 1) x the tile
+        uint8_t *d = ps.mc + drow;
+#pragma unroll
+        for (int j = 0; j < PX / 4; j++) {
+          const int xq = xw + 4 * (lane + 32 * j);
+          if (xq < width) st_mc_v4(d + 4 * (size_t)xq, v[j]);
+        }
+      } else
       for (int i = 0; i < ps.world; i++) {
         int p = ps.rank + i;   // own frame first, then the peers starting at the right-hand neighbour:
         if (p >= ps.world) p -= ps.world;   // at any instant the ranks push towards different destinations

@@ -13,6 +13,16 @@
  *   videocompare      GstVideoCompare      GstVideoAggregator   video/videofx/src/videocompare/imp.rs
  *   colordetect       GstColorDetect       GstVideoFilter       video/videofx/src/colordetect/imp.rs
  *
+ * PARITY STATUS per element (what a user of the reference can rely on):
+ *   colorlut, hsvfilter, hsvdetector : bit-exact against a CPU restatement of the reference's Rust arithmetic, which is
+ *       pinned to every test vector the reference holds (parser and hsvutils unit tests) and to SURVEY App. C.
+ *   videocompare : all five `hash-algo` values and every frame size larger than 8x8 hash; the bit patterns restate the
+ *       third-party crates image_hasher 3.1.1 / image 0.25.10 (not in the reference tree) FROM MEMORY -- UNPINNED.  Guaranteed
+ *       are the behaviours the reference's tests assert: distance 0 for identical frames, > 0 for snow vs red.
+ *   colordetect  : exact 5-bit histogram; palette (color-thief) and CSS name (color-name) restated from memory -- UNPINNED
+ *       beyond "a red frame is named red".
+ *   roundedcorners : analytic mask; exact 0/255 away from the edge, the anti-aliased ring approximates cairo -- UNPINNED.
+ *
  * Every element owns one b200vfx_ctx (created in start(), destroyed in stop()) and calls the
  * C ABI of b200vfx.h for all pixel work -- the same calls the Rust shim makes.
  * Frames are borrowed, already "mapped" {format,width,height,data[],stride[]} descriptors, like

@@ -287,6 +287,15 @@ int b200vfx_peer_status(b200vfx_ctx *ctx, const void *flags, uint32_t *error_epo
 int b200vfx_colorlut_process_tile_gather(b200vfx_ctx *ctx, int fmt, int width, int tile_rows, const void *src,
                                          int src_stride, int world, int rank, void *const *frames, int frame_stride,
                                          int frame_row0, void *const *flags, uint32_t epoch);
+/* The same with ONE NVSwitch multicast mapping in front of the frame buffers: multicast_frame is a device address from a
+ * multicast object (cuMulticastCreate / cuMulticastBindMem, or torch.distributed._symmetric_memory's multicast_ptr) to
+ * which frames[p] of every rank is bound at the same offset.  Every result vector then leaves the GPU once
+ * (multimem.st) and the switch writes it into all `world` buffers, this rank's own included: egress per GPU is the
+ * tile instead of (world - 1) x the tile.  frames[] is still needed (hazard tracking, frames[rank] is where the frame is
+ * read); NULL multicast_frame = the unicast call above.  Needs width % 4 == 0 and 16-byte aligned frames. */
+int b200vfx_colorlut_process_tile_gather_mc(b200vfx_ctx *ctx, int fmt, int width, int tile_rows, const void *src,
+                                            int src_stride, int world, int rank, void *const *frames, void *multicast_frame,
+                                            int frame_stride, int frame_row0, void *const *flags, uint32_t epoch);
 
 /* ---- test hooks (host logic only, no GPU needed) ---------------------------------------------------------------
  * The admission rule for overlapping consecutive frames (programmatic dependent launch): would a launch with these

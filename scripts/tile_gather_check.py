@@ -90,6 +90,52 @@ for name, opts in (("stg_ctas8", (0, 0, 8)), ("stg_ctas4", (0, 0, 4)), ("stg_cta
                    ("tma_8k", (1, 1, 0)), ("tma_4k", (1, 2, 0)), ("tma_32k", (1, 3, 0)), ("tma_16k_1cta", (1, 0, 1))):
     ctx.set_option("tile_gather_path", opts[0]); ctx.set_option("tile_gather_cfg", opts[1]); ctx.set_option("tile_gather_ctas", opts[2] or (8 if opts[0] == 0 else 0))
     variants[name] = round(dev_time(k_fused, a.iters) * 1e6, 1)
+# NVSwitch multicast variant: one multimem.st per result vector, the switch fans it out to all ranks
+mc_note, t_mc = None, float("nan")
+try:
+    ctx.set_option("tile_gather_path", 0); ctx.set_option("tile_gather_ctas", 8)
+    pm = sharding.PeerFrames(ctx, dist, H, 4 * W, nbuf=2, multicast=True)
+    mc_ok = True
+    for e in range(6):
+        k = pm.process(W, tiles[e % 3], 4 * W)
+        got = torch.as_tensor(pm.frame(k), device="cuda").clone()
+        mc_ok = mc_ok and bool((got.cpu().numpy() == exps[e % 3]).all())
+    mc_ok = mc_ok and pm.status() == 0
+    mc_times = {}
+    for nct in (8, 4, 2, 1):
+        ctx.set_option("tile_gather_ctas", nct)
+        mc_times["mc_ctas%d" % nct] = round(dev_time(lambda i: pm.process(W, d_in[i % R], 4 * W), a.iters) * 1e6, 1)
+    t_mc = min(mc_times.values()) * 1e-6
+    mc_note = {"parity": mc_ok, "us": mc_times, "timeouts": pm.status()}
+    ok = ok and mc_ok
+    pm.close()
+except Exception as ex:   # no multicast on this box / torch build: recorded, not fatal
+    mc_note = {"unavailable": repr(ex)[:300]}
+print("rank %d multicast: %s" % (rank, mc_note), flush=True)
+ctx.set_option("tile_gather_ctas", 8)
+# yardstick: the same bytes pushed by the copy engines -- every rank cudaMemcpyAsync's its finished tile into every peer's
+# frame buffer on world-1 side streams, all ranks at once (what the fabric delivers to one GPU from 7 senders without any
+# kernel involved)
+import ctypes
+rt = ctypes.CDLL("libcudart.so.12")
+rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+side = [torch.cuda.Stream() for _ in range(max(1, world - 1))]
+fork, joins = torch.cuda.Event(), [torch.cuda.Event() for _ in side]
+tile_bytes = rows * 4 * W
+def k_ce(i):
+    cur = torch.cuda.current_stream()
+    fork.record(cur)
+    j = 0
+    for p in range(world):
+        if p == rank:
+            continue
+        st = side[j]
+        st.wait_event(fork)
+        rc = rt.cudaMemcpyAsync(pf.frames[i % 2][p] + r0 * 4 * W, d_out[i % R].data_ptr(), tile_bytes, 3, st.cuda_stream)
+        assert rc == 0, rc
+        joins[j].record(st); cur.wait_event(joins[j])
+        j += 1
+t_ce = dev_time(k_ce, a.iters) if world > 1 and even else float("nan")
 best = min(variants, key=variants.get)
 t_f = variants[best] * 1e-6
 err = pf.status()
@@ -101,7 +147,9 @@ if rank == 0:
                       "fused_tile_gather_us": round(t_f * 1e6, 1), "fused_variant": best, "fused_variants_us": variants, "speedup_vs_nccl": round(t_n / t_f, 2),
                       "frames_per_s_nccl": round(1 / t_n), "frames_per_s_fused": round(1 / t_f),
                       "recv_bytes_per_gpu": recv, "fused_recv_GBps_per_gpu": round(recv / t_f / 1e9, 1),
-                      "nccl_recv_GBps_per_gpu": round(recv / t_n / 1e9, 1), "timeouts": err, "parity": ok}), flush=True)
+                      "nccl_recv_GBps_per_gpu": round(recv / t_n / 1e9, 1),
+                      "multicast": mc_note, "fused_multicast_us": round(t_mc * 1e6, 1), "multicast_recv_GBps_per_gpu": round(recv / t_mc / 1e9, 1),
+                      "copy_engine_push_us": round(t_ce * 1e6, 1), "copy_engine_recv_GBps_per_gpu": round(recv / t_ce / 1e9, 1), "timeouts": err, "parity": ok}), flush=True)
 ctx.close()
 dist.barrier()
 dist.destroy_process_group()
