@@ -2090,8 +2090,11 @@ int b200vfx_colorlut_process_tile_gather_mc(b200vfx_ctx *c, int fmt, int width, 
 #define LAUNCH_TG(V, L)                                                                                              \
   CU(c, launch_k(false, colorlut_tile_gather_kernel<PX, V, L>, grid, dim3(256), 0, st, c->d_memo, c->d_memo1d,       \
                  (const uint8_t *)src, ss, ps, ds, doff, w, h))
-    if (vec) { if (l1d) LAUNCH_TG(true, true); else LAUNCH_TG(true, false); }
-    else { if (l1d) LAUNCH_TG(false, true); else LAUNCH_TG(false, false); }
+    bool v32 = vec && c->tg_cfg == 1 && !ps.mc && (w % 8) == 0 && (ds % 32) == 0 && (doff % 32) == 0;
+    for (int p = 0; p < world; p++) v32 = v32 && (uintptr_t)ps.frame[p] % 32 == 0;
+    if (v32) { if (l1d) LAUNCH_TG(2, true); else LAUNCH_TG(2, false); }
+    else if (vec) { if (l1d) LAUNCH_TG(1, true); else LAUNCH_TG(1, false); }
+    else { if (l1d) LAUNCH_TG(0, true); else LAUNCH_TG(0, false); }
 #undef LAUNCH_TG
   }
   c->launches++;

@@ -69,6 +69,10 @@ __device__ __forceinline__ void st_mc_v4(uint8_t *p, uint4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
+__device__ __forceinline__ void st_v8(uint8_t *p, uint4 a, uint4 b) {   // STG.E.ENL2.256: 1 KB per warp instruction
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
 __device__ __forceinline__ void st_u32(uint8_t *p, uint32_t v) {
   asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -122,7 +126,7 @@ __device__ __forceinline__ void peer_exit(const PeerSet &ps, uint64_t deadline, 
 // flight per thread), persistent CTAs looping over (strip, row).  VEC: results are transposed through a warp-private
 // shared-memory strip so that every lane stores 16 consecutive bytes -- 512-byte warp stores, 4x fewer store
 // instructions per destination, full NVLink packets.
-template <int PX, bool VEC, bool LUT1D>
+template <int PX, int VEC, bool LUT1D>   // VEC: 0 = 4-byte stores, 1 = 16-byte, 2 = 32-byte (PX == 8, 32-byte aligned rows)
 __global__ void __launch_bounds__(256) colorlut_tile_gather_kernel(const uint32_t *__restrict__ memo,
                                                                    const uint8_t *__restrict__ memo1d,
                                                                    const uint8_t *__restrict__ src, long sstride,
@@ -162,7 +166,20 @@ __global__ void __launch_bounds__(256) colorlut_tile_gather_kernel(const uint32_
         o[k] = __ldg(memo + memo_index(px[k] & 0x00FFFFFFu)) | (px[k] & 0xFF000000u);
       }
     }
-    if (VEC) {
+    if (VEC == 2) {
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < PX; k++) xp[32 * k + lane] = o[k];
+      __syncwarp();
+      const uint4 a = *reinterpret_cast<const uint4 *>(xp + 8 * lane), b = *reinterpret_cast<const uint4 *>(xp + 8 * lane + 4);
+      const int xq = xw + 8 * lane;
+      if (xq < width)   // width % 8 == 0 on this path
+        for (int i = 0; i < ps.world; i++) {
+          int p = ps.rank + i;
+          if (p >= ps.world) p -= ps.world;
+          st_v8(ps.frame[p] + drow + 4 * (size_t)xq, a, b);
+        }
+    } else if (VEC) {
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < PX; k++) xp[32 * k + lane] = o[k];

@@ -38,8 +38,8 @@ gens = [lambda: synth.frame_natural("RGBA", W, H, 0x5EED0005), lambda: synth.fra
 frames_np = [g() for g in gens]
 exps = [orc.colorlut_apply(cube, "RGBA", W, H, f, threads=16) for f in frames_np]
 tiles = [torch.from_numpy(f[r0:r1].copy()).cuda() for f in frames_np]
-for nbuf, path in ((1, 0), (2, 0), (1, 1), (2, 1)):
-    ctx.set_option("tile_gather_path", path)
+for nbuf, path, cfg in ((1, 0, 0), (2, 0, 0), (2, 0, 1), (1, 1, 0), (2, 1, 0)):
+    ctx.set_option("tile_gather_path", path); ctx.set_option("tile_gather_cfg", cfg)
     pf = sharding.PeerFrames(ctx, dist, H, 4 * W, nbuf=nbuf)
     for e in range(6):   # back to back, no host synchronisation between epochs: the entry handshake orders buffer reuse
         k = pf.process(W, tiles[e % 3], 4 * W)
@@ -48,7 +48,7 @@ for nbuf, path in ((1, 0), (2, 0), (1, 1), (2, 1)):
         ok = ok and good
     ok = ok and pf.status() == 0
     pf.close()
-print("rank %d/%d rows [%d,%d): fused tile-gather frame == oracle (STG and TMA variants, nbuf 1 and 2, 6 epochs each): %s" % (rank, world, r0, r1, ok), flush=True)
+print("rank %d/%d rows [%d,%d): fused tile-gather frame == oracle (STG, STG.256 and TMA variants, nbuf 1 and 2, 6 epochs each): %s" % (rank, world, r0, r1, ok), flush=True)
 
 # ---- 2. timing -----------------------------------------------------------------------------------
 def dev_time(fn, iters, warm=10):
@@ -86,7 +86,8 @@ even = H % world == 0
 t_k = dev_time(k_only, a.iters)
 t_n = dev_time(k_nccl, a.iters) if even else float("nan")
 variants = {}
-for name, opts in (("stg_ctas8", (0, 0, 8)), ("stg_ctas4", (0, 0, 4)), ("stg_ctas2", (0, 0, 2)), ("tma_16k", (1, 0, 0)),
+for name, opts in (("stg_ctas8", (0, 0, 8)), ("stg_ctas4", (0, 0, 4)), ("stg_ctas2", (0, 0, 2)), ("stg256_ctas4", (0, 1, 4)),
+                   ("stg256_ctas2", (0, 1, 2)), ("tma_16k", (1, 0, 0)),
                    ("tma_8k", (1, 1, 0)), ("tma_4k", (1, 2, 0)), ("tma_32k", (1, 3, 0)), ("tma_16k_1cta", (1, 0, 1))):
     ctx.set_option("tile_gather_path", opts[0]); ctx.set_option("tile_gather_cfg", opts[1]); ctx.set_option("tile_gather_ctas", opts[2] or (8 if opts[0] == 0 else 0))
     variants[name] = round(dev_time(k_fused, a.iters) * 1e6, 1)

@@ -17,12 +17,13 @@ def _cube(size=17, kind="mix"):
     return orc.cube_parse(synth.cube_text_3d(size, kind))
 
 
-PATH = {"stg": 0, "tma": 1}
+PATH = {"stg": 0, "tma": 1, "stg256": 0}   # stg256: 32-byte stores where the geometry allows, 16-byte otherwise
 
 
 def _ctx(cube, dev=0, stream=None, path="stg"):
     c = b200vfx.Context(dev)
     c.set_option("tile_gather_path", PATH[path])
+    c.set_option("tile_gather_cfg", 1 if path == "stg256" else 0)
     c.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
     if stream is not None:
         c.set_stream(stream.cuda_stream)
@@ -34,7 +35,7 @@ def _to_np(ptr, nbytes, dev=0):
     return torch.as_tensor(buf, device="cuda:%d" % dev).cpu().numpy()
 
 
-@pytest.mark.parametrize("path", ["stg", "tma"])
+@pytest.mark.parametrize("path", ["stg", "tma", "stg256"])
 @pytest.mark.parametrize("w,h,pad", [(256, 64, 0), (1920, 33, 0), (250, 17, 0), (251, 9, 12), (64, 5, 64), (3840, 24, 0), (7680, 8, 0)])
 def test_world1_matches_oracle(w, h, pad, path):
     cube = _cube()
@@ -54,7 +55,7 @@ def test_world1_matches_oracle(w, h, pad, path):
         pf.close()
 
 
-@pytest.mark.parametrize("path", ["stg", "tma"])
+@pytest.mark.parametrize("path", ["stg", "tma", "stg256"])
 def test_world1_lut1d(path):
     cube = orc.cube_parse(synth.cube_text_1d(16))
     w, h = 512, 16
@@ -105,7 +106,7 @@ def _virtual_ranks(world, w, h, devices, epochs=4, nbuf=1, align=1, path="stg"):
         ctxs[r].close()
 
 
-@pytest.mark.parametrize("path", ["stg", "tma"])
+@pytest.mark.parametrize("path", ["stg", "tma", "stg256"])
 @pytest.mark.parametrize("world,w,h", [(2, 256, 8), (3, 100, 10), (4, 64, 3), (8, 128, 16)])
 def test_virtual_ranks_one_device(world, w, h, path):
     # small frames: the kernels of all "ranks" are co-resident on the one GPU, so the handshake cannot starve
