@@ -79,6 +79,9 @@ struct b200vfx_ctx {
                              // (profiles/r01_l2_persist_experiment.jsonl)
   size_t l2_persist_max = 0, l2_window_max = 0, l2_set_aside = 0;
   bool blockhash_tma = false; // videocompare block sums through the TMA-fed kernel (measured equal or slightly slower than the register-staged LDG kernel: profiles/r01_kernel_matrix.md)
+  int blockhash_rows = 2;      // videocompare block sums: whole-row streaming kernel with 2 * SMs / value CTAs (2 = one CTA per SM, which
+                               // leaves room for the next launch's CTAs to stream while this one drains: 6.4 vs 8.3 us per 4K frame);
+                               // 0 = one CTA per hash block, the round-1 decomposition
   int zero_copy = 2;       // pinned host frames: TMA kernel reads/writes host memory directly; 0 never, 1 always, 2 auto-probe
   int zc_calls = 0, zc_bad_streak = 0; double zc_best_ms[2] = {1e30, 1e30};   // auto-probe state: [0] zero-copy, [1] staged
   int zc_cfg = 2, zc_ctas = 1, zc_grid = 96;
@@ -301,7 +304,9 @@ inline Span span_of(const void *p, long stride, size_t row_bytes, int rows) {
 inline bool overlap(Span a, Span b) { return a.lo < b.hi && b.lo < a.hi; }
 
 // returns whether the launch may use PDL, and records it
-bool pdl_admit(bool want, cudaStream_t st, Span src, Span dst) {
+// dst_after_wait: the kernel writes dst only after its griddepcontrol.wait, i.e. after every earlier launch has completed --
+// its writes cannot race with them, only its early reads of src can
+bool pdl_admit(bool want, cudaStream_t st, Span src, Span dst, bool dst_after_wait = false) {
   std::lock_guard<std::mutex> g(g_recent_mu);
   std::deque<RecentLaunch> &q = g_recent[st];
   bool ok = want;
@@ -316,7 +321,7 @@ bool pdl_admit(bool want, cudaStream_t st, Span src, Span dst) {
     for (size_t i = q.size(); i-- > 0;) {
       const RecentLaunch &r = q[i];
       if (!(newer_linger && newer >= g_capacity_threads)) {
-        if (overlap(dst, r.src) || overlap(dst, r.dst) || overlap(src, r.dst)) { ok = false; break; }
+        if ((!dst_after_wait && (overlap(dst, r.src) || overlap(dst, r.dst))) || overlap(src, r.dst)) { ok = false; break; }
         oldest_unknown = i;
       }
       newer += r.threads;
@@ -1026,6 +1031,7 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "stream_hint") c->stream_hint = value;
   else if (n == "memo_px") c->memo_px = value;
   else if (n == "pdl") c->pdl = value != 0;
+  else if (n == "blockhash_rows") c->blockhash_rows = std::max(0, std::min(value, 8));
   else if (n == "tile_gather_path") c->tg_path = value;
   else if (n == "tile_gather_cfg") c->tg_cfg = value;
   else if (n == "tile_gather_ctas") c->tg_ctas = value;
@@ -1381,7 +1387,6 @@ int b200vfx_blockhash_sums_batch(b200vfx_ctx *c, int fmt, int width, int height,
   const int nbins = hw * hh * n_frames;
   const size_t nb = sizeof(uint32_t) * (size_t)nbins;
   if (!sums_dev) { CU(c, c->stage_sums.reserve(nb)); d_sums = (uint32_t *)c->stage_sums.p; }
-  pdl_admit(false, st, Span{0, 0}, Span{0, 0});
   // rows per CTA: aim for >= ~8 CTAs per SM over the whole batch
   int rows_per_cta = bh;
   const long ctas_target = (long)c->sm_count * 8;
@@ -1392,17 +1397,40 @@ int b200vfx_blockhash_sums_batch(b200vfx_ctx *c, int fmt, int width, int height,
   for (int f = 0; f < n_frames; f++) vec = vec && aligned(fr.src[f], fr.stride[f], 16);
   if (vec && c->blockhash_tma && n_frames == 1 && bw * 4 <= kBlockhashTileBytes) {
     // TMA-fed variant (option "blockhash_tma"): whole tile in flight through cp.async.bulk, tile <= 32 KB
+    pdl_admit(false, st, Span{0, 0}, Span{0, 0});
     CU(c, cudaMemsetAsync(d_sums, 0, nb, st));
     const int rows_tma = std::max(1, std::min(rows_per_cta, kBlockhashTileBytes / (bw * 4)));
     dim3 g2((unsigned)hw, (unsigned)hh, (unsigned)ceil_div(bh, rows_tma));
     blockhash_sums_tma_kernel<<<g2, 128, (size_t)rows_tma * bw * 4, st>>>(fr.src[0], fr.stride[0], bw, bh, hw, rows_tma, d_sums);
   } else {
     uint32_t *partials = nullptr; unsigned *ticket = nullptr;
-    if (int rc = reduce_scratch(c, (size_t)nbins * zchunks * 4, &ticket, &partials)) return rc;
+    const bool rows_kernel = vec && hw <= kBlockhashRowsMaxHW && c->blockhash_rows;
+    int zc = zchunks, rpc = rows_per_cta;
+    if (rows_kernel) {   // whole rows per CTA, two CTAs per SM in ONE wave
+      const int want = std::max(1, std::min(bh, (2 * c->sm_count / c->blockhash_rows) / std::max(1, hh * n_frames)));
+      rpc = ceil_div(bh, want);
+      zc = ceil_div(bh, rpc);
+    }
+    if (int rc = reduce_scratch(c, (size_t)nbins * zc * 4, &ticket, &partials)) return rc;
     if (st != c->stream()) if (int rc = order_after_ctx_stream(c, st)) return rc;   // one launch of this context at a time uses the scratch
-    if (vec) blockhash_sums_kernel<4, true><<<grid, 128, 0, st>>>(fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums, partials, ticket);
-    else if (bpp == 4) blockhash_sums_kernel<4, false><<<grid, 128, 0, st>>>(fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums, partials, ticket);
-    else blockhash_sums_kernel<3, false><<<grid, 128, 0, st>>>(fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums, partials, ticket);
+    // consecutive frames overlap (programmatic dependent launch): the kernel reads its frames while the previous launch
+    // drains and touches scratch / sums only after griddepcontrol.wait.  Frames staged from the host follow a copy: plain.
+    Span src_hull{0, 0};
+    for (int f = 0; f < n_frames; f++) {
+      const Span sp = span_of(fr.src[f], fr.stride[f], row, height);
+      src_hull = f == 0 ? sp : Span{std::min(src_hull.lo, sp.lo), std::max(src_hull.hi, sp.hi)};
+    }
+    const bool pdl = pdl_admit(c->pdl && all_dev && st == c->stream(), st, src_hull, span_of(d_sums, (long)nb, nb, 1), true);
+    if (rows_kernel) {
+      const int n4row = (bw >> 2) * hw;
+      dim3 gr((unsigned)zc, (unsigned)hh, (unsigned)n_frames);
+      if (n4row <= 256) CU(c, launch_k(pdl, blockhash_rows_kernel<1>, gr, dim3(256), 0, st, fr, zc, bw, bh, hw, hh, rpc, d_sums, partials, ticket));
+      else if (n4row <= 512) CU(c, launch_k(pdl, blockhash_rows_kernel<2>, gr, dim3(256), 0, st, fr, zc, bw, bh, hw, hh, rpc, d_sums, partials, ticket));
+      else CU(c, launch_k(pdl, blockhash_rows_kernel<4>, gr, dim3(256), 0, st, fr, zc, bw, bh, hw, hh, rpc, d_sums, partials, ticket));
+    } else if (vec) CU(c, launch_k(pdl, blockhash_sums_kernel<4, true>, grid, dim3(128), 0, st, fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums, partials, ticket));
+    else if (bpp == 4) CU(c, launch_k(pdl, blockhash_sums_kernel<4, false>, grid, dim3(128), 0, st, fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums, partials, ticket));
+    else CU(c, launch_k(pdl, blockhash_sums_kernel<3, false>, grid, dim3(128), 0, st, fr, zchunks, bw, bh, hw, hh, rows_per_cta, d_sums, partials, ticket));
+    pdl_note_linger(st);   // every CTA passes griddepcontrol.wait before it retires
   }
   c->launches++;
   CU(c, cudaGetLastError());
@@ -1897,7 +1925,10 @@ int b200vfx_colordetect_histogram(b200vfx_ctx *c, int fmt, int width, int height
   const size_t nb = sizeof(uint32_t) * kColorDetectBins;
   if (!hist_dev) { CU(c, c->stage_sums.reserve(nb)); d_hist = (uint32_t *)c->stage_sums.p; }
   if (((uintptr_t)d_hist % 4) != 0) return fail(c, B200VFX_ERR_INVALID, "colordetect: histogram pointer is not 4-byte aligned");
-  pdl_admit(false, st, Span{0, 0}, Span{0, 0});
+  // consecutive frames overlap: the kernel reads the plane while the previous launch drains, histogram and counters after
+  // its griddepcontrol.wait.  A frame staged from the host follows a copy: plain launch.
+  const bool pdl = pdl_admit(c->pdl && src_dev && nsamples > 0 && st == c->stream(), st, Span{(uintptr_t)d_src, (uintptr_t)d_src + plane_bytes},
+                             span_of(d_hist, (long)nb, nb, 1), true);
   unsigned *gsync = nullptr;
   if (int rc = reduce_scratch(c, 0, &gsync, nullptr)) return rc;
   gsync += 4;                                                     // words 4,5: colordetect's counters (word 0: blockhash ticket)
@@ -1951,10 +1982,14 @@ int b200vfx_colordetect_histogram(b200vfx_ctx *c, int fmt, int width, int height
     grid -= grid % cl;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kColorDetectThreads); cfg.dynamicSmemBytes = nb; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    pdl_note_threads(st, (long long)grid * kColorDetectThreads);
+    pdl_note_linger(st);   // every CTA passes griddepcontrol.wait before it retires
     CU(c, cudaLaunchKernelEx(&cfg, k, d_src, nsamples, quality, d_hist, gsync));
     c->launches++;
     CU(c, cudaGetLastError());

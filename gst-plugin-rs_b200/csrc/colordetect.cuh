@@ -18,14 +18,16 @@
 //   quality == 1, 4-byte pixels, 16-byte aligned plane: every thread streams 4 x uint4 (16 pixels, 64 KB in flight
 //     per SM -- one CTA per SM has to cover the DRAM latency alone);
 //   otherwise: lane-consecutive samples, one 4-byte (or 3 x 1-byte) load each.
-// ONE launch per frame: every CTA first zeroes its slice of the global histogram and arrives at a grid-wide counter; the
-// wait for that counter sits right before the global atomics, i.e. after the whole pixel pass, where it costs nothing.
+// ONE launch per frame: after its pixel pass every CTA zeroes its slice of the global histogram and arrives at a grid-wide
+// counter; the CTAs wait for that counter right before the global atomics (they finish the pixel pass together).
 // (All CTAs of the grid are co-resident by construction -- the launcher caps the grid at the occupancy maximum -- so the
 // spin cannot deadlock.)  The last CTA to retire resets the two counters for the next launch.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "kernels.cuh"
 
 namespace b200vfx {
 
@@ -73,16 +75,10 @@ colordetect_hist_kernel(const uint8_t *__restrict__ plane, long long nsamples, i
                         unsigned *__restrict__ gsync) {   // gsync[0]: CTAs that have zeroed their slice, gsync[1]: CTAs retired
   using F = CdFmt<FMT>;
   extern __shared__ __align__(16) uint32_t sh_hist[];
+  pdl_trigger();   // the next launch may be scheduled; its CTAs take the SMs as ours retire
   for (int i = threadIdx.x; i < kColorDetectBins / 4; i += kColorDetectThreads)
     reinterpret_cast<uint4 *>(sh_hist)[i] = make_uint4(0u, 0u, 0u, 0u);
-  {  // this CTA's slice of the global histogram
-    const int per = (kColorDetectBins + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int lo = (int)blockIdx.x * per, hi = min(kColorDetectBins, lo + per);
-    for (int i = lo + (int)threadIdx.x; i < hi; i += kColorDetectThreads) hist[i] = 0u;
-  }
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(gsync, 1u);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int U = 4;
   if (MODE == 2) {
@@ -149,9 +145,20 @@ colordetect_hist_kernel(const uint8_t *__restrict__ plane, long long nsamples, i
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned csize = cluster.num_blocks(), crank = cluster.block_rank();
+  // everything up to here only read the plane and wrote shared memory: with programmatic dependent launch it ran while the
+  // previous launch on the stream drained.  The global histogram and the counters are touched after that launch completed.
+  pdl_wait_prior();
+  {  // this CTA's slice of the global histogram
+    const int per = (kColorDetectBins + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int lo = (int)blockIdx.x * per, hi = min(kColorDetectBins, lo + per);
+    for (int i = lo + (int)threadIdx.x; i < hi; i += kColorDetectThreads) hist[i] = 0u;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(gsync, 1u);
   cluster.sync();
-  if (threadIdx.x == 0) {   // every CTA has zeroed its slice (they did so before their pixel pass: no waiting in practice)
-    while (*(volatile unsigned *)gsync < gridDim.x) __nanosleep(64);
+  if (threadIdx.x == 0) {   // every CTA has zeroed its slice (the CTAs finish their pixel pass at about the same time)
+    while (*(volatile unsigned *)gsync < gridDim.x) __nanosleep(32);
     __threadfence();
   }
   __syncthreads();

@@ -650,6 +650,7 @@ template <int BPP, bool VEC>
 __global__ void __launch_bounds__(128) blockhash_sums_kernel(BlockhashFrames fr, int zchunks, int bw, int bh, int hw, int hh,
                                                              int rows_per_cta, uint32_t *__restrict__ sums,
                                                              uint32_t *__restrict__ partials, unsigned *__restrict__ ticket) {
+  pdl_trigger();   // the next launch may start reading ITS frame; whatever it writes is ordered by the wait below
   const int bx = blockIdx.x, by = blockIdx.y;
   const int f = (int)blockIdx.z / zchunks, chunk = (int)blockIdx.z - f * zchunks;
   const uint8_t *__restrict__ src = fr.src[f];
@@ -689,6 +690,9 @@ __global__ void __launch_bounds__(128) blockhash_sums_kernel(BlockhashFrames fr,
   }
   __shared__ uint32_t wsum[4];
   __shared__ int s_last;
+  // launched with programmatic serialisation: the frame was read while the previous launch on the stream drained; the
+  // shared scratch (partials, ticket) and the sums are touched only once that launch has completed
+  pdl_wait_prior();
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -713,6 +717,89 @@ __global__ void __launch_bounds__(128) blockhash_sums_kernel(BlockhashFrames fr,
       sums[i] = t;
     }
     if (threadIdx.x == 0) *ticket = 0u;            // re-armed for the next launch
+  }
+}
+
+// Row-streaming variant for 16-byte aligned RGBA: a CTA owns `rows_per_cta` WHOLE rows inside one row of hash blocks and
+// reads them left to right -- every DRAM page is read once, sequentially, by one CTA -- instead of one CTA per hash block
+// reading bw-pixel row segments 'stride' bytes apart.  A thread keeps K fixed columns (16 bytes each, one hash block each)
+// over 16/K rows per batch = 16 independent loads in flight; per-column sums go to shared bins once per column group
+// (match.any + redux: one shared atomic per distinct block in a warp).  grid = (chunks, hh, frames), 256 threads.
+constexpr int kBlockhashRowsMaxHW = 256;
+template <int K>
+__global__ void __launch_bounds__(256) blockhash_rows_kernel(BlockhashFrames fr, int zchunks, int bw, int bh, int hw, int hh,
+                                                             int rows_per_cta, uint32_t *__restrict__ sums,
+                                                             uint32_t *__restrict__ partials, unsigned *__restrict__ ticket) {
+  constexpr int U = 16 / K;
+  __shared__ uint32_t bins[kBlockhashRowsMaxHW];
+  __shared__ int s_last;
+  pdl_trigger();
+  const int chunk = blockIdx.x, by = blockIdx.y, f = blockIdx.z, tid = threadIdx.x, lane = tid & 31;
+  const uint8_t *__restrict__ src = fr.src[f];
+  const long stride = fr.stride[f];
+  const int y0 = by * bh + chunk * rows_per_cta;
+  const int y1 = min(y0 + rows_per_cta, (by + 1) * bh);
+  for (int i = tid; i < hw; i += 256) bins[i] = 0u;
+  __syncthreads();
+  const int n4blk = bw >> 2, n4row = n4blk * hw;
+  const uint4 black = make_uint4(0xFF000000u, 0xFF000000u, 0xFF000000u, 0xFF000000u);   // opaque black: contributes 0
+  for (int i0 = 0; i0 < n4row; i0 += 256 * K) {
+    uint32_t acc[K];
+    bool okc[K];
+    const uint8_t *col[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int i = i0 + tid + 256 * k;
+      acc[k] = 0u; okc[k] = i < n4row;
+      col[k] = src + (size_t)(okc[k] ? i : 0) * 16;
+    }
+    for (int y = y0; y < y1; y += U) {
+      uint4 q[U][K];
+#pragma unroll
+      for (int r = 0; r < U; r++)
+#pragma unroll
+        for (int k = 0; k < K; k++)
+          q[r][k] = (okc[k] && y + r < y1) ? __ldcs(reinterpret_cast<const uint4 *>(col[k] + (size_t)(y + r) * stride)) : black;
+#pragma unroll
+      for (int r = 0; r < U; r++)
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const uint4 v = q[r][k];
+          acc[k] += (v.x >> 24) ? __dp4a(v.x, 0x00010101u, 0u) : 765u;   // A==0 counts as white (765)
+          acc[k] += (v.y >> 24) ? __dp4a(v.y, 0x00010101u, 0u) : 765u;
+          acc[k] += (v.z >> 24) ? __dp4a(v.z, 0x00010101u, 0u) : 765u;
+          acc[k] += (v.w >> 24) ? __dp4a(v.w, 0x00010101u, 0u) : 765u;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int b = okc[k] ? (i0 + tid + 256 * k) / n4blk : -1;
+      const unsigned grp = __match_any_sync(0xFFFFFFFFu, b);
+      const uint32_t t = __reduce_add_sync(grp, acc[k]);
+      if (b >= 0 && lane == __ffs(grp) - 1) atomicAdd(&bins[b], t);
+    }
+  }
+  __syncthreads();
+  pdl_wait_prior();                                // scratch and sums: only after the previous launch has completed
+  const int nbins = hw * hh;                       // per frame
+  // partial of (frame f, chunk, bin): the layout blockhash_sums_kernel uses
+  for (int i = tid; i < hw; i += 256) partials[((size_t)f * zchunks + chunk) * nbins + by * hw + i] = bins[i];
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y * gridDim.z - 1u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const int nframes = (int)gridDim.z;
+    for (int i = tid; i < nframes * nbins; i += 256) {
+      const int ff = i / nbins, bin = i - ff * nbins;
+      uint32_t t = 0;
+      for (int c = 0; c < zchunks; c++) t += __ldcg(partials + ((size_t)ff * zchunks + c) * nbins + bin);
+      sums[i] = t;
+    }
+    if (tid == 0) *ticket = 0u;                    // re-armed for the next launch
   }
 }
 

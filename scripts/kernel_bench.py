@@ -177,7 +177,7 @@ def main():
             t = graph_time(in_graph(lambda i: ctx.blockhash_sums("RGBA", W, H, frames[i % RING], 4 * W, sums)))
             report("blockhash_sums_rgba", t, W * H * 4, content="noise", frame="3840x2160", note="CUDA-graph replay: device time per launch")
             sums2g = torch.zeros(128, dtype=torch.int32, device="cuda")
-            t = graph_time(in_graph(lambda i: ctx.blockhash_sums_batch("RGBA", W, H, [frames[i % RING], frames[(i + 1) % RING]], [4 * W, 4 * W], sums2g)))
+            t = graph_time(in_graph(lambda i: ctx.blockhash_sums_batch("RGBA", W, H, [frames[(2 * i) % RING], frames[(2 * i + 1) % RING]], [4 * W, 4 * W], sums2g)))
             report("blockhash_sums_rgba_batch2", t, 2 * W * H * 4, content="noise", frame="2 x 3840x2160", note="CUDA-graph replay: device time per launch")
             histg = torch.zeros(32768, dtype=torch.int32, device="cuda")
             for q in (10, 1):
@@ -188,7 +188,7 @@ def main():
             print(json.dumps({"graph_timing_error": str(exc)[:200]}), flush=True)
             ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         sums2 = torch.zeros(128, dtype=torch.int32, device="cuda")
-        t = timeit(lambda i: ctx.blockhash_sums_batch("RGBA", W, H, [frames[i % RING], frames[(i + 1) % RING]], [4 * W, 4 * W], sums2), args.iters)
+        t = timeit(lambda i: ctx.blockhash_sums_batch("RGBA", W, H, [frames[(2 * i) % RING], frames[(2 * i + 1) % RING]], [4 * W, 4 * W], sums2), args.iters)
         report("blockhash_sums_rgba_batch2", t, 2 * W * H * 4, content="noise", frame="2 x 3840x2160", note="BASELINE config 4: both streams in one launch")
         m = torch.empty((1080, 1920), dtype=torch.uint8, device="cuda")
         t = timeit(lambda i: ctx.roundmask_generate(1920, 1080, 1920, 64, m), 20)

@@ -148,6 +148,39 @@ def test_gpu_histogram_device_pointers_unaligned_and_errors():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("quality", [1, 10])
+def test_gpu_histogram_back_to_back_launches_overlap_safely(quality):
+    """consecutive histogram launches overlap (the plane is read while the previous launch drains; the global histogram and
+    the counters are touched after griddepcontrol.wait): a long unsynchronised train over few histograms, and a plane that
+    the launch just before produced, stay exact"""
+    torch = pytest.importorskip("torch")
+    w, h = 1920, 1080
+    with b200vfx.Context(0) as ctx:
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        frames = [synth.frame_noise("RGBA", w, h, 70 + i) if i % 2 else synth.frame_natural("RGBA", w, h, 70 + i) for i in range(4)]
+        exp = [orc.colordetect_histogram("RGBA", w, h, f, quality) for f in frames]
+        dev = [torch.from_numpy(f).cuda() for f in frames]
+        hists = [torch.full((32768,), 9, dtype=torch.int32, device="cuda") for _ in range(3)]
+        for i in range(40):
+            ctx.colordetect_histogram("RGBA", w, h, dev[i % 4], 4 * w, quality, hists[i % 3])
+        torch.cuda.synchronize()
+        for k in range(3):
+            last = max(i for i in range(40) if i % 3 == k)
+            assert (hists[k].cpu().numpy().view(np.uint32) == exp[last % 4]).all(), k
+        cube = orc.cube_parse(synth.cube_text_3d(9, "mix"))
+        ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+        want = [orc.colordetect_histogram("RGBA", w, h, orc.colorlut_apply(cube, "RGBA", w, h, f), quality) for f in frames]
+        out = torch.empty_like(dev[0])
+        got = [torch.zeros(32768, dtype=torch.int32, device="cuda") for _ in range(12)]
+        for i in range(12):   # colorlut rewrites the plane the previous histogram launch is reading
+            ctx.colorlut_process("RGBA", w, h, dev[i % 4], 4 * w, out, 4 * w)
+            ctx.colordetect_histogram("RGBA", w, h, out, 4 * w, quality, got[i])
+        torch.cuda.synchronize()
+        for i in range(12):
+            assert (got[i].cpu().numpy().view(np.uint32) == want[i % 4]).all(), i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("quality", [1, 10])
 def test_gpu_histogram_4k_full_size(quality):
     """3840x2160 RGBA (the BASELINE frame shape): oracle equality plus the size-independent checksum
     sum(hist) == number of sampled pixels that pass the alpha / white test"""

@@ -16,11 +16,13 @@ def ctx():
     c.close()
 
 
-@pytest.mark.parametrize("tma", [1, 0])
+@pytest.mark.parametrize("variant", ["tma", "blocks", "rows", "rows_2_per_sm"])
 @pytest.mark.parametrize("w,h,pad", [(3840, 2160, 0), (7680, 4320, 0), (1920, 1080, 64), (64, 48, 0), (32, 8, 16), (4096, 16, 0)])
-def test_blockhash_tma_and_plain_variants(ctx, tma, w, h, pad):
+def test_blockhash_kernel_variants(ctx, variant, w, h, pad):
+    """the three decompositions of the block sums: TMA-fed tiles, one CTA per hash block, whole-row streaming CTAs"""
     torch = pytest.importorskip("torch")
-    ctx.set_option("blockhash_tma", tma)
+    ctx.set_option("blockhash_tma", 1 if variant == "tma" else 0)
+    ctx.set_option("blockhash_rows", {"rows": 2, "rows_2_per_sm": 1}.get(variant, 0))
     try:
         frame = synth.frame_noise("RGBA", w, h, 0x5EED0004, stride=4 * w + pad)
         frame[::5, 3:4 * w:28] = 0   # transparent pixels count as 765
@@ -36,7 +38,71 @@ def test_blockhash_tma_and_plain_variants(ctx, tma, w, h, pad):
         torch.cuda.synchronize()
         assert (ds.cpu().numpy().view(np.uint32) == exp).all()
     finally:
-        ctx.set_option("blockhash_tma", 1)
+        ctx.set_option("blockhash_tma", 0)
+        ctx.set_option("blockhash_rows", 2)
+
+
+@pytest.mark.parametrize("rows", [2, 1, 0])
+@pytest.mark.parametrize("w,h,hw,hh,n", [(3840, 2160, 16, 16, 1), (1920, 1080, 4, 4, 2), (640, 480, 16, 8, 3), (256, 256, 64, 64, 1),
+                                         (1280, 720, 80, 16, 2), (4096, 64, 256, 2, 1), (2048, 4, 512, 4, 1)])
+def test_blockhash_other_grids(ctx, rows, w, h, hw, hh, n):
+    """hash grids other than 8x8 (image_hasher's hash_size), batches, block widths down to one 16-byte vector; a grid wider
+    than the row kernel's shared bins falls back to the per-block kernel"""
+    torch = pytest.importorskip("torch")
+    ctx.set_option("blockhash_tma", 0)
+    ctx.set_option("blockhash_rows", rows)
+    try:
+        frames = [synth.frame_noise("RGBA", w, h, 900 + i) for i in range(n)]
+        frames[0][::3, 3::20] = 0
+        exp = np.concatenate([orc.blockhash_sums("RGBA", w, h, f, hw, hh) for f in frames])
+        dev = [torch.from_numpy(f).cuda() for f in frames]
+        ds = torch.zeros(hw * hh * n, dtype=torch.int32, device="cuda")
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        for _ in range(2):
+            ctx.blockhash_sums_batch("RGBA", w, h, dev, [4 * w] * n, ds, hw=hw, hh=hh)
+        torch.cuda.synchronize()
+        assert (ds.cpu().numpy().view(np.uint32) == exp).all()
+    finally:
+        ctx.set_option("blockhash_tma", 0)
+        ctx.set_option("blockhash_rows", 2)
+
+
+@pytest.mark.parametrize("rows", [2, 1, 0])
+def test_blockhash_back_to_back_launches_overlap_safely(ctx, rows):
+    """consecutive block-sum launches overlap (programmatic dependent launch: the frame is read while the previous launch
+    drains, scratch and sums are touched after griddepcontrol.wait): results of a long unsynchronised train, and a frame
+    produced by the launch just before (colorlut -> blockhash on its output) must still be exact"""
+    torch = pytest.importorskip("torch")
+    w, h = 1920, 1080
+    ctx.set_option("blockhash_tma", 0)
+    ctx.set_option("blockhash_rows", rows)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        frames = [synth.frame_noise("RGBA", w, h, 300 + i) for i in range(4)]
+        exp = [orc.blockhash_sums("RGBA", w, h, f) for f in frames]
+        dev = [torch.from_numpy(f).cuda() for f in frames]
+        sums = [torch.zeros(64, dtype=torch.int32, device="cuda") for _ in range(5)]
+        for i in range(60):
+            ctx.blockhash_sums("RGBA", w, h, dev[i % 4], 4 * w, sums[i % 5])
+        torch.cuda.synchronize()
+        for k in range(5):
+            last = max(i for i in range(60) if i % 5 == k)
+            assert (sums[k].cpu().numpy().view(np.uint32) == exp[last % 4]).all(), k
+        # producer -> consumer: the frame being hashed is written by the kernel launched just before
+        cube = orc.cube_parse(synth.cube_text_3d(9, "mix"))
+        ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+        graded = [orc.colorlut_apply(cube, "RGBA", w, h, f) for f in frames]
+        exp2 = [orc.blockhash_sums("RGBA", w, h, g) for g in graded]
+        out = torch.empty_like(dev[0])
+        got = [torch.zeros(64, dtype=torch.int32, device="cuda") for _ in range(12)]
+        for i in range(12):
+            ctx.colorlut_process("RGBA", w, h, dev[i % 4], 4 * w, out, 4 * w)   # overwrites the frame the previous hash is reading
+            ctx.blockhash_sums("RGBA", w, h, out, 4 * w, got[i])
+        torch.cuda.synchronize()
+        for i in range(12):
+            assert (got[i].cpu().numpy().view(np.uint32) == exp2[i % 4]).all(), i
+    finally:
+        ctx.set_option("blockhash_rows", 2)
 
 
 def test_contexts_on_every_visible_device():
