@@ -1064,7 +1064,7 @@ void b200vfx_host_free(void *p) { if (p) cudaFreeHost(p); }
 int b200vfx_debug_pdl_admit(void *stream_key, uintptr_t src_lo, uintptr_t src_hi, uintptr_t dst_lo, uintptr_t dst_hi,
                             int want_pdl, long long threads, int lingers) {
   cudaStream_t st = (cudaStream_t)stream_key;
-  const bool ok = pdl_admit(want_pdl != 0, st, Span{src_lo, src_hi}, Span{dst_lo, dst_hi});
+  const bool ok = pdl_admit(want_pdl != 0, st, Span{src_lo, src_hi}, Span{dst_lo, dst_hi}, (lingers & 2) != 0);
   pdl_note_threads(st, threads);
   if (lingers) pdl_note_linger(st);
   return ok ? 1 : 0;

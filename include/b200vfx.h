@@ -300,7 +300,9 @@ int b200vfx_colorlut_process_tile_gather_mc(b200vfx_ctx *ctx, int fmt, int width
 /* ---- test hooks (host logic only, no GPU needed) ---------------------------------------------------------------
  * The admission rule for overlapping consecutive frames (programmatic dependent launch): would a launch with these
  * source / destination byte ranges be allowed to start before our earlier launches on `stream_key` have completed?
- * Records the launch exactly like a real one (threads = grid x block size, lingers = it ends on griddepcontrol.wait).
+ * Records the launch exactly like a real one (threads = grid x block size, lingers = it ends on griddepcontrol.wait;
+ * lingers = 3: it passes griddepcontrol.wait BEFORE its first write to dst -- the reductions -- so only its early reads of
+ * src can race with earlier launches).
  * b200vfx_debug_pdl_reset forgets the stream (what a stream synchronisation does). */
 int b200vfx_debug_pdl_admit(void *stream_key, uintptr_t src_lo, uintptr_t src_hi, uintptr_t dst_lo, uintptr_t dst_hi,
                             int want_pdl, long long threads, int lingers);

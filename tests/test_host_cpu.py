@@ -296,5 +296,19 @@ def test_pdl_admission_rule():
     assert _admit(L, key, buf(2), buf(3), huge, True) == 1
     assert _admit(L, key, buf(4), buf(1), huge, True) == 1            # two launches back: cannot still be resident
     assert _admit(L, key, buf(6), buf(1), huge, True) == 0            # the previous launch itself
-    for k in range(0x1000, 0x1009):
+    # 5. reductions (block sums, colordetect): the kernel writes only after its griddepcontrol.wait -> rewriting the result
+    #    buffer of the launch before is fine, reading a frame that launch is still writing is not; and a later launch
+    #    that overwrites the frame a reduction may still be reading is refused
+    key = 0x1009
+    L.b200vfx_debug_pdl_reset(key)
+    red = 148 * 256
+    sums = (0x90000000, 0x90000100)
+    assert L.b200vfx_debug_pdl_admit(key, *buf(0), *sums, 1, red, 3) == 1
+    assert L.b200vfx_debug_pdl_admit(key, *buf(1), *sums, 1, red, 3) == 1      # same result buffer: written after the wait
+    assert L.b200vfx_debug_pdl_admit(key, *buf(2), *sums, 1, red, 1) == 0      # an ordinary kernel may not
+    assert _admit(L, key, buf(3), buf(4), capped, True) == 1                    # colorlut writes buf(4) ...
+    assert L.b200vfx_debug_pdl_admit(key, *buf(4), *sums, 1, red, 3) == 0      # ... a reduction reading it waits
+    assert L.b200vfx_debug_pdl_admit(key, *buf(5), *sums, 1, red, 3) == 1
+    assert _admit(L, key, buf(6), buf(5), capped, True) == 0                    # overwriting the frame being reduced
+    for k in range(0x1000, 0x100A):
         L.b200vfx_debug_pdl_reset(k)
