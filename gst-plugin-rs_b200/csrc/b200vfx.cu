@@ -70,6 +70,7 @@ struct b200vfx_ctx {
   std::vector<cudaEvent_t> ev_in, ev_k;
   cudaEvent_t ev_order = nullptr;      // orders the internal pipeline stream after the context stream (mixed host/device calls)
   DevBuf stage_in, stage_out, stage_sums;
+  uint8_t *result_pinned = nullptr;   // small results (block sums, resized luma, histogram) come back through pinned memory
   DevBuf reduce_scratch;               // single-launch reductions: [0,64) two grid counters (kept zero between launches), then partials
   int chunk_rows = 0;
   int sm_count = 148;
@@ -993,6 +994,7 @@ void b200vfx_ctx_destroy(b200vfx_ctx *c) {
   if (c->ev_order) cudaEventDestroy(c->ev_order);
   for (auto &kv : c->taps_cache) { cudaFree(kv.second.taps); cudaFree(kv.second.meta); }
   c->stage_in.release(); c->stage_out.release(); c->stage_sums.release(); c->reduce_scratch.release();
+  if (c->result_pinned) { cudaFreeHost(c->result_pinned); c->result_pinned = nullptr; }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_k) cudaStreamDestroy(c->s_k);
@@ -1340,6 +1342,22 @@ int b200vfx_roundmask_generate(b200vfx_ctx *c, int width, int height, int stride
 }
 
 // ---- videocompare / blockhash -----------------------------------------------------------------
+// device -> host of a small result + stream synchronisation.  A copy into pageable memory makes the driver stage and
+// synchronise internally (~25 us per call); through the context's pinned bounce buffer it is one DMA and one spin.
+constexpr size_t kResultPinnedBytes = 256 << 10;
+static int read_back_small(b200vfx_ctx *c, void *host_dst, const void *dev_src, size_t n, cudaStream_t st) {
+  if (n > kResultPinnedBytes) {
+    CU(c, cudaMemcpyAsync(host_dst, dev_src, n, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    return 0;
+  }
+  if (!c->result_pinned) CU(c, cudaHostAlloc((void **)&c->result_pinned, kResultPinnedBytes, cudaHostAllocDefault));
+  CU(c, cudaMemcpyAsync(c->result_pinned, dev_src, n, cudaMemcpyDeviceToHost, st));
+  CU(c, cudaStreamSynchronize(st));
+  std::memcpy(host_dst, c->result_pinned, n);
+  return 0;
+}
+
 int b200vfx_blockhash_sums_batch(b200vfx_ctx *c, int fmt, int width, int height, int n_frames, const void *const *srcs,
                                  const int *strides, int hw, int hh, uint32_t *sums) {
   if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
@@ -1435,8 +1453,7 @@ int b200vfx_blockhash_sums_batch(b200vfx_ctx *c, int fmt, int width, int height,
   c->launches++;
   CU(c, cudaGetLastError());
   if (!sums_dev) {
-    CU(c, cudaMemcpyAsync(sums, d_sums, nb, cudaMemcpyDeviceToHost, st));
-    CU(c, cudaStreamSynchronize(st));
+    if (int rc = read_back_small(c, sums, d_sums, nb, st)) return rc;
   } else if (!all_dev) {
     CU(c, cudaStreamSynchronize(st));
   }
@@ -1802,17 +1819,19 @@ int b200vfx_luma_resize(b200vfx_ctx *c, int fmt, int width, int height, const vo
     if (int rc = taps_for(height, nh, &tv)) return rc;
     if (int rc = taps_for(width, nw, &th)) return rc;
     float *d_tmp = (float *)base;
-    dim3 grid((unsigned)ceil_div(width, 128), (unsigned)nh);
+    dim3 grid((unsigned)ceil_div(width, kVresCols), (unsigned)nh);
     const bool al = bpp == 4 && aligned(d_src, d_stride, 4);
-    if (al) luma_vresize_kernel<4><<<grid, 128, 0, st>>>(d_src, d_stride, width, tv.taps, tv.meta, tv.max_taps, d_tmp);
-    else if (bpp == 4) luma_vresize_bytes_kernel<4><<<grid, 128, 0, st>>>(d_src, d_stride, width, tv.taps, tv.meta, tv.max_taps, d_tmp);
-    else luma_vresize_kernel<3><<<grid, 128, 0, st>>>(d_src, d_stride, width, tv.taps, tv.meta, tv.max_taps, d_tmp);
-    luma_hresize_kernel<<<ceil_div(nw * nh, 32), 32, 0, st>>>(d_tmp, width, nw, nh, th.taps, th.meta, th.max_taps, d_out);
+    if (al) luma_vresize_kernel<4, true><<<grid, kVresThreads, 0, st>>>(d_src, d_stride, width, tv.taps, tv.meta, tv.max_taps, d_tmp);
+    else if (bpp == 4) luma_vresize_kernel<4, false><<<grid, kVresThreads, 0, st>>>(d_src, d_stride, width, tv.taps, tv.meta, tv.max_taps, d_tmp);
+    else luma_vresize_kernel<3, false><<<grid, kVresThreads, 0, st>>>(d_src, d_stride, width, tv.taps, tv.meta, tv.max_taps, d_tmp);
+    luma_hresize_kernel<<<(unsigned)(nw * nh), 256, 0, st>>>(d_tmp, width, nw, nh, th.taps, th.meta, th.max_taps, d_out);
     c->launches += 2;
   }
   CU(c, cudaGetLastError());
-  CU(c, cudaMemcpyAsync(out, d_out, (size_t)nw * nh, cudaMemcpyDefault, st));
-  CU(c, cudaStreamSynchronize(st));
+  if (is_device_ptr(out)) {
+    CU(c, cudaMemcpyAsync(out, d_out, (size_t)nw * nh, cudaMemcpyDeviceToDevice, st));
+    CU(c, cudaStreamSynchronize(st));
+  } else if (int rc = read_back_small(c, out, d_out, (size_t)nw * nh, st)) return rc;
   pdl_forget(st);
   return 0;
 }
@@ -1995,8 +2014,7 @@ int b200vfx_colordetect_histogram(b200vfx_ctx *c, int fmt, int width, int height
     CU(c, cudaGetLastError());
   }
   if (!hist_dev) {
-    CU(c, cudaMemcpyAsync(hist, d_hist, nb, cudaMemcpyDeviceToHost, st));
-    CU(c, cudaStreamSynchronize(st));
+    if (int rc = read_back_small(c, hist, d_hist, nb, st)) return rc;
   } else if (!src_dev) {
     CU(c, cudaStreamSynchronize(st));
   }

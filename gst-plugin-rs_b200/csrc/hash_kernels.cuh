@@ -4,8 +4,7 @@
 //   * Mean / Gradient / VertGradient / DoubleGradient: image::imageops::grayscale + imageops::resize(Lanczos3) to
 //     8x8 / 9x8 / 8x9 / 5x5.  A 4K frame shrinks by 270-480x, so every output sample is a weighted sum of ~1600 (vertical)
 //     resp. ~2900 (horizontal) source samples accumulated IN SOURCE ORDER in f32 (t += v * w, unfused): the serial chain
-//     per output sample is part of the result and is kept; the parallelism is across the W x new_h (vertical pass) and
-//     new_w x new_h (horizontal pass) independent chains.  The normalised tap weights are computed on the host (they
+//     of additions per output sample is part of the result and is kept; the products are formed in parallel.  The normalised tap weights are computed on the host (they
 //     need libm's sinf, which the device's sinf does not reproduce bit for bit) and uploaded once per frame size.
 //   * Blockhash for frames whose size is not a multiple of the hash grid: block index by the reference's f32 division.
 //     The reference accumulates the block sums in f32 in raster order; while a block's sum stays below 2^24 that is exact
@@ -18,93 +17,110 @@ namespace b200vfx {
 
 __device__ __forceinline__ unsigned luma_of(unsigned r, unsigned g, unsigned b) { return (2126u * r + 7152u * g + 722u * b) / 10000u; }
 
-// vertical pass: tmp[oy][x] = sum_i luma(x, left[oy] + i) * w[oy][i].  taps: [nh][max_taps] floats, meta[oy] = {left, n}.
-template <int BPP>
-__global__ void __launch_bounds__(128) luma_vresize_kernel(const uint8_t *__restrict__ src, long stride, int width,
-                                                          const float *__restrict__ taps, const int2 *__restrict__ meta,
-                                                          int max_taps, float *__restrict__ tmp) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
-  if (x >= width) return;
-  const int2 m = meta[oy];
-  const float *w = taps + (size_t)oy * max_taps;
-  const uint8_t *p = src + (size_t)m.x * stride + (size_t)x * BPP;
-  float t = 0.0f;
-  // U independent loads in flight, and the NEXT batch is requested before the current one is accumulated (there are only
-  // W x new_h threads -- ~1.6 warps per scheduler on a 4K frame -- so memory latency is hidden inside a thread or not at
-  // all); the accumulation itself stays strictly in source order
-  constexpr int U = 16;
-  auto fetch = [&](int i0, uint32_t (&raw)[U], float (&wt)[U]) {
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const uint8_t *q = p + (size_t)(i0 + u) * stride;
-      if (BPP == 4) raw[u] = __ldg(reinterpret_cast<const uint32_t *>(q));
-      else raw[u] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
-      wt[u] = __ldg(w + i0 + u);
-    }
-  };
-  int i = 0;
-  uint32_t cur[U], nxt[U];
-  float cw[U], nw[U];
-  if (U <= m.y) fetch(0, cur, cw);
-  for (; i + U <= m.y; i += U) {
-    const bool more = i + 2 * U <= m.y;
-    if (more) fetch(i + U, nxt, nw);
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const unsigned l = luma_of(cur[u] & 255u, (cur[u] >> 8) & 255u, (cur[u] >> 16) & 255u);
-      t = __fadd_rn(t, __fmul_rn((float)l, cw[u]));
-    }
-    if (more) {
-#pragma unroll
-      for (int u = 0; u < U; u++) { cur[u] = nxt[u]; cw[u] = nw[u]; }
-    }
-  }
-  for (; i < m.y; i++) {
-    const uint8_t *q = p + (size_t)i * stride;
-    const unsigned l = (BPP == 4) ? luma_of(q[0], q[1], q[2]) : luma_of(q[0], q[1], q[2]);
-    t = __fadd_rn(t, __fmul_rn((float)l, __ldg(w + i)));
-  }
-  tmp[(size_t)oy * width + x] = t;
+// 0..255 -> f32 without the conversion pipe: 0x4B000000 | l is the float 2^23 + l, the subtraction is exact
+__device__ __forceinline__ float small_uint_as_float(unsigned l) { return __fsub_rn(__uint_as_float(0x4B000000u | l), 8388608.0f); }
+
+// vertical pass: tmp[oy][x] = sum_i luma(x, left[oy] + i) * w[oy][i], the additions IN ORDER.  taps: [nh][max_taps] floats,
+// meta[oy] = {left, n}.  Only the chain of additions is serial: the products luma * w are rounded one by one and do not
+// depend on each other.  A CTA owns 64 columns of one output row; all 256 threads fetch a 64-row x 64-column block of
+// the window (next block already in flight), turn it into products in shared memory, then 64 threads run the 64
+// additions of their column in source order.  (Round 2's first version gave every chain its own thread: ~1.6 warps per
+// scheduler, latency-bound at 100-240 us per 4K frame.)
+constexpr int kVresCols = 64, kVresRows = 64, kVresThreads = 256, kVresPer = kVresCols * kVresRows / kVresThreads;
+// (2126 r + 7152 g + 722 b) / 10000 of a pixel word r | g << 8 | b << 16 in five instructions: the weights split into
+// bytes (2126 = 8 * 256 + 78, 7152 = 27 * 256 + 240, 722 = 2 * 256 + 210) for two dp4a, the division as a multiply-high
+__device__ __forceinline__ unsigned luma_of_word(uint32_t px) {
+  const unsigned s = __dp4a(px, 0x00021B08u, 0u) * 256u + __dp4a(px, 0x00D2F04Eu, 0u);   // <= 2 550 000
+  return __umulhi(s, 0xD1B71759u) >> 13;                                                  // s / 10000, exact for 32-bit s
 }
-// BPP == 4 rows that are not 4-byte aligned take the byte loads of the tail loop everywhere
-template <int BPP>
-__global__ void __launch_bounds__(128) luma_vresize_bytes_kernel(const uint8_t *__restrict__ src, long stride, int width,
-                                                                const float *__restrict__ taps, const int2 *__restrict__ meta,
-                                                                int max_taps, float *__restrict__ tmp) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
-  if (x >= width) return;
+template <int BPP, bool AL4>
+__global__ void __launch_bounds__(kVresThreads) luma_vresize_kernel(const uint8_t *__restrict__ src, long stride, int width,
+                                                                   const float *__restrict__ taps, const int2 *__restrict__ meta,
+                                                                   int max_taps, float *__restrict__ tmp) {
+  __shared__ float prod[kVresRows][kVresCols];
+  // thread (c, r0) handles column c of rows r0 * 16 .. r0 * 16 + 15 of every 64-row block
+  const int oy = blockIdx.y, c = threadIdx.x & (kVresCols - 1), r0 = (threadIdx.x / kVresCols) * kVresPer;
+  const int x = blockIdx.x * kVresCols + c;
+  const bool xin = x < width;
   const int2 m = meta[oy];
-  const float *w = taps + (size_t)oy * max_taps;
-  const uint8_t *p = src + (size_t)m.x * stride + (size_t)x * BPP;
+  const float *w = taps + (size_t)oy * max_taps + r0;
+  const uint8_t *p = src + (size_t)(m.x + r0) * stride + (size_t)(xin ? x : 0) * BPP;
+  const size_t block_step = (size_t)kVresRows * stride;
+  uint32_t raw[kVresPer];
+  auto load_px = [&](const uint8_t *q) -> uint32_t {
+    if (BPP == 4 && AL4) return __ldg(reinterpret_cast<const uint32_t *>(q));
+    return (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+  };
+  auto fetch = [&](int base) {   // rows base + r0 + k; p already points at row base + r0
+    const uint8_t *q = p;
+    if (xin && base + kVresRows <= m.y) {
+#pragma unroll
+      for (int k = 0; k < kVresPer; k++, q += stride) raw[k] = load_px(q);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kVresPer; k++, q += stride) raw[k] = (xin && base + r0 + k < m.y) ? load_px(q) : 0u;
+    }
+    p += block_step;
+  };
   float t = 0.0f;
-  for (int i = 0; i < m.y; i++) {
-    const uint8_t *q = p + (size_t)i * stride;
-    t = __fadd_rn(t, __fmul_rn((float)luma_of(q[0], q[1], q[2]), __ldg(w + i)));
+  fetch(0);
+  for (int base = 0; base < m.y; base += kVresRows) {
+    const float *wb = w + base;
+    if (base + kVresRows <= m.y) {
+#pragma unroll
+      for (int k = 0; k < kVresPer; k++)
+        prod[r0 + k][c] = __fmul_rn(small_uint_as_float(luma_of_word(raw[k] & 0x00FFFFFFu)), __ldg(wb + k));
+    } else {
+#pragma unroll
+      for (int k = 0; k < kVresPer; k++)
+        prod[r0 + k][c] = __fmul_rn(small_uint_as_float(luma_of_word(raw[k] & 0x00FFFFFFu)), base + r0 + k < m.y ? __ldg(wb + k) : 0.0f);
+    }
+    __syncthreads();
+    if (base + kVresRows < m.y) fetch(base + kVresRows);   // in flight while the chains below run
+    if (threadIdx.x < kVresCols) {
+      const int n = min(kVresRows, m.y - base);
+      int r = 0;
+      for (; r + 8 <= n; r += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) t = __fadd_rn(t, prod[r + u][c]);
+      }
+      for (; r < n; r++) t = __fadd_rn(t, prod[r][c]);
+    }
+    __syncthreads();
   }
-  tmp[(size_t)oy * width + x] = t;
+  if (threadIdx.x < kVresCols && xin) tmp[(size_t)oy * width + x] = t;
 }
 
-// horizontal pass on the f32 intermediate + clamp(0,255).round(): one thread per output sample (at most 81 of them)
-__global__ void luma_hresize_kernel(const float *__restrict__ tmp, int width, int nw, int nh, const float *__restrict__ taps,
-                                    const int2 *__restrict__ meta, int max_taps, uint8_t *__restrict__ out) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= nw * nh) return;
+// horizontal pass on the f32 intermediate + clamp(0,255).round(): one CTA per output sample (at most 81 of them); all
+// threads form the products of a block of taps in shared memory, one thread adds them up in source order
+constexpr int kHresBlock = 4096;
+__global__ void __launch_bounds__(256) luma_hresize_kernel(const float *__restrict__ tmp, int width, int nw, int nh,
+                                                          const float *__restrict__ taps, const int2 *__restrict__ meta,
+                                                          int max_taps, uint8_t *__restrict__ out) {
+  __shared__ float prod[kHresBlock];
+  const int o = blockIdx.x;
   const int oy = o / nw, ox = o - oy * nw;
   const int2 m = meta[ox];
   const float *w = taps + (size_t)ox * max_taps, *row = tmp + (size_t)oy * width + m.x;
   float t = 0.0f;
-  constexpr int U = 16;   // operands of the next 16 steps are loaded before the in-order accumulation of the current 16
-  int i = 0;
-  for (; i + U <= m.y; i += U) {
-    float a[U], b[U];
+  for (int base = 0; base < m.y; base += kHresBlock) {
+    const int n = min(kHresBlock, m.y - base);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) prod[j] = __fmul_rn(__ldg(row + base + j), __ldg(w + base + j));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int j = 0;
+      for (; j + 16 <= n; j += 16) {
 #pragma unroll
-    for (int u = 0; u < U; u++) { a[u] = __ldg(row + i + u); b[u] = __ldg(w + i + u); }
-#pragma unroll
-    for (int u = 0; u < U; u++) t = __fadd_rn(t, __fmul_rn(a[u], b[u]));
+        for (int u = 0; u < 16; u++) t = __fadd_rn(t, prod[j + u]);
+      }
+      for (; j < n; j++) t = __fadd_rn(t, prod[j]);
+    }
+    __syncthreads();
   }
-  for (; i < m.y; i++) t = __fadd_rn(t, __fmul_rn(__ldg(row + i), __ldg(w + i)));
-  t = t < 0.0f ? 0.0f : (t > 255.0f ? 255.0f : t);
-  out[o] = (uint8_t)roundf(t);
+  if (threadIdx.x == 0) {
+    t = t < 0.0f ? 0.0f : (t > 255.0f ? 255.0f : t);
+    out[o] = (uint8_t)roundf(t);
+  }
 }
 // nothing to resize (frame already new_w x new_h): grayscale only
 template <int BPP>

@@ -193,6 +193,20 @@ def main():
         m = torch.empty((1080, 1920), dtype=torch.uint8, device="cuda")
         t = timeit(lambda i: ctx.roundmask_generate(1920, 1080, 1920, 64, m), 20)
         report("roundmask_a8", t, 1920 * 1080, frame="1920x1080", radius=64, note="once per caps/radius change")
+    if want("hashes"):
+        # videocompare's other hash algorithms: grayscale + Lanczos3 resize to 8x8 / 9x8 / 8x9 / 5x5 (two kernels) + the
+        # 64-81 byte read-back the bit rule needs on the host -- a synchronous call, timed by the host clock
+        import time
+        frames, _ = ring_of(contents["natural"])
+        for algo in ("mean", "gradient", "vertgradient", "doublegradient", "blockhash"):
+            for i in range(4):
+                ctx.hash_image(algo, "RGBA", W, H, frames[i % RING], 4 * W)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(args.iters):
+                ctx.hash_image(algo, "RGBA", W, H, frames[i % RING], 4 * W)
+            t = (time.perf_counter() - t0) / args.iters
+            report("videocompare_hash_image_" + algo, t, W * H * 4, content="natural", frame="3840x2160", note="synchronous call on a device frame: kernels + read-back + host bit rule")
     if want("colordetect"):
         hist = torch.zeros(32768, dtype=torch.int32, device="cuda")
         for cname in ("ramps", "noise", "natural"):
