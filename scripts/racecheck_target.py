@@ -35,6 +35,23 @@ for i in range(3):
     ctx.blockhash_sums_batch("RGBA", w, h, [d, outs[0]], [4 * w, 4 * w], sums)
     ctx.colordetect_histogram("RGBA", w, h, d, 4 * w, 1, hist)
     ctx.colordetect_histogram("RGBA", w, h, d, 4 * w, 10, hist)
+sums16 = torch.zeros(512, dtype=torch.int32, device="cuda")
+for rows in (0, 1, 2):                               # block-sum decompositions, PDL-overlapped trains, 16x8 grid, two frames
+    ctx.set_option("blockhash_rows", rows)
+    for i in range(4):
+        ctx.blockhash_sums_batch("RGBA", w, h, [d, outs[i % 3]], [4 * w, 4 * w], sums16, hw=16, hh=8)
+        ctx.blockhash_sums("RGBA", w, h, outs[i % 3], 4 * w, sums)
+        ctx.colorlut_process("RGBA", w, h, d, 4 * w, outs[(i + 1) % 3], 4 * w)   # producer of the next frame to hash
+ctx.set_option("blockhash_rows", 2)
+from b200vfx import sharding
+for cfg in (0, 1):                                   # fused tile gather on one rank: 16- and 32-byte stores
+    ctx.set_option("tile_gather_cfg", cfg)
+    pf = sharding.PeerFrames(ctx, None, h, 4 * w, nbuf=2)
+    for i in range(3):
+        pf.process(w, d, 4 * w)
+    assert pf.status() == 0
+    pf.close()
+ctx.set_option("tile_gather_cfg", 0)
 for algo in ("mean", "gradient", "vertgradient", "doublegradient", "blockhash"):
     ctx.hash_image(algo, "RGBA", w, h, d, 4 * w)
     ctx.hash_image(algo, "RGBA", w - 3, h - 1, d, 4 * w)
