@@ -95,7 +95,12 @@ uint64_t b200vfx_ctx_kernel_launches(const b200vfx_ctx *ctx);
  * "cd_cluster" 1|2|4|8 (colordetect: CTAs per cluster that merge their shared-memory histograms over DSMEM),
  * "memo_ctas" 2..8 (CTAs per SM of the persistent table-lookup kernels; 4 = two consecutive frames resident together),
  * "memo_tile" 0|1 (4-byte-pixel table lookups through a per-tile shared-memory copy of the colour sub-cube; wins on
- * medium-noise content only, profiles/r01_memo_tile_experiment.jsonl). */
+ * medium-noise content only, profiles/r01_memo_tile_experiment.jsonl),
+ * "rgba64_x4" 0|1 (RGBA64 3D-LUT kernel that keeps the LUT cell of four neighbouring pixels in registers),
+ * "blockhash_rows" 0..8 (videocompare block sums: 0 = one CTA per hash block, n > 0 = whole-row streaming CTAs,
+ * 2 * SMs / n of them; default 2 = one per SM), "blockhash_tma" 0|1 (TMA-fed block-sum tiles),
+ * "tile_gather_path" 0|1 (fused colorlut + all-gather: register stores | TMA bulk stores), "tile_gather_cfg" (path 0:
+ * 1 = 32-byte stores; path 1: tile size 16/8/4/32 KB), "tile_gather_ctas" CTAs per SM, "peer_timeout_ms". */
 int b200vfx_ctx_set_option(b200vfx_ctx *ctx, const char *name, int value);
 
 /* Page-locked host memory for a GstAllocator handed out in
