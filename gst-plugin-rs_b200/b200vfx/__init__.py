@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
         "b200vfx_convert_to_planar": ([vp, ci, ci, ci, ci, vp, ci, C.POINTER(vp), C.POINTER(ci), ci], ci),
         "b200vfx_convert_from_planar": ([vp, ci, ci, ci, ci, C.POINTER(vp), C.POINTER(ci), vp, ci, ci], ci),
         "b200vfx_a420_append": ([vp, ci, ci, C.POINTER(vp), C.POINTER(ci), vp, ci, C.POINTER(vp), C.POINTER(ci)], ci),
+        "b200vfx_colorlut_process_planar": ([vp, ci, ci, ci, C.POINTER(vp), C.POINTER(ci), C.POINTER(vp), C.POINTER(ci), ci], ci),
         "b200vfx_hsvfilter_process": ([vp, ci, ci, ci, vp, ci] + [cf] * 5, ci),
         "b200vfx_hsvdetector_process": ([vp, ci, ci, ci, ci, vp, ci, vp, ci] + [cf] * 6, ci),
         "b200vfx_roundmask_generate": ([vp, ci, ci, ci, cu, vp], ci),
@@ -303,6 +304,11 @@ class Context:
     def convert_from_planar(self, src_fmt, dst_fmt, width, height, planes, strides, dst, dstride, matrix=0):
         pp, ss = self._planes(planes, strides)
         self._chk(lib().b200vfx_convert_from_planar(self._h, FMT[src_fmt], FMT[dst_fmt], width, height, pp, ss, _ptr(dst), dstride, matrix))
+
+    def colorlut_process_planar(self, fmt, width, height, src_planes, src_strides, dst_planes, dst_strides, matrix=0):
+        sp, ss = self._planes(src_planes, src_strides)
+        dp, ds = self._planes(dst_planes, dst_strides)
+        self._chk(lib().b200vfx_colorlut_process_planar(self._h, FMT[fmt], width, height, sp, ss, dp, ds, matrix))
 
     def a420_append(self, width, height, i420_planes, i420_strides, a8, a8_stride, out_planes, out_strides):
         ip, istr = self._planes(i420_planes, i420_strides)

@@ -1733,6 +1733,86 @@ int b200vfx_convert_from_planar(b200vfx_ctx *c, int src_fmt, int dst_fmt, int wi
   return 0;
 }
 
+// ColorLut::transform_frame on a planar YUV frame: I420 -> RGB, the LUT, RGB -> I420 in one kernel (convert.cuh).  The A plane
+// of an A420 frame is copied (colorlut copies alpha, imp.rs:262,291).
+int b200vfx_colorlut_process_planar(b200vfx_ctx *c, int fmt, int width, int height, const void *const *src_planes,
+                                    const int *src_strides, void *const *dst_planes, const int *dst_strides, int matrix) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  if (!c->have_lut) return fail(c, B200VFX_ERR_NOT_NEGOTIATED, "No LUT configured");  // imp.rs:210-213
+  if (fmt != B200VFX_FORMAT_I420 && fmt != B200VFX_FORMAT_A420)
+    return fail(c, B200VFX_ERR_UNSUPPORTED, "colorlut (planar): format %d is not I420 / A420", fmt);
+  if (!src_planes || !src_strides || !dst_planes || !dst_strides || (matrix != 0 && matrix != 601 && matrix != 709))
+    return fail(c, B200VFX_ERR_INVALID, "colorlut (planar): bad argument");
+  if (width <= 0 || height <= 0) return fail(c, B200VFX_ERR_INVALID, "colorlut (planar): empty frame");
+  PlaneSet ps;
+  planar_geometry(fmt, width, height, &ps);
+  for (int i = 0; i < ps.n; i++) {
+    if (!src_planes[i] || src_strides[i] < 0 || (size_t)src_strides[i] < ps.row[i] || !dst_planes[i] || dst_strides[i] < 0 ||
+        (size_t)dst_strides[i] < ps.row[i])
+      return fail(c, B200VFX_ERR_INVALID, "colorlut (planar): bad plane %d", i);
+    if (src_planes[i] == dst_planes[i]) return fail(c, B200VFX_ERR_INVALID, "colorlut (planar): in-place is not supported (the element is never in place)");
+  }
+  DeviceGuard g(c->device);
+  bool sdev, ddev;
+  if (int rc = planes_location(c, src_planes, ps.n, src_planes[0], &sdev)) return rc;
+  if (int rc = planes_location(c, (const void *const *)dst_planes, ps.n, dst_planes[0], &ddev)) return rc;
+  if (sdev != ddev) return fail(c, B200VFX_ERR_INVALID, "colorlut (planar): source and destination planes must both be device or both be host memory");
+  const bool dev = sdev;
+  const YuvMatrix m = yuv_matrix(matrix, height);
+  cudaStream_t st = dev ? c->stream() : c->s_k;
+  const uint8_t *sp[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint8_t *dp[4] = {nullptr, nullptr, nullptr, nullptr};
+  long sstr[4] = {0, 0, 0, 0}, dstr[4] = {0, 0, 0, 0};
+  if (dev) {
+    for (int i = 0; i < ps.n; i++) { sp[i] = (const uint8_t *)src_planes[i]; sstr[i] = src_strides[i]; dp[i] = (uint8_t *)dst_planes[i]; dstr[i] = dst_strides[i]; }
+  } else {   // staged copies keep the caller's strides, rounded up so that the vector kernel stays usable
+    size_t tin = 0, tout = 0;
+    for (int i = 0; i < ps.n; i++) { tin += (((size_t)src_strides[i] + 15) & ~(size_t)15) * ps.rows[i]; tout += (((size_t)dst_strides[i] + 15) & ~(size_t)15) * ps.rows[i]; }
+    CU(c, c->stage_in.reserve(tin));
+    CU(c, c->stage_out.reserve(tout));
+    size_t oin = 0, oout = 0;
+    for (int i = 0; i < ps.n; i++) {
+      const size_t si = ((size_t)src_strides[i] + 15) & ~(size_t)15, so = ((size_t)dst_strides[i] + 15) & ~(size_t)15;
+      CU(c, cudaMemcpy2DAsync(c->stage_in.p + oin, si, src_planes[i], (size_t)src_strides[i], ps.row[i], (size_t)ps.rows[i], cudaMemcpyHostToDevice, st));
+      sp[i] = c->stage_in.p + oin; sstr[i] = (long)si; oin += si * ps.rows[i];
+      dp[i] = c->stage_out.p + oout; dstr[i] = (long)so; oout += so * ps.rows[i];
+    }
+  }
+  pdl_admit(false, st, Span{0, 0}, Span{0, 0});
+  if (int rc = build_axis(c, st)) return rc;
+  if (int rc = ensure_colorlut_memo(c, lut_dev(c), st)) return rc;
+  // forward matrix as dp4a byte weights (Y: unsigned, chroma: signed): true for BT.601 / BT.709 at 8 fractional bits
+  auto ub = [](int v) { return v >= 0 && v <= 255; };
+  auto sb = [](int v) { return v >= -128 && v <= 127; };
+  if (!(ub(m.yr) && ub(m.yg) && ub(m.yb) && sb(m.ur) && sb(m.ug) && sb(m.ub) && sb(m.vr) && sb(m.vg) && sb(m.vb)) || m.ry != m.gy || m.ry != m.by)
+    return fail(c, B200VFX_ERR_UNSUPPORTED, "colorlut (planar): matrix coefficients do not fit the packed form");
+  auto pack = [](int a, int b, int d) { return (uint32_t)(a & 255) | ((uint32_t)(b & 255) << 8) | ((uint32_t)(d & 255) << 16); };
+  const YuvPacked w{pack(m.yr, m.yg, m.yb), pack(m.ur, m.ug, m.ub), pack(m.vr, m.vg, m.vb)};
+  const bool l1d = c->lut_kind != 3;
+  const bool x8 = (width % 8) == 0 && (height % 2) == 0 && aligned(sp[0], sstr[0], 8) && aligned(dp[0], dstr[0], 8) &&
+                  aligned(sp[1], sstr[1], 4) && aligned(sp[2], sstr[2], 4) && aligned(dp[1], dstr[1], 4) && aligned(dp[2], dstr[2], 4);
+  dim3 block(32, 8);
+  if (x8) {
+    dim3 grid((unsigned)ceil_div(width / 8, 32), (unsigned)ceil_div(height / 2, 8));
+    if (l1d) colorlut_i420_x8_kernel<true><<<grid, block, 0, st>>>(c->d_memo, c->d_memo1d, sp[0], sstr[0], sp[1], sstr[1], sp[2], sstr[2], width, height, m, w, dp[0], dstr[0], dp[1], dstr[1], dp[2], dstr[2]);
+    else colorlut_i420_x8_kernel<false><<<grid, block, 0, st>>>(c->d_memo, c->d_memo1d, sp[0], sstr[0], sp[1], sstr[1], sp[2], sstr[2], width, height, m, w, dp[0], dstr[0], dp[1], dstr[1], dp[2], dstr[2]);
+  } else {
+    dim3 grid((unsigned)ceil_div((width + 1) / 2, 32), (unsigned)ceil_div((height + 1) / 2, 8));
+    if (l1d) colorlut_i420_kernel<true><<<grid, block, 0, st>>>(c->d_memo, c->d_memo1d, sp[0], sstr[0], sp[1], sstr[1], sp[2], sstr[2], width, height, m, w, dp[0], dstr[0], dp[1], dstr[1], dp[2], dstr[2]);
+    else colorlut_i420_kernel<false><<<grid, block, 0, st>>>(c->d_memo, c->d_memo1d, sp[0], sstr[0], sp[1], sstr[1], sp[2], sstr[2], width, height, m, w, dp[0], dstr[0], dp[1], dstr[1], dp[2], dstr[2]);
+  }
+  c->launches++;
+  CU(c, cudaGetLastError());
+  if (ps.n == 4) CU(c, cudaMemcpy2DAsync(dp[3], (size_t)dstr[3], sp[3], (size_t)sstr[3], ps.row[3], (size_t)ps.rows[3], cudaMemcpyDeviceToDevice, st));
+  if (!dev) {
+    for (int i = 0; i < ps.n; i++)
+      CU(c, cudaMemcpy2DAsync(dst_planes[i], (size_t)dst_strides[i], dp[i], (size_t)dstr[i], ps.row[i], (size_t)ps.rows[i], cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    pdl_forget(st);
+  }
+  return 0;
+}
+
 // RoundedCorners::prepare_output_buffer (border/imp.rs:482-559) for a device-resident pipeline: the reference appends the
 // shared alpha GstMemory to the I420 buffer; device frames are plain plane pointers, so A420 = the three I420 planes + the
 // mask plane copied into the output frame (device-to-device, asynchronous on the context stream)

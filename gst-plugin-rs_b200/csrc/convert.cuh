@@ -115,4 +115,136 @@ __global__ void __launch_bounds__(256) i420_to_rgb_kernel(const uint8_t *__restr
   }
 }
 
+// ---- colorlut on I420 / A420 frames ("planar YUV via fused convert") --------------------------------
+// "videoconvert ! colorlut ! videoconvert" (the doc pipeline of colorlut/imp.rs:18) on a planar frame = I420 -> RGB (spec
+// above), ColorLut::transform_rgba (imp.rs:267-294), RGB -> I420 (spec above).  Fused: 1.5 B/px in, 1.5 B/px out instead of
+// 19 B/px through two RGBA intermediates; the result is the composition, bit for bit.  The LUT is the memoised answer table
+// (3D) or the three per-channel byte tables (1D).
+__device__ __forceinline__ uint32_t yuv_to_rgb24(const YuvMatrix &m, int Y, int U, int V) {   // -> r | g << 8 | b << 16
+  const int r = clamp255((m.ry * Y + m.rv * V + 128) >> 8);
+  const int g = clamp255((m.gy * Y + m.gu * U + m.gv * V + 128) >> 8);
+  const int b = clamp255((m.by * Y + m.bu * U + 128) >> 8);
+  return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+}
+// the same two conversions with the work shared inside a 2x2 block: the chroma terms of the inverse matrix are formed once
+// per block, and the forward matrix is three dp4a on the packed table answer (Y weights as unsigned bytes, chroma weights
+// as signed bytes; yuv_pack_ok() says whether the coefficients fit -- they do for BT.601 and BT.709).  Integer arithmetic:
+// regrouping the sums changes nothing.
+struct YuvChroma { int cr, cg, cb; };
+__device__ __forceinline__ YuvChroma yuv_chroma_terms(const YuvMatrix &m, int U, int V) {
+  return YuvChroma{m.rv * V + 128, m.gu * U + m.gv * V + 128, m.bu * U + 128};
+}
+__device__ __forceinline__ uint32_t yuv_to_rgb24(const YuvMatrix &m, int Y, const YuvChroma &c) {
+  const int yt = m.ry * Y;   // ry == gy == by
+  return (uint32_t)clamp255((yt + c.cr) >> 8) | ((uint32_t)clamp255((yt + c.cg) >> 8) << 8) | ((uint32_t)clamp255((yt + c.cb) >> 8) << 16);
+}
+struct YuvPacked { uint32_t wy, wu, wv; };   // byte 0: R weight, 1: G, 2: B
+__device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ void rgb24_to_yuv(const YuvPacked &w, uint32_t rgb, int &y, int &u, int &v) {
+  y = clamp255((int)__dp4a(rgb, w.wy, (unsigned)((16 << 8) + 128)) >> 8);
+  u = clamp255(dp4a_u8_s8(rgb, w.wu, (128 << 8) + 128) >> 8);
+  v = clamp255(dp4a_u8_s8(rgb, w.wv, (128 << 8) + 128) >> 8);
+}
+
+template <bool LUT1D>
+__device__ __forceinline__ uint32_t lut_rgb24(const uint32_t *__restrict__ memo, const uint8_t *tab, uint32_t c) {
+  if (LUT1D) return (uint32_t)tab[c & 255u] | ((uint32_t)tab[256 + ((c >> 8) & 255u)] << 8) | ((uint32_t)tab[512 + (c >> 16)] << 16);
+  return __ldg(memo + memo_index(c));
+}
+
+// any size, any alignment: one thread per 2x2 block (edge pixels replicated exactly like rgb_to_i420_kernel)
+template <bool LUT1D>
+__global__ void __launch_bounds__(256) colorlut_i420_kernel(const uint32_t *__restrict__ memo, const uint8_t *__restrict__ memo1d,
+                                                            const uint8_t *__restrict__ yp, long ys, const uint8_t *__restrict__ up, long us,
+                                                            const uint8_t *__restrict__ vp, long vs, int width, int height, YuvMatrix m, YuvPacked w,
+                                                            uint8_t *__restrict__ oy, long oys, uint8_t *__restrict__ ou, long ous,
+                                                            uint8_t *__restrict__ ov, long ovs) {
+  __shared__ uint8_t tab[LUT1D ? 768 : 4];
+  if (LUT1D) {
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 768; i += blockDim.x * blockDim.y) tab[i] = memo1d[i];
+    __syncthreads();
+  }
+  const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y * blockDim.y + threadIdx.y;
+  const int cw = (width + 1) >> 1, ch = (height + 1) >> 1;
+  if (cx >= cw || cy >= ch) return;
+  const YuvChroma ct = yuv_chroma_terms(m, (int)up[(size_t)cy * us + cx] - 128, (int)vp[(size_t)cy * vs + cx] - 128);
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int x = min(2 * cx + (k & 1), width - 1), y = min(2 * cy + (k >> 1), height - 1);
+    o[k] = lut_rgb24<LUT1D>(memo, tab, yuv_to_rgb24(m, (int)yp[(size_t)y * ys + x] - 16, ct)) & 0x00FFFFFFu;
+  }
+  int su = 0, sv = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int x = 2 * cx + (k & 1), y = 2 * cy + (k >> 1);
+    int Y2, U2, V2;
+    rgb24_to_yuv(w, o[k], Y2, U2, V2);
+    su += U2; sv += V2;
+    if (x < width && y < height) oy[(size_t)y * oys + x] = (uint8_t)Y2;
+  }
+  ou[(size_t)cy * ous + cx] = (uint8_t)((su + 2) >> 2);
+  ov[(size_t)cy * ovs + cx] = (uint8_t)((sv + 2) >> 2);
+}
+
+// width % 8 == 0, height % 2 == 0, Y rows 8-byte and chroma rows 4-byte aligned: a thread owns 8 x 2 pixels (four 2x2
+// blocks): two 8-byte Y loads, one 4-byte U and V load, 16 table gathers in flight, the same widths on the way out
+template <bool LUT1D>
+__global__ void __launch_bounds__(256) colorlut_i420_x8_kernel(const uint32_t *__restrict__ memo, const uint8_t *__restrict__ memo1d,
+                                                               const uint8_t *__restrict__ yp, long ys, const uint8_t *__restrict__ up, long us,
+                                                               const uint8_t *__restrict__ vp, long vs, int width, int height, YuvMatrix m, YuvPacked w,
+                                                               uint8_t *__restrict__ oy, long oys, uint8_t *__restrict__ ou, long ous,
+                                                               uint8_t *__restrict__ ov, long ovs) {
+  __shared__ uint8_t tab[LUT1D ? 768 : 4];
+  if (LUT1D) {
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 768; i += blockDim.x * blockDim.y) tab[i] = memo1d[i];
+    __syncthreads();
+  }
+  const int gx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (gx * 8 >= width || cy * 2 >= height) return;
+  const uint2 y0 = __ldcs(reinterpret_cast<const uint2 *>(yp + (size_t)(2 * cy) * ys) + gx);
+  const uint2 y1 = __ldcs(reinterpret_cast<const uint2 *>(yp + (size_t)(2 * cy + 1) * ys) + gx);
+  const uint32_t u4 = __ldcs(reinterpret_cast<const uint32_t *>(up + (size_t)cy * us) + gx);
+  const uint32_t v4 = __ldcs(reinterpret_cast<const uint32_t *>(vp + (size_t)cy * vs) + gx);
+  const uint32_t yw[2][2] = {{y0.x, y0.y}, {y1.x, y1.y}};
+  uint32_t o[2][8];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const YuvChroma ct = yuv_chroma_terms(m, (int)((u4 >> (8 * j)) & 255u) - 128, (int)((v4 >> (8 * j)) & 255u) - 128);
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int d = 0; d < 2; d++) {
+        const int px = 2 * j + d;
+        const int Y = (int)((yw[r][px >> 2] >> (8 * (px & 3))) & 255u) - 16;
+        o[r][px] = lut_rgb24<LUT1D>(memo, tab, yuv_to_rgb24(m, Y, ct)) & 0x00FFFFFFu;
+      }
+  }
+  uint32_t yo[2][2] = {{0u, 0u}, {0u, 0u}}, uo = 0u, vo = 0u;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    int su = 0, sv = 0;
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int d = 0; d < 2; d++) {
+        const int px = 2 * j + d;
+        int Y2, U2, V2;
+        rgb24_to_yuv(w, o[r][px], Y2, U2, V2);
+        su += U2; sv += V2;
+        yo[r][px >> 2] |= (uint32_t)Y2 << (8 * (px & 3));
+      }
+    uo |= (uint32_t)((su + 2) >> 2) << (8 * j);
+    vo |= (uint32_t)((sv + 2) >> 2) << (8 * j);
+  }
+  __stcs(reinterpret_cast<uint2 *>(oy + (size_t)(2 * cy) * oys) + gx, make_uint2(yo[0][0], yo[0][1]));
+  __stcs(reinterpret_cast<uint2 *>(oy + (size_t)(2 * cy + 1) * oys) + gx, make_uint2(yo[1][0], yo[1][1]));
+  __stcs(reinterpret_cast<uint32_t *>(ou + (size_t)cy * ous) + gx, uo);
+  __stcs(reinterpret_cast<uint32_t *>(ov + (size_t)cy * ovs) + gx, vo);
+}
+
 }  // namespace b200vfx

@@ -178,6 +178,13 @@ int b200vfx_convert_from_planar(b200vfx_ctx *ctx, int src_fmt, int dst_fmt, int 
                                 const void *const *planes, const int *strides, void *dst, int dst_stride, int matrix);
 int b200vfx_a420_append(b200vfx_ctx *ctx, int width, int height, const void *const *i420_planes, const int *i420_strides,
                         const void *a8, int a8_stride, void *const *out_planes, const int *out_strides);
+/* ColorLut::transform_frame (colorlut/imp.rs:204-235) on an I420 / A420 frame ("planar YUV via fused
+ * convert"): I420 -> RGB, ColorLut::transform_rgba (imp.rs:267-294), RGB -> I420 in ONE kernel -- 3 bytes of HBM traffic per
+ * pixel instead of 19 through two RGBA intermediates.  The answer is the composition b200vfx_convert_from_planar ->
+ * b200vfx_colorlut_process(RGBA) -> b200vfx_convert_to_planar, bit for bit (conversion arithmetic: csrc/convert.cuh, parity
+ * with `videoconvert` unpinned); the A plane of A420 is copied.  Planes all host or all device memory; never in place. */
+int b200vfx_colorlut_process_planar(b200vfx_ctx *ctx, int fmt, int width, int height, const void *const *src_planes,
+                                    const int *src_strides, void *const *dst_planes, const int *dst_strides, int matrix);
 
 /* ---- hsvfilter ----------------------------------------------------------
  * HsvFilter::transform_frame_ip + hsv_filter (video/hsv/src/hsvfilter/imp.rs:76-120,323-376).

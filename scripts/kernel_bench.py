@@ -193,6 +193,30 @@ def main():
         m = torch.empty((1080, 1920), dtype=torch.uint8, device="cuda")
         t = timeit(lambda i: ctx.roundmask_generate(1920, 1080, 1920, 64, m), 20)
         report("roundmask_a8", t, 1920 * 1080, frame="1920x1080", radius=64, note="once per caps/radius change")
+    if want("planar"):
+        # colorlut on I420 frames with both videoconverts fused: 1.5 B/px in, 1.5 B/px out
+        k, s_, v, sc, of = b200vfx.cube_parse(synth.cube_text_3d(33, "mix"))
+        ctx.colorlut_set_lut(k, s_, v, sc, of)
+        rng = np.random.default_rng(5)
+        strides = [W, W // 2, W // 2]
+        shapes = [(H, W), (H // 2, W // 2), (H // 2, W // 2)]
+        yy, xx = np.mgrid[0:H, 0:W]
+        smooth = [((xx * 200 // W) + (yy * 40 // H) + 16).astype(np.uint8), np.full(shapes[1], 110, np.uint8), np.full(shapes[2], 150, np.uint8)]
+        gens = {"noise": lambda i: [rng.integers(0, 256, sh, dtype=np.uint8) for sh in shapes],
+                "natural": lambda i: [np.clip(b.astype(np.int16) + rng.integers(-3, 4, b.shape), 0, 255).astype(np.uint8) for b in smooth]}
+        for cname, gen in gens.items():
+            src = [[torch.from_numpy(p).cuda() for p in gen(i)] for i in range(RING)]
+            dst = [[torch.empty_like(p) for p in f] for f in src]
+            t = timeit(lambda i: ctx.colorlut_process_planar("I420", W, H, src[i % RING], strides, dst[i % RING], strides), args.iters)
+            report("colorlut_i420_fused_converts", t, W * H * 3, content=cname, frame="3840x2160", note="I420 -> RGB -> LUT 33^3 -> I420 in one kernel")
+            rgba = [torch.empty((H, 4 * W), dtype=torch.uint8, device="cuda") for _ in range(2)]
+            def chain(i):
+                ctx.convert_from_planar("I420", "RGBA", W, H, src[i % RING], strides, rgba[0], 4 * W)
+                ctx.colorlut_process("RGBA", W, H, rgba[0], 4 * W, rgba[1], 4 * W)
+                ctx.convert_to_planar("RGBA", "I420", W, H, rgba[1], 4 * W, dst[i % RING], strides)
+            t = timeit(chain, args.iters)
+            report("colorlut_i420_three_kernels", t, W * H * 3, content=cname, frame="3840x2160", note="convert_from_planar + colorlut + convert_to_planar")
+            del src, dst, rgba
     if want("hashes"):
         # videocompare's other hash algorithms: grayscale + Lanczos3 resize to 8x8 / 9x8 / 8x9 / 5x5 (two kernels) + the
         # 64-81 byte read-back the bit rule needs on the host -- a synchronous call, timed by the host clock

@@ -119,6 +119,96 @@ def test_planar_round_trip_against_spec(ctx, fmt, w, h, kind):
     assert np.abs(npc.from_planar(gp, "RGB", gr.shape[1] // 3, 2, kind).astype(int) - gr).max() <= 3
 
 
+def _planar_frame(w, h, seed, with_a, pad=0, natural=False):
+    """random (or smooth) I420 / A420 planes with GStreamer's strides (App. E) + optional extra padding"""
+    rng = np.random.default_rng(seed)
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    ys, cs = ((w + 3) // 4) * 4 + pad, ((cw + 3) // 4) * 4 + pad
+    shapes = [(h, ys), (ch, cs), (ch, cs)] + ([(h, ys)] if with_a else [])
+    if natural:
+        yy, xx = np.mgrid[0:h, 0:ys]
+        base = [((xx * 200 // max(1, ys)) + (yy * 40 // max(1, h)) + 16).astype(np.uint8)]
+        base += [np.full((ch, cs), v, np.uint8) for v in (110, 150)]
+        planes = [np.clip(b.astype(np.int64) + rng.integers(-3, 4, b.shape), 0, 255).astype(np.uint8) for b in base]
+        if with_a:
+            planes.append(rng.integers(0, 256, (h, ys), dtype=np.uint8))
+    else:
+        planes = [rng.integers(0, 256, sh, dtype=np.uint8) for sh in shapes]
+    return planes, [sh[1] for sh in shapes]
+
+
+def _planar_expected(cube, fmt, w, h, planes, kind):
+    """the composition the fused kernel replaces: I420 -> RGBA (spec), colorlut (oracle), RGBA -> I420 (spec)"""
+    with_a = fmt == "A420"
+    rgba = npc.from_planar(planes, "RGBA", w, h, kind)
+    lut = orc.colorlut_apply(cube, "RGBA", w, h, rgba)
+    return npc.to_planar("RGBA", w, h, lut, kind, with_alpha=with_a)
+
+
+@pytest.mark.parametrize("lut", ["3d", "1d"])
+@pytest.mark.parametrize("fmt,w,h,kind,pad", [("I420", 64, 48, 0, 0), ("I420", 641, 361, 601, 0), ("A420", 1920, 1080, 0, 0), ("I420", 33, 17, 709, 0),
+                                              ("A420", 1280, 720, 709, 12), ("I420", 8, 2, 0, 0), ("I420", 1, 1, 0, 0), ("I420", 1288, 6, 0, 4)])
+def test_colorlut_on_planar_frames(ctx, lut, fmt, w, h, kind, pad):
+    """colorlut on I420 / A420 with both converts fused == convert -> colorlut (oracle) -> convert"""
+    torch = pytest.importorskip("torch")
+    cube = orc.cube_parse(synth.cube_text_3d(17, "mix") if lut == "3d" else synth.cube_text_1d(256, 2.2))
+    ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    planes, strides = _planar_frame(w, h, 5 * w + h, fmt == "A420", pad)
+    exp = _planar_expected(cube, fmt, w, h, planes, kind)
+    out = [np.full(p.shape, 9, np.uint8) for p in planes]
+    ctx.colorlut_process_planar(fmt, w, h, planes, strides, out, strides, kind)                      # host planes
+    for o, e in zip(out, exp):
+        assert (o[:, :e.shape[1]] == e).all() and (o[:, e.shape[1]:] == 9).all(), (fmt, w, h, "host")
+    dsrc = [torch.from_numpy(p).cuda() for p in planes]
+    ddst = [torch.full(p.shape, 9, dtype=torch.uint8, device="cuda") for p in planes]
+    for _ in range(2):
+        ctx.colorlut_process_planar(fmt, w, h, dsrc, strides, ddst, strides, kind)                   # device planes
+    torch.cuda.synchronize()
+    for o, e in zip(ddst, exp):
+        o = o.cpu().numpy()
+        assert (o[:, :e.shape[1]] == e).all() and (o[:, e.shape[1]:] == 9).all(), (fmt, w, h, "device")
+    # and it is what the three separate device calls produce
+    rgba = torch.zeros((h, 4 * w), dtype=torch.uint8, device="cuda")
+    graded = torch.zeros_like(rgba)
+    back = [torch.zeros(p.shape, dtype=torch.uint8, device="cuda") for p in planes]
+    ctx.convert_from_planar(fmt, "RGBA", w, h, dsrc, strides, rgba, 4 * w, kind)
+    ctx.colorlut_process("RGBA", w, h, rgba, 4 * w, graded, 4 * w)
+    ctx.convert_to_planar("RGBA", fmt, w, h, graded, 4 * w, back, strides, kind)
+    torch.cuda.synchronize()
+    for o, b, e in zip(ddst, back, exp):
+        assert (o.cpu().numpy()[:, :e.shape[1]] == b.cpu().numpy()[:, :e.shape[1]]).all()
+
+
+def test_colorlut_on_planar_4k_and_errors(ctx):
+    torch = pytest.importorskip("torch")
+    w, h = 3840, 2160
+    cube = orc.cube_parse(synth.cube_text_3d(33, "mix"))
+    ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    for natural in (False, True):
+        planes, strides = _planar_frame(w, h, 77, False, natural=natural)
+        exp = _planar_expected(cube, "I420", w, h, planes, 0)
+        dsrc = [torch.from_numpy(p).cuda() for p in planes]
+        ddst = [torch.zeros(p.shape, dtype=torch.uint8, device="cuda") for p in planes]
+        ctx.colorlut_process_planar("I420", w, h, dsrc, strides, ddst, strides)
+        torch.cuda.synchronize()
+        for o, e in zip(ddst, exp):
+            assert (o.cpu().numpy() == e).all()
+    with pytest.raises(b200vfx.B200VfxError):
+        ctx.colorlut_process_planar("I420", w, h, dsrc, strides, dsrc, strides)                       # in place
+    with pytest.raises(b200vfx.B200VfxError):
+        ctx.colorlut_process_planar("RGBA", w, h, dsrc, strides, ddst, strides)                       # not planar
+    with pytest.raises(b200vfx.B200VfxError):
+        ctx.colorlut_process_planar("I420", w, h, dsrc, strides, [p.cpu().numpy() for p in ddst], strides)   # device -> host planes
+    with pytest.raises(b200vfx.B200VfxError):
+        ctx.colorlut_process_planar("I420", w, h, dsrc, [s - 8 for s in strides], ddst, strides)     # stride < row
+    with b200vfx.Context(0) as fresh:
+        with pytest.raises(b200vfx.B200VfxError) as e:
+            fresh.colorlut_process_planar("I420", w, h, dsrc, strides, ddst, strides)
+        assert e.value.code == b200vfx.ERR_NOT_NEGOTIATED                                              # imp.rs:210-213
+
+
 def test_device_resident_chain_with_converters():
     """BGRx camera frame -> [fused convert] colorlut -> hsvdetector -> RGBA -> I420 -> roundedcorners (A420), everything in
     HBM on one stream: one upload, one download per plane.  The RGB part must equal the oracle chain bit for bit; the I420
