@@ -70,6 +70,11 @@ def lib() -> C.CDLL:
         "b200vfx_ctx_set_stream": ([vp, vp], ci),
         "b200vfx_ctx_synchronize": ([vp], ci),
         "b200vfx_ctx_set_chunk_rows": ([vp, ci], ci),
+        "b200vfx_ctx_set_host_async": ([vp, ci], ci),
+        "b200vfx_fence_create": ([vp, C.POINTER(vp)], ci),
+        "b200vfx_fence_wait": ([vp], ci),
+        "b200vfx_fence_query": ([vp], ci),
+        "b200vfx_fence_destroy": ([vp], None),
         "b200vfx_ctx_kernel_launches": ([vp], C.c_uint64),
         "b200vfx_ctx_set_option": ([vp, C.c_char_p, ci], ci),
         "b200vfx_host_alloc": ([C.c_size_t], vp),
@@ -179,6 +184,32 @@ def cube_parse(text):
     return kind.value, size.value, values, scale, offset
 
 
+class Fence:
+    def __init__(self, handle):
+        self._h = handle
+
+    def wait(self):
+        if lib().b200vfx_fence_wait(self._h) != 0:
+            raise B200VfxError(ERR_CUDA, "fence wait failed")
+
+    def done(self) -> bool:
+        r = lib().b200vfx_fence_query(self._h)
+        if r < 0:
+            raise B200VfxError(ERR_CUDA, "fence query failed")
+        return r == 1
+
+    def close(self):
+        if self._h:
+            lib().b200vfx_fence_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """One b200vfx_ctx (= one element instance)."""
 
@@ -215,6 +246,16 @@ class Context:
 
     def synchronize(self):
         self._chk(lib().b200vfx_ctx_synchronize(self._h))
+
+    def set_host_async(self, enable: bool):
+        """asynchronous host-frame mode: per-pixel calls on (pinned) host frames return once enqueued; see fence()"""
+        self._chk(lib().b200vfx_ctx_set_host_async(self._h, 1 if enable else 0))
+
+    def fence(self) -> "Fence":
+        """marks everything submitted so far from host frames; wait() before touching those frames"""
+        h = C.c_void_p()
+        self._chk(lib().b200vfx_fence_create(self._h, C.byref(h)))
+        return Fence(h)
 
     def set_chunk_rows(self, rows: int):
         self._chk(lib().b200vfx_ctx_set_chunk_rows(self._h, rows))

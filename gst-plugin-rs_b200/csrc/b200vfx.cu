@@ -70,6 +70,14 @@ struct b200vfx_ctx {
   std::vector<cudaEvent_t> ev_in, ev_k;
   cudaEvent_t ev_order = nullptr;      // orders the internal pipeline stream after the context stream (mixed host/device calls)
   DevBuf stage_in, stage_out, stage_sums;
+  // asynchronous host-frame mode (b200vfx_ctx_set_host_async): calls return once their copies and kernels are enqueued, so
+  // frame i+1's upload overlaps frame i's download.  Two staging slots of their own; a slot is reused only after the
+  // download of its previous frame (slot_done, recorded on s_d2h resp. s_k) -- the slot's upload and kernels wait for it.
+  bool host_async = false;
+  int async_slot = 0;
+  DevBuf astage_in[2], astage_out[2];
+  cudaEvent_t slot_done[2] = {nullptr, nullptr};
+  bool slot_used[2] = {false, false};
   uint8_t *result_pinned = nullptr;   // small results (block sums, resized luma, histogram) come back through pinned memory
   DevBuf reduce_scratch;               // single-launch reductions: [0,64) two grid counters (kept zero between launches), then partials
   int chunk_rows = 0;
@@ -790,6 +798,7 @@ int launch_map_zero_copy(b200vfx_ctx *c, Op op, const uint8_t *dsrc, long ss, ui
   k<<<grid, THREADS, smem, c->s_k>>>(op, dsrc, ss, ddst, ds, row_bytes, h);
   c->launches++;
   CU(c, cudaGetLastError());
+  if (c->host_async) return 0;   // asynchronous host-frame mode: the caller holds a fence
   CU(c, cudaStreamSynchronize(c->s_k));
   pdl_forget(c->s_k);
   return 0;
@@ -820,21 +829,36 @@ int run_staged(b200vfx_ctx *c, const Staged &s, LaunchFn launch) {
   const uint8_t *d_in = nullptr;
   uint8_t *d_out = nullptr;
   long d_in_stride = 0, d_out_stride = 0;
-  if (s.in_place) {
-    CU(c, c->stage_in.reserve((size_t)in_ds * s.height));
-    d_in = d_out = c->stage_in.p; d_in_stride = d_out_stride = in_ds;
-  } else {
-    if (src_dev) { d_in = s.src; d_in_stride = s.sstride; }
-    else { CU(c, c->stage_in.reserve((size_t)in_ds * s.height)); d_in = c->stage_in.p; d_in_stride = in_ds; }
-    if (dst_dev) { d_out = s.dst; d_out_stride = s.dstride; }
-    else { CU(c, c->stage_out.reserve((size_t)out_ds * s.height)); d_out = c->stage_out.p; d_out_stride = out_ds; }
-  }
   const bool need_h2d = s.in_place ? true : !src_dev;
   const bool need_d2h = s.in_place ? true : !dst_dev;
+  const bool async = c->host_async;
+  const int slot = c->async_slot;
+  DevBuf &st_in = async ? c->astage_in[slot] : c->stage_in, &st_out = async ? c->astage_out[slot] : c->stage_out;
+  if (async) {
+    c->async_slot ^= 1;
+    if (!c->slot_done[slot]) CU(c, cudaEventCreateWithFlags(&c->slot_done[slot], cudaEventDisableTiming));
+    if (c->slot_used[slot]) {   // the frame that used this slot two calls ago must have left it
+      CU(c, cudaStreamWaitEvent(c->s_h2d, c->slot_done[slot], 0));
+      CU(c, cudaStreamWaitEvent(c->s_k, c->slot_done[slot], 0));
+    }
+    // growing a slot frees memory that earlier frames may still use: drain first (happens on a caps change only)
+    const size_t want_in = (s.in_place || !src_dev) ? (size_t)in_ds * s.height : 0, want_out = (!s.in_place && !dst_dev) ? (size_t)out_ds * s.height : 0;
+    if (want_in > st_in.cap || want_out > st_out.cap) CU(c, cudaDeviceSynchronize());
+  }
+  if (s.in_place) {
+    CU(c, st_in.reserve((size_t)in_ds * s.height));
+    d_in = d_out = st_in.p; d_in_stride = d_out_stride = in_ds;
+  } else {
+    if (src_dev) { d_in = s.src; d_in_stride = s.sstride; }
+    else { CU(c, st_in.reserve((size_t)in_ds * s.height)); d_in = st_in.p; d_in_stride = in_ds; }
+    if (dst_dev) { d_out = s.dst; d_out_stride = s.dstride; }
+    else { CU(c, st_out.reserve((size_t)out_ds * s.height)); d_out = st_out.p; d_out_stride = out_ds; }
+  }
   // one plane in HBM, the other on the host: the device plane is ordered on the context stream (header contract)
   if (!s.in_place && ((src_dev && s.src && !(s.device_addressable & 1)) || (dst_dev && !(s.device_addressable & 2))))
     if (int rc = order_after_ctx_stream(c, c->s_k)) return rc;
   int rows = c->chunk_rows;
+  if (rows <= 0 && async) rows = s.height;   // frames overlap each other: chunking one frame only adds events (1379 vs 1084 frames/s)
   if (rows <= 0) {
     // measured on B200/PCIe5 (profiles/r01_e2e_chunks.md): ~8 MB chunks win for 4K frames (4 chunks);
     // never fewer than 4 chunks (so the two PCIe directions overlap) and never more than 16
@@ -878,6 +902,11 @@ int run_staged(b200vfx_ctx *c, const Staged &s, LaunchFn launch) {
         CU(c, cudaMemcpy2DAsync(hp, (size_t)s.dstride, dp, (size_t)d_out_stride, s.out_row_bytes, (size_t)(r1 - r0),
                                 cudaMemcpyDeviceToHost, c->s_d2h));
     }
+  }
+  if (async) {   // the call returns here; b200vfx_fence / b200vfx_ctx_synchronize tell when the frame is on the host
+    CU(c, cudaEventRecord(c->slot_done[slot], need_d2h ? c->s_d2h : c->s_k));
+    c->slot_used[slot] = true;
+    return 0;
   }
   if (need_d2h) CU(c, cudaStreamSynchronize(c->s_d2h));
   else CU(c, cudaStreamSynchronize(c->s_k));
@@ -995,6 +1024,7 @@ void b200vfx_ctx_destroy(b200vfx_ctx *c) {
   for (auto &kv : c->taps_cache) { cudaFree(kv.second.taps); cudaFree(kv.second.meta); }
   c->stage_in.release(); c->stage_out.release(); c->stage_sums.release(); c->reduce_scratch.release();
   if (c->result_pinned) { cudaFreeHost(c->result_pinned); c->result_pinned = nullptr; }
+  for (int i = 0; i < 2; i++) { c->astage_in[i].release(); c->astage_out[i].release(); if (c->slot_done[i]) { cudaEventDestroy(c->slot_done[i]); c->slot_done[i] = nullptr; } }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_k) cudaStreamDestroy(c->s_k);
@@ -1013,7 +1043,60 @@ int b200vfx_ctx_synchronize(b200vfx_ctx *c) {
   if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
   DeviceGuard g(c->device);
   CU(c, cudaStreamSynchronize(c->stream()));
+  if (c->host_async) {   // frames submitted asynchronously from host memory
+    CU(c, cudaStreamSynchronize(c->s_k));
+    CU(c, cudaStreamSynchronize(c->s_d2h));
+    pdl_forget(c->s_k);
+  }
   return 0;
+}
+
+int b200vfx_ctx_set_host_async(b200vfx_ctx *c, int enable) {
+  if (!c) return fail(nullptr, B200VFX_ERR_INVALID, "null context");
+  DeviceGuard g(c->device);
+  if (c->host_async && !enable) {   // leaving the mode: nothing may be in flight when synchronous calls resume
+    CU(c, cudaStreamSynchronize(c->s_h2d));
+    CU(c, cudaStreamSynchronize(c->s_k));
+    CU(c, cudaStreamSynchronize(c->s_d2h));
+    pdl_forget(c->s_k);
+  }
+  c->host_async = enable != 0;
+  return 0;
+}
+
+struct b200vfx_fence { cudaEvent_t ev; int device; };
+
+int b200vfx_fence_create(b200vfx_ctx *c, b200vfx_fence **out) {
+  if (!c || !out) return fail(c, B200VFX_ERR_INVALID, "fence: null argument");
+  DeviceGuard g(c->device);
+  cudaEvent_t ev = nullptr, k = nullptr;
+  CU(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  // everything the host-frame pipeline has been given so far: the download stream follows the kernel stream, which follows
+  // the upload stream, chunk by chunk; a call without a download ends on the kernel stream
+  if (cudaEventCreateWithFlags(&k, cudaEventDisableTiming) != cudaSuccess) { cudaEventDestroy(ev); return fail(c, B200VFX_ERR_CUDA, "fence: event"); }
+  cudaError_t e = cudaEventRecord(k, c->s_k);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(c->s_d2h, k, 0);
+  if (e == cudaSuccess) e = cudaEventRecord(ev, c->s_d2h);
+  cudaEventDestroy(k);   // destruction is deferred until the event has completed
+  if (e != cudaSuccess) { cudaEventDestroy(ev); return fail(c, B200VFX_ERR_CUDA, "fence: %s", cudaGetErrorString(e)); }
+  *out = new b200vfx_fence{ev, c->device};
+  return 0;
+}
+int b200vfx_fence_wait(b200vfx_fence *f) {
+  if (!f) return B200VFX_ERR_INVALID;
+  return cudaEventSynchronize(f->ev) == cudaSuccess ? 0 : B200VFX_ERR_CUDA;
+}
+int b200vfx_fence_query(b200vfx_fence *f) {
+  if (!f) return B200VFX_ERR_INVALID;
+  const cudaError_t e = cudaEventQuery(f->ev);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+  return B200VFX_ERR_CUDA;
+}
+void b200vfx_fence_destroy(b200vfx_fence *f) {
+  if (!f) return;
+  cudaEventDestroy(f->ev);
+  delete f;
 }
 
 int b200vfx_ctx_set_chunk_rows(b200vfx_ctx *c, int rows) {
@@ -1215,8 +1298,12 @@ int b200vfx_colorlut_process(b200vfx_ctx *c, int fmt, int width, int height, con
   const bool eligible = c->zero_copy != 0 && fmt == B200VFX_FORMAT_RGBA && c->mode == 0 && (width % 4) == 0 &&
                         aligned(src, src_stride, 16) && aligned(dst, dst_stride, 16) && pinned_device_ptr(src, &dsrc) &&
                         pinned_device_ptr(dst, &ddst);
-  const bool probing = eligible && c->zero_copy == 2 && c->zc_calls < 6;
-  const bool use_zc = eligible && c->zc_hybrid == 0 && (c->zero_copy == 1 || (probing ? (c->zc_calls % 2 == 0) : (c->zc_best_ms[0] <= c->zc_best_ms[1])));
+  // asynchronous host-frame mode: consecutive frames overlap on the copy engines (upload of frame i+1 beside the download of
+  // frame i), which beats kernel-issued PCIe traffic (1379 vs 1180 frames/s, profiles/r02_e2e_async.jsonl): "auto" means
+  // the staged pipeline there, and nothing is probed
+  const bool probing = eligible && c->zero_copy == 2 && c->zc_calls < 6 && !c->host_async;
+  const bool use_zc = eligible && c->zc_hybrid == 0 &&
+                      (c->zero_copy == 1 || (!c->host_async && (probing ? (c->zc_calls % 2 == 0) : (c->zc_best_ms[0] <= c->zc_best_ms[1]))));
   const auto t_begin = std::chrono::steady_clock::now();
   auto probe_done = [&](int which) {
     if (!eligible || c->zero_copy != 2) return;
@@ -1238,6 +1325,7 @@ int b200vfx_colorlut_process(b200vfx_ctx *c, int fmt, int width, int height, con
     int rc = launch_colorlut(c, fmt, Frame{(const uint8_t *)dsrc, src_stride, (uint8_t *)ddst, dst_stride, width, height}, c->s_k);
     c->stream_path = saved_path; c->stream_cfg = saved_cfg; c->stream_ctas = saved_ctas; c->stream_grid = saved_grid;
     if (rc) return rc;
+    if (c->host_async) return 0;   // asynchronous host-frame mode: the caller holds a fence
     CU(c, cudaStreamSynchronize(c->s_k));
     pdl_forget(c->s_k);
     probe_done(0);
@@ -1249,7 +1337,7 @@ int b200vfx_colorlut_process(b200vfx_ctx *c, int fmt, int width, int height, con
   const int rc = run_staged(c, s, [&](const uint8_t *ds, long dss, uint8_t *dd, long dds, int, int rows, cudaStream_t st) {
     return launch_colorlut(c, fmt, Frame{ds, dss, dd, dds, width, rows}, st);
   });
-  if (rc == 0) probe_done(1);
+  if (rc == 0 && !c->host_async) probe_done(1);
   return rc;
 }
 

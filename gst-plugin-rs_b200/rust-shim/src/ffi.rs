@@ -11,6 +11,10 @@ use std::ffi::{c_char, c_float, c_int, c_uint, c_void, CStr};
 pub struct b200vfx_ctx {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct b200vfx_fence {
+    _private: [u8; 0],
+}
 
 pub const B200VFX_OK: c_int = 0;
 pub const B200VFX_ERR_NOT_NEGOTIATED: c_int = -3;
@@ -50,6 +54,11 @@ extern "C" {
     pub fn b200vfx_upload(ctx: *mut b200vfx_ctx, dev_dst: *mut c_void, dst_stride: c_int, host_src: *const c_void, src_stride: c_int, row_bytes: usize, rows: c_int) -> c_int;
     pub fn b200vfx_download(ctx: *mut b200vfx_ctx, host_dst: *mut c_void, dst_stride: c_int, dev_src: *const c_void, src_stride: c_int, row_bytes: usize, rows: c_int) -> c_int;
     pub fn b200vfx_ctx_synchronize(ctx: *mut b200vfx_ctx) -> c_int;
+    pub fn b200vfx_ctx_set_host_async(ctx: *mut b200vfx_ctx, enable: c_int) -> c_int;
+    pub fn b200vfx_fence_create(ctx: *mut b200vfx_ctx, fence_out: *mut *mut b200vfx_fence) -> c_int;
+    pub fn b200vfx_fence_wait(fence: *mut b200vfx_fence) -> c_int;
+    pub fn b200vfx_fence_query(fence: *mut b200vfx_fence) -> c_int;
+    pub fn b200vfx_fence_destroy(fence: *mut b200vfx_fence);
 
     pub fn b200vfx_colorlut_load_file(ctx: *mut b200vfx_ctx, location: *const c_char) -> c_int;
     pub fn b200vfx_colorlut_clear(ctx: *mut b200vfx_ctx) -> c_int;

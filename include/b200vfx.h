@@ -81,6 +81,21 @@ const char *b200vfx_last_error(const b200vfx_ctx *ctx); /* ctx may be NULL: last
  * Default: a non-blocking stream owned by the context. */
 int b200vfx_ctx_set_stream(b200vfx_ctx *ctx, void *cuda_stream);
 int b200vfx_ctx_synchronize(b200vfx_ctx *ctx);
+/* Asynchronous host-frame mode.  By default a call on HOST frames returns when its output is in host memory (what
+ * GstBaseTransform's transform_frame promises), so the upload of frame i+1 can never overlap the download of frame i: with
+ * the default four chunks per frame the two PCIe directions idle a fifth of the time.  With the mode enabled, the
+ * per-pixel entry points on host frames (colorlut, colorlut_fmt, hsvfilter, hsvdetector, convert_packed) return as soon as
+ * their copies and kernels are enqueued; b200vfx_fence_create marks "everything submitted so far", and the caller must not
+ * read the output frames, or reuse the input frames, before that fence has been waited on (or b200vfx_ctx_synchronize).
+ * The element-side pattern is the one GstCudaMemory uses: the pinned GstMemory handed downstream carries the fence and
+ * its map() waits (rust-shim/src/allocator.rs).  Frames must be pinned (b200vfx_host_alloc) to be copied asynchronously
+ * at all.  Reductions and hashes (blockhash, colordetect, hash_image) stay synchronous: they return values. */
+typedef struct b200vfx_fence b200vfx_fence;
+int b200vfx_ctx_set_host_async(b200vfx_ctx *ctx, int enable);
+int b200vfx_fence_create(b200vfx_ctx *ctx, b200vfx_fence **fence_out);
+int b200vfx_fence_wait(b200vfx_fence *fence);          /* blocks the calling thread */
+int b200vfx_fence_query(b200vfx_fence *fence);         /* 1 = reached, 0 = pending, < 0 = error */
+void b200vfx_fence_destroy(b200vfx_fence *fence);
 /* rows per H2D/kernel/D2H pipeline chunk for HOST-pointer calls (0 = auto) */
 int b200vfx_ctx_set_chunk_rows(b200vfx_ctx *ctx, int rows);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */

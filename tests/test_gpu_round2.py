@@ -228,3 +228,74 @@ def test_colorlut_rgba64_four_pixels_per_thread_kernel(ctx, fmt, lut):
         out = np.zeros_like(frame)
         ctx.colorlut_process(fmt, w, h, frame, 8 * w, out, 8 * w)      # host frames (staged)
         assert (out == exp).all(), (fmt, lut, w, h, kind, "host")
+
+
+# ---- asynchronous host-frame mode (b200vfx_ctx_set_host_async + fences) --------------------------------------------------
+@pytest.mark.parametrize("zero_copy", [0, 1, 2])
+def test_host_async_colorlut_stream_matches_sync(zero_copy):
+    """frames submitted from pinned host memory without waiting for each other: every output equals the synchronous call's,
+    with the staged copy-engine pipeline (two staging slots), the zero-copy kernel, and the auto-probe in between"""
+    torch = pytest.importorskip("torch")
+    w, h = 1920, 1080
+    cube = orc.cube_parse(synth.cube_text_3d(17, "mix"))
+    frames = [synth.frame_noise("RGBA", w, h, 500 + i) if i % 2 else synth.frame_natural("RGBA", w, h, 500 + i) for i in range(5)]
+    exp = [orc.colorlut_apply(cube, "RGBA", w, h, f, threads=8) for f in frames]
+    with b200vfx.Context(0) as ctx:
+        ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+        ctx.set_option("zero_copy", zero_copy)
+        ring = 4
+        h_in = [torch.empty((h, 4 * w), dtype=torch.uint8).pin_memory() for _ in range(ring)]
+        h_out = [torch.empty((h, 4 * w), dtype=torch.uint8).pin_memory() for _ in range(ring)]
+        ctx.set_host_async(True)
+        fences, checked = [], 0
+        n = 23
+        for i in range(n):
+            if i >= 3:                      # at most three frames in flight: frame i - 3 is done, its buffers are ours again
+                fences[i - 3].wait()
+                assert (h_out[(i - 3) % ring].numpy() == exp[(i - 3) % 5]).all(), i
+                checked += 1
+            h_in[i % ring].numpy()[:] = frames[i % 5]
+            h_out[i % ring].numpy()[:] = 0x5A
+            ctx.colorlut_process("RGBA", w, h, h_in[i % ring].numpy(), 4 * w, h_out[i % ring].numpy(), 4 * w)
+            fences.append(ctx.fence())
+        ctx.synchronize()
+        assert all(f.done() for f in fences)
+        for i in range(n - 3, n):
+            assert (h_out[i % ring].numpy() == exp[i % 5]).all(), i
+        assert checked == n - 3
+        ctx.set_host_async(False)           # back to synchronous calls on the same context
+        out = np.zeros_like(frames[0])
+        ctx.colorlut_process("RGBA", w, h, frames[2], 4 * w, out, 4 * w)
+        assert (out == exp[2]).all()
+        for f in fences:
+            f.close()
+
+
+def test_host_async_in_place_and_two_plane_elements():
+    """hsvfilter (in place), hsvdetector and convert_packed in asynchronous mode, strides with padding, frame sizes changing
+    between calls (staging slots regrow)"""
+    torch = pytest.importorskip("torch")
+    with b200vfx.Context(0) as ctx:
+        ctx.set_host_async(True)
+        ctx.set_option("hsv_memo", 0)
+        jobs = []
+        for k, (w, h, pad) in enumerate(((640, 360, 0), (1280, 720, 16), (322, 100, 0), (1280, 720, 16), (640, 360, 0), (1920, 1080, 0))):
+            f = synth.frame_noise("RGBA", w, h, 40 + k, stride=4 * w + pad)
+            a = torch.from_numpy(f.copy()).pin_memory()
+            ctx.hsvfilter_process("RGBA", w, h, a.numpy(), 4 * w + pad, hue_shift=15.0 * k, saturation_mul=1.1)
+            b_in = torch.from_numpy(f.copy()).pin_memory()
+            b_out = torch.zeros((h, 4 * w + pad), dtype=torch.uint8).pin_memory()
+            ctx.hsvdetector_process("BGRx", "BGRA", w, h, b_in.numpy(), 4 * w + pad, b_out.numpy(), 4 * w + pad, hue_ref=40.0 * k, hue_var=60.0,
+                                    saturation_ref=0.5, saturation_var=0.5, value_ref=0.5, value_var=0.5)
+            c_out = torch.zeros((h, 4 * w), dtype=torch.uint8).pin_memory()
+            ctx.convert_packed("RGBA", "xBGR", w, h, b_in.numpy(), 4 * w + pad, c_out.numpy(), 4 * w)
+            jobs.append((k, w, h, pad, f, a, b_in, b_out, c_out, ctx.fence()))
+        import np_convert as npc
+        for k, w, h, pad, f, a, b_in, b_out, c_out, fence in jobs:
+            fence.wait()
+            assert (a.numpy()[:, :4 * w] == orc.hsvfilter("RGBA", w, h, f, hue_shift=15.0 * k, sat_mul=1.1)[:, :4 * w]).all(), k
+            expd = orc.hsvdetector("BGRx", "BGRA", w, h, f, hue_ref=40.0 * k, hue_var=60.0, sat_ref=0.5, sat_var=0.5, val_ref=0.5, val_var=0.5)
+            assert (b_out.numpy()[:, :4 * w] == expd[:, :4 * w]).all(), k
+            assert (c_out.numpy() == npc.convert_packed("RGBA", "xBGR", w, h, f)).all(), k
+            fence.close()
+        ctx.synchronize()
