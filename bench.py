@@ -126,6 +126,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.ok = index, [], set(), False, None, False
+        self.power_w = 0
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -147,6 +148,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
+                    self.power_w = max(self.power_w, nv.nvmlDeviceGetPowerUsage(self.h) // 1000)
+                except Exception:
+                    pass
+                try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -159,8 +164,13 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         s = sorted(self.samples)
+        # B200s of this pool run the first ~60-100 ms of a load at the maximum SM clock and then settle ~11 % lower
+        # (1965 -> 1750 MHz, no throttle reason reported; profiles/r02_ab_clock_drift.jsonl): a short timed region sees the
+        # former, a long one the latter -- first / last / min say which this run was
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "sm_mhz_min": (s[0] if s else None),
+                "sm_mhz_first": (self.samples[0] if s else None), "sm_mhz_last": (self.samples[-1] if s else None),
+                "power_w_max": self.power_w or None}
 
 
 # --------------------------------------------------------------------------------------------------
