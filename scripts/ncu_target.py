@@ -13,7 +13,7 @@ import b200vfx
 from b200vfx import synth
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--kernel", default="memo", choices=["memo", "direct", "direct64", "hsvfilter", "hsvdetector", "blockhash", "colordetect", "hash", "fmt"])
+ap.add_argument("--kernel", default="memo", choices=["memo", "direct", "direct64", "hsvfilter", "hsvdetector", "blockhash", "colordetect", "hash", "fmt", "planar"])
 ap.add_argument("--content", default="ramps", choices=["ramps", "noise", "natural"])
 ap.add_argument("--lut", type=int, default=33)
 ap.add_argument("--launches", type=int, default=6)
@@ -70,6 +70,19 @@ elif a.kernel == "fmt":         # colorlut with the surrounding converts fused i
     out = [torch.empty_like(f) for f in fr]
     for i in range(a.launches):
         ctx.colorlut_process_fmt("BGRx", "RGBA", W, H, fr[i % 4], 4 * W, out[i % 4], 4 * W)
+elif a.kernel == "planar":      # colorlut on I420 frames, both converts fused in
+    k, s, v, sc, of = b200vfx.cube_parse(synth.cube_text_3d(a.lut, "mix"))
+    ctx.colorlut_set_lut(k, s, v, sc, of)
+    rgba = [frame("RGBA", W, H, i) for i in range(4)]
+    strides = [W, W // 2, W // 2]
+    src = []
+    for f in rgba:   # planes of a frame with the chosen content: luma = green channel, chroma = subsampled red / blue
+        px = f.reshape(H, W, 4)
+        src.append([torch.from_numpy(np.ascontiguousarray(px[:, :, 1])).cuda(), torch.from_numpy(np.ascontiguousarray(px[::2, ::2, 0])).cuda(),
+                    torch.from_numpy(np.ascontiguousarray(px[::2, ::2, 2])).cuda()])
+    dst = [[torch.empty_like(p) for p in fr_] for fr_ in src]
+    for i in range(a.launches):
+        ctx.colorlut_process_planar("I420", W, H, src[i % 4], strides, dst[i % 4], strides)
 elif a.kernel == "colordetect":
     fr = [torch.from_numpy(frame("RGBA", W, H, i)).cuda() for i in range(4)]
     hist = torch.zeros(32768, dtype=torch.int32, device="cuda")
