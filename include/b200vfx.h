@@ -72,7 +72,11 @@ int b200vfx_abi_version(void);
 int b200vfx_device_count(void); /* <=0: no usable CUDA device */
 
 /* Created in BaseTransformImpl::start() (or first set_caps), destroyed in stop().
- * device < 0 selects the current CUDA device. */
+ * device < 0 selects the current CUDA device.
+ * Threading: a context belongs to one streaming thread at a time, like the GstBaseTransform instance that owns it (the
+ * vfuncs of one element run under its stream lock).  Different contexts may be used from different threads concurrently;
+ * calls on ONE context must be serialised by the caller.  b200vfx_fence_wait / _query / _destroy may be called from any
+ * thread (e.g. a downstream element mapping the buffer). */
 int b200vfx_ctx_create(b200vfx_ctx **out, int device);
 void b200vfx_ctx_destroy(b200vfx_ctx *ctx);
 const char *b200vfx_last_error(const b200vfx_ctx *ctx); /* ctx may be NULL: last create/parse error of this thread */
