@@ -647,7 +647,7 @@ struct BlockhashFrames { const uint8_t *src[kBlockhashMaxFrames]; long stride[kB
 // ONE launch: every CTA publishes its partial sum, the last CTA to arrive (ticket) adds the partials of each bin in a
 // fixed order and writes the final sums -- no zeroing pass, no atomics on the bins, nothing to wait for.
 template <int BPP, bool VEC>
-__global__ void __launch_bounds__(128) blockhash_sums_kernel(BlockhashFrames fr, int zchunks, int bw, int bh, int hw, int hh,
+__global__ void __launch_bounds__(128) blockhash_sums_kernel(const __grid_constant__ BlockhashFrames fr, int zchunks, int bw, int bh, int hw, int hh,
                                                              int rows_per_cta, uint32_t *__restrict__ sums,
                                                              uint32_t *__restrict__ partials, unsigned *__restrict__ ticket) {
   pdl_trigger();   // the next launch may start reading ITS frame; whatever it writes is ordered by the wait below
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(128) blockhash_sums_kernel(BlockhashFrames fr,
 // (match.any + redux: one shared atomic per distinct block in a warp).  grid = (chunks, hh, frames), 256 threads.
 constexpr int kBlockhashRowsMaxHW = 256;
 template <int K>
-__global__ void __launch_bounds__(256) blockhash_rows_kernel(BlockhashFrames fr, int zchunks, int bw, int bh, int hw, int hh,
+__global__ void __launch_bounds__(256) blockhash_rows_kernel(const __grid_constant__ BlockhashFrames fr, int zchunks, int bw, int bh, int hw, int hh,
                                                              int rows_per_cta, uint32_t *__restrict__ sums,
                                                              uint32_t *__restrict__ partials, unsigned *__restrict__ ticket) {
   constexpr int U = 16 / K;

@@ -49,6 +49,30 @@ def wall_time(fn, iters=12, warm=7):
     return (time.perf_counter() - t0) / iters
 
 
+def async_wall_time(ctx, fn, iters, warm, inflight=3):
+    """the same calls in asynchronous host-frame mode: <= `inflight` frames in flight (a fence per frame), final synchronise
+    inside the timed region; the callers' rings hold more buffers than that"""
+    for i in range(warm):
+        fn(i)
+    ctx.set_host_async(True)
+    fences = []
+    for i in range(4):
+        fn(i); fences.append(ctx.fence())
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    for i in range(iters):
+        if len(fences) >= inflight:
+            f = fences.pop(0); f.wait(); f.close()
+        fn(i)
+        fences.append(ctx.fence())
+    ctx.synchronize()
+    dt = (time.perf_counter() - t0) / iters
+    for f in fences:
+        f.close()
+    ctx.set_host_async(False)
+    return dt
+
+
 def cpu_time(fn, budget=4.0):
     fn()
     n, t0 = 0, time.perf_counter()
@@ -78,6 +102,7 @@ def configs_1_to_4():
     warm = (1 << 24) // (w * h) + 4
     t_dev = dev_time(lambda i: ctx.hsvfilter_process("RGBA", w, h, d[i % R], 4 * w, hue_shift=90.0), 200, warm)
     t_e2e = wall_time(lambda i: ctx.hsvfilter_process("RGBA", w, h, hp[i % R].numpy(), 4 * w, hue_shift=90.0), 200, 60)
+    t_e2e_async = async_wall_time(ctx, lambda i: ctx.hsvfilter_process("RGBA", w, h, hp[i % R].numpy(), 4 * w, hue_shift=90.0), 400, 10)
     ctx.set_option("hsv_memo", 0)
     t_dev_direct = dev_time(lambda i: ctx.hsvfilter_process("RGBA", w, h, d[i % R], 4 * w, hue_shift=90.0), 200, 5)
     ctx.set_option("hsv_memo", -1)
@@ -85,7 +110,7 @@ def configs_1_to_4():
     t_cpuN = cpu_time(lambda: orc.hsvfilter("RGBA", w, h, frames[0], hue_shift=90.0, threads=T), 1.5)
     print(json.dumps({"config": 1, "what": "hsvfilter hue-shift=90, 640x480 RGBA, in place", "device_us": round(t_dev * 1e6, 2),
                       "device_fps": round(1 / t_dev), "algo_GBps": round(2 * w * h * 4 / t_dev / 1e9, 1), "device_us_direct_kernel": round(t_dev_direct * 1e6, 2),
-                      "e2e_fps": round(1 / t_e2e), "cpu_fps_1thread": round(1 / t_cpu1, 1), "cpu_fps_%dthreads" % T: round(1 / t_cpuN, 1)}), flush=True)
+                      "e2e_fps": round(1 / t_e2e), "e2e_fps_async_mode": round(1 / t_e2e_async), "cpu_fps_1thread": round(1 / t_cpu1, 1), "cpu_fps_%dthreads" % T: round(1 / t_cpuN, 1)}), flush=True)
     # ---- config 3: hsvdetector (BGRx -> RGBA) + roundedcorners mask, 1920x1080 -------------------------------------
     w, h = 1920, 1080
     kw = dict(hue_ref=120.0, hue_var=30.0, saturation_ref=0.8, saturation_var=0.2, value_ref=0.8, value_var=0.2)
@@ -97,6 +122,7 @@ def configs_1_to_4():
     warm = (1 << 24) // (w * h) + 4
     t_dev = dev_time(lambda i: ctx.hsvdetector_process("BGRx", "RGBA", w, h, d[i % R], 4 * w, do[i % R], 4 * w, **kw), 100, warm)
     t_e2e = wall_time(lambda i: ctx.hsvdetector_process("BGRx", "RGBA", w, h, hp[i % R].numpy(), 4 * w, ho[i % R].numpy(), 4 * w, **kw), 60, 20)
+    t_e2e_async = async_wall_time(ctx, lambda i: ctx.hsvdetector_process("BGRx", "RGBA", w, h, hp[i % R].numpy(), 4 * w, ho[i % R].numpy(), 4 * w, **kw), 120, 6)
     ctx.set_option("hsv_memo", 0)
     t_dev_direct = dev_time(lambda i: ctx.hsvdetector_process("BGRx", "RGBA", w, h, d[i % R], 4 * w, do[i % R], 4 * w, **kw), 100, 5)
     ctx.set_option("hsv_memo", -1)
@@ -107,7 +133,7 @@ def configs_1_to_4():
     t_mask_cpu = cpu_time(lambda: orc.roundmask(w, h, w, 64), 1.0)
     print(json.dumps({"config": 3, "what": "hsvdetector BGRx->RGBA 1920x1080 (+ roundedcorners r=64 mask once per caps/radius; the two "
                       "elements cannot be linked directly: SURVEY D1)", "device_us": round(t_dev * 1e6, 2), "device_fps": round(1 / t_dev),
-                      "algo_GBps": round(2 * w * h * 4 / t_dev / 1e9, 1), "device_us_direct_kernel": round(t_dev_direct * 1e6, 2), "e2e_fps": round(1 / t_e2e),
+                      "algo_GBps": round(2 * w * h * 4 / t_dev / 1e9, 1), "device_us_direct_kernel": round(t_dev_direct * 1e6, 2), "e2e_fps": round(1 / t_e2e), "e2e_fps_async_mode": round(1 / t_e2e_async),
                       "cpu_fps_1thread": round(1 / t_cpu1, 1), "cpu_fps_%dthreads" % T: round(1 / t_cpuN, 1), "mask_device_us": round(t_mask * 1e6, 1), "mask_cpu_us": round(t_mask_cpu * 1e6, 1)}), flush=True)
     # ---- chain: hsvfilter -> hsvdetector on 1920x1080 BGRx, host frame in, host frame out -------------
     # (a) as two unchanged elements with system memory between them: every element uploads and downloads its frame;

@@ -299,3 +299,38 @@ def test_host_async_in_place_and_two_plane_elements():
             assert (c_out.numpy() == npc.convert_packed("RGBA", "xBGR", w, h, f)).all(), k
             fence.close()
         ctx.synchronize()
+
+
+def test_host_async_edge_cases():
+    """a fence with nothing submitted is reached at once; pageable frames work in asynchronous mode (the driver stages them, so
+    the call is effectively synchronous); device-pointer calls are untouched by the mode; toggling the mode drains"""
+    torch = pytest.importorskip("torch")
+    w, h = 320, 96
+    cube = orc.cube_parse(synth.cube_text_1d(32))
+    frame = synth.frame_noise("RGBA", w, h, 3)
+    exp = orc.colorlut_apply(cube, "RGBA", w, h, frame)
+    with b200vfx.Context(0) as ctx:
+        f0 = ctx.fence(); f0.wait(); assert f0.done(); f0.close()          # nothing submitted, mode off
+        ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+        ctx.set_host_async(True)
+        out = np.zeros_like(frame)
+        ctx.colorlut_process("RGBA", w, h, frame, 4 * w, out, 4 * w)       # pageable numpy arrays
+        f1 = ctx.fence(); f1.wait(); f1.close()
+        assert (out == exp).all()
+        d_in, d_out = torch.from_numpy(frame).cuda(), torch.zeros((h, 4 * w), dtype=torch.uint8, device="cuda")
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.colorlut_process("RGBA", w, h, d_in, 4 * w, d_out, 4 * w)      # device frames: the context stream, as always
+        torch.cuda.synchronize()
+        assert (d_out.cpu().numpy() == exp).all()
+        pin_in, pin_out = torch.from_numpy(frame).pin_memory(), torch.zeros((h, 4 * w), dtype=torch.uint8).pin_memory()
+        for _ in range(5):
+            ctx.colorlut_process("RGBA", w, h, pin_in.numpy(), 4 * w, pin_out.numpy(), 4 * w)
+        ctx.set_host_async(False)                                            # drains what is in flight
+        assert (pin_out.numpy() == exp).all()
+        sums = np.zeros(64, np.uint32)
+        ctx.set_host_async(True)
+        ctx.colorlut_process("RGBA", w, h, pin_in.numpy(), 4 * w, pin_out.numpy(), 4 * w)
+        ctx.blockhash_sums("RGBA", w, h, frame, 4 * w, sums)                # a reduction stays synchronous in the mode
+        assert (sums == orc.blockhash_sums("RGBA", w, h, frame)).all()
+        ctx.synchronize()
+        assert (pin_out.numpy() == exp).all()
