@@ -105,6 +105,7 @@ struct b200vfx_ctx {
                          // frame's kernel (PDL) is resident beside this one (profiles/r01_memo_ctas_experiment.jsonl)
   int rgba64_x4 = 1;     // RGBA64 + 3D LUT: 4 consecutive pixels per thread with the LUT cell cached in registers (0: one pixel per thread)
   int memo_tile = 0;     // 4-byte-pixel table lookups through memo_tile_kernel (per-tile shared-memory copy of the colour sub-cube)
+  int cd_split = 0;      // colordetect, asynchronous calls: a launch takes 1/cd_split of the SMs so that consecutive launches overlap (0 = auto: 4 for quality <= 2, else 2; 1 = all SMs)
   int cd_cluster = 2;    // colordetect: CTAs per cluster merging their shared-memory histograms (1, 2, 4, 8)
   int peer_timeout_ms = 2000;  // deadline of the cross-GPU waits in the tile-gather kernel
   std::string err;
@@ -1116,6 +1117,7 @@ int b200vfx_ctx_set_option(b200vfx_ctx *c, const char *name, int value) {
   else if (n == "stream_hint") c->stream_hint = value;
   else if (n == "memo_px") c->memo_px = value;
   else if (n == "pdl") c->pdl = value != 0;
+  else if (n == "cd_split") c->cd_split = std::max(0, std::min(value, 8));
   else if (n == "blockhash_rows") c->blockhash_rows = std::max(0, std::min(value, 8));
   else if (n == "tile_gather_path") c->tg_path = value;
   else if (n == "tile_gather_cfg") c->tg_cfg = value;
@@ -2164,7 +2166,13 @@ int b200vfx_colordetect_histogram(b200vfx_ctx *c, int fmt, int width, int height
     }
     const long long units = mode == 2 ? (nsamples >> 2) : nsamples;
     const long long per_cta = (long long)kColorDetectThreads * 4;
-    unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(resident, (units + per_cta - 1) / per_cta));
+    // An asynchronous call (device histogram) is one of a train: taking only a fraction of the SMs leaves the rest to the
+    // next launch (PDL), which then runs beside this one, and fewer CTAs flush fewer partial histograms with global atomics:
+    // 4K, quality 10: 11.9 -> 7.8 us per frame (14.1 -> 10.3 on noise), quality 1 on noise 32.2 -> 15.8 us
+    // (profiles/r02_colordetect_split.jsonl).  A call that returns the histogram to the host is alone: all SMs.
+    const int split = c->cd_split > 0 ? c->cd_split : (quality <= 2 ? 4 : 2);
+    const long long cap = (pdl && hist_dev && split > 1) ? std::max<long long>(cluster, resident / split) : resident;
+    unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(cap, (units + per_cta - 1) / per_cta));
     const unsigned cl = grid >= (unsigned)cluster ? (unsigned)cluster : 1u;
     grid -= grid % cl;
     cudaLaunchConfig_t cfg = {};

@@ -112,6 +112,8 @@ uint64_t b200vfx_ctx_kernel_launches(const b200vfx_ctx *ctx);
  * "hsv_memo" -1 auto | 0 never | 1 at once (settings-keyed answer tables of hsvfilter / hsvdetector; auto builds
  * the table after the same settings have processed 2^24 pixels),
  * "cd_cluster" 1|2|4|8 (colordetect: CTAs per cluster that merge their shared-memory histograms over DSMEM),
+ * "cd_split" 0 auto | 1 | 2..8 (colordetect with a DEVICE histogram: fraction 1/n of the SMs per launch, so that the launches
+ * of a train run beside each other),
  * "memo_ctas" 2..8 (CTAs per SM of the persistent table-lookup kernels; 4 = two consecutive frames resident together),
  * "memo_tile" 0|1 (4-byte-pixel table lookups through a per-tile shared-memory copy of the colour sub-cube; wins on
  * medium-noise content only, profiles/r01_memo_tile_experiment.jsonl),
