@@ -165,6 +165,9 @@ extern "C" {
     pub fn b200vfx_convert_from_planar(ctx: *mut b200vfx_ctx, src_fmt: c_int, dst_fmt: c_int, width: c_int, height: c_int,
                                        planes: *const *const c_void, strides: *const c_int, dst: *mut c_void, dst_stride: c_int,
                                        matrix: c_int) -> c_int;
+    /// colorlut on I420 / A420 planes, both videoconverts inside the kernel
+    pub fn b200vfx_colorlut_process_planar(ctx: *mut b200vfx_ctx, fmt: c_int, width: c_int, height: c_int, src_planes: *const *const c_void,
+        src_strides: *const c_int, dst_planes: *const *mut c_void, dst_strides: *const c_int, matrix: c_int) -> c_int;
     pub fn b200vfx_a420_append(ctx: *mut b200vfx_ctx, width: c_int, height: c_int, i420_planes: *const *const c_void,
                                i420_strides: *const c_int, a8: *const c_void, a8_stride: c_int,
                                out_planes: *const *mut c_void, out_strides: *const c_int) -> c_int;
