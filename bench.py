@@ -10,7 +10,10 @@ A STEP = one GOP of `--gop` (default 64) frames through the element; the inputs 
 of 12 distinct frames and 12 distinct outputs (796 MB > the 126 MB L2), so no frame is L2-resident when
 it is processed ("inputs larger than L2"; no explicit flush: the memo LUT is *meant* to live in L2).
   value : device-resident frames/s (frames already in HBM), CUDA events on the launching stream.
-  e2e   : the same GOPs through the same C-ABI call with HOST (pinned) buffers, H2D and D2H inside.
+  e2e   : the same GOPs through the same C-ABI call with HOST (pinned) buffers, H2D and D2H inside the timed region --
+          measured twice: synchronous calls (every call returns with its output in host memory) and the asynchronous
+          host-frame mode (b200vfx_ctx_set_host_async: <= 3 frames in flight, a fence per frame, final synchronise inside
+          the timed region); `e2e.value` is the faster of the two (all ranks take the same decision), both are reported.
 Multi-GPU (weak scaling, no data-path collective): every frame is row-tiled N ways, rank r owns tile r;
 a rank's tiles of N consecutive frames are stacked in its buffer, so its per-step work is the same
 number of rows as at N=1.  value = all frames finished by all ranks / max-over-ranks time.
