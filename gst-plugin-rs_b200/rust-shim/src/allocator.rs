@@ -26,7 +26,8 @@ pub const CAPS_FEATURE_MEMORY_B200: &str = "memory:B200Memory";
 // ---- pinned host memory ---------------------------------------------------------------------------------------------
 // A pinned block can carry a FENCE: in asynchronous host-frame mode (b200vfx_ctx_set_host_async) transform_frame returns
 // as soon as the frame's copies and kernel are enqueued, the output buffer is pushed downstream at once, and whoever maps
-// it for the CPU waits here -- what GstCudaMemory does on map(READ).  The upload of frame i+1 then overlaps the download
+// it for the CPU waits here -- what the reference's d3d12colorlut does with D3D12Memory::set_fence
+// (video/colorlut/src/d3d12colorlut/imp.rs:711-714) and GstCudaMemory does on map(READ).  The upload of frame i+1 then overlaps the download
 // of frame i: 1380 instead of 1176 frames/s end to end on 4K RGBA (profiles/r02_e2e_async.jsonl).
 struct PinnedBlock {
     ptr: *mut u8,

@@ -91,8 +91,10 @@ int b200vfx_ctx_synchronize(b200vfx_ctx *ctx);
  * per-pixel entry points on host frames (colorlut, colorlut_fmt, hsvfilter, hsvdetector, convert_packed) return as soon as
  * their copies and kernels are enqueued; b200vfx_fence_create marks "everything submitted so far", and the caller must not
  * read the output frames, or reuse the input frames, before that fence has been waited on (or b200vfx_ctx_synchronize).
- * The element-side pattern is the one GstCudaMemory uses: the pinned GstMemory handed downstream carries the fence and
- * its map() waits (rust-shim/src/allocator.rs).  Frames must be pinned (b200vfx_host_alloc) to be copied asynchronously
+ * This is the contract of the reference's own GPU element: D3D12ColorLut::transform submits its command list, stamps the
+ * output memories with the queue's fence value and returns (video/colorlut/src/d3d12colorlut/imp.rs:698-718; input fences
+ * are waited for on the queue, :579-602, :694-696) -- whoever maps the memory waits.  Here the pinned GstMemory handed
+ * downstream carries the fence and its map() waits (rust-shim/src/allocator.rs).  Frames must be pinned (b200vfx_host_alloc) to be copied asynchronously
  * at all.  Reductions and hashes (blockhash, colordetect, hash_image) stay synchronous: they return values. */
 typedef struct b200vfx_fence b200vfx_fence;
 int b200vfx_ctx_set_host_async(b200vfx_ctx *ctx, int enable);
