@@ -69,6 +69,7 @@ struct b200vfx_ctx {
   cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;  // host-pointer pipeline
   std::vector<cudaEvent_t> ev_in, ev_k;
   cudaEvent_t ev_order = nullptr;      // orders the internal pipeline stream after the context stream (mixed host/device calls)
+  cudaEvent_t ev_order_back = nullptr; // ... and the context stream after the internal one (asynchronous mode)
   DevBuf stage_in, stage_out, stage_sums;
   // asynchronous host-frame mode (b200vfx_ctx_set_host_async): calls return once their copies and kernels are enqueued, so
   // frame i+1's upload overlaps frame i's download.  Two staging slots of their own; a slot is reused only after the
@@ -175,6 +176,16 @@ int order_after_ctx_stream(b200vfx_ctx *c, cudaStream_t st) {
   if (!c->ev_order) CU(c, cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
   CU(c, cudaEventRecord(c->ev_order, c->stream()));
   CU(c, cudaStreamWaitEvent(st, c->ev_order, 0));
+  return 0;
+}
+
+// the reverse: what follows on the context stream is ordered after what `st` has been given so far (asynchronous host-frame
+// mode with one plane in HBM: nothing synchronises the internal stream before the call returns)
+int order_ctx_stream_after(b200vfx_ctx *c, cudaStream_t st) {
+  if (st == c->stream()) return 0;
+  if (!c->ev_order_back) CU(c, cudaEventCreateWithFlags(&c->ev_order_back, cudaEventDisableTiming));
+  CU(c, cudaEventRecord(c->ev_order_back, st));
+  CU(c, cudaStreamWaitEvent(c->stream(), c->ev_order_back, 0));
   return 0;
 }
 
@@ -907,6 +918,9 @@ int run_staged(b200vfx_ctx *c, const Staged &s, LaunchFn launch) {
   if (async) {   // the call returns here; b200vfx_fence / b200vfx_ctx_synchronize tell when the frame is on the host
     CU(c, cudaEventRecord(c->slot_done[slot], need_d2h ? c->s_d2h : c->s_k));
     c->slot_used[slot] = true;
+    // a plane in HBM was read or written on the internal stream: later device-pointer calls (context stream) come after it
+    if (!s.in_place && ((src_dev && s.src && !(s.device_addressable & 1)) || (dst_dev && !(s.device_addressable & 2))))
+      if (int rc = order_ctx_stream_after(c, c->s_k)) return rc;
     return 0;
   }
   if (need_d2h) CU(c, cudaStreamSynchronize(c->s_d2h));
@@ -1022,6 +1036,7 @@ void b200vfx_ctx_destroy(b200vfx_ctx *c) {
   for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
   if (c->ev_order) cudaEventDestroy(c->ev_order);
+  if (c->ev_order_back) cudaEventDestroy(c->ev_order_back);
   for (auto &kv : c->taps_cache) { cudaFree(kv.second.taps); cudaFree(kv.second.meta); }
   c->stage_in.release(); c->stage_out.release(); c->stage_sums.release(); c->reduce_scratch.release();
   if (c->result_pinned) { cudaFreeHost(c->result_pinned); c->result_pinned = nullptr; }

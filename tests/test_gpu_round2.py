@@ -334,3 +334,32 @@ def test_host_async_edge_cases():
         assert (sums == orc.blockhash_sums("RGBA", w, h, frame)).all()
         ctx.synchronize()
         assert (pin_out.numpy() == exp).all()
+
+
+def test_host_async_mixed_planes_are_ordered_with_the_context_stream():
+    """asynchronous mode, host frame in, DEVICE frame out: the kernel runs on the internal stream and nothing waits for it
+    before the call returns -- a device-pointer call that follows (context stream) must still see its result"""
+    torch = pytest.importorskip("torch")
+    w, h = 1920, 1080
+    cube = orc.cube_parse(synth.cube_text_3d(17, "mix"))
+    frames = [synth.frame_noise("BGRx", w, h, 900 + i) for i in range(6)]
+    kw = dict(hue_ref=200.0, hue_var=90.0, saturation_ref=0.5, saturation_var=0.5, value_ref=0.5, value_var=0.5)
+    okw = dict(hue_ref=200.0, hue_var=90.0, sat_ref=0.5, sat_var=0.5, val_ref=0.5, val_var=0.5)
+    with b200vfx.Context(0) as ctx:
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.set_option("hsv_memo", 0)
+        ctx.colorlut_set_lut(cube.kind, cube.size, cube.values, cube.scale, cube.offset)
+        ctx.set_host_async(True)
+        pins = [torch.from_numpy(f).pin_memory() for f in frames]
+        mid = torch.zeros((h, 4 * w), dtype=torch.uint8, device="cuda")
+        outs = [torch.zeros((h, 4 * w), dtype=torch.uint8, device="cuda") for _ in frames]
+        for i, p in enumerate(pins):
+            # host -> device on the internal stream (asynchronous), then device -> device on the context stream; `mid` is
+            # rewritten by the next iteration's first call while this iteration's second call may still be reading it
+            ctx.hsvdetector_process("BGRx", "RGBA", w, h, p.numpy(), 4 * w, mid, 4 * w, **kw)
+            ctx.colorlut_process("RGBA", w, h, mid, 4 * w, outs[i], 4 * w)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        for i, f in enumerate(frames):
+            exp = orc.colorlut_apply(cube, "RGBA", w, h, orc.hsvdetector("BGRx", "RGBA", w, h, f, **okw))
+            assert (outs[i].cpu().numpy() == exp).all(), i
