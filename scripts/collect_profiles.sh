@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 profile collection: everything that profiles/r02_* is digested from
+# profile collection: everything that profiles/r02_* is digested from (run on one B200 through gpurun)
 mkdir -p gpurun_out/prof
 O=gpurun_out/prof
 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
