@@ -83,3 +83,26 @@ def test_blackwell_native_instructions_present(sass):
         assert "SYNCS.ARRIVE.TRANS64" in body and "SYNCS.PHASECHK" in body, n   # mbarrier expect_tx / try_wait
     assert any("LDG.E.ENL2.256" in i for n, b in sass.items() if "colorlut_direct_kernel" in n for i in b)
     assert any(re.search(r"\bACQBULK|UTMACMDFLUSH|UBLKCP", i) for n in stream for i in sass[n])
+
+
+def test_round2_kernels_use_the_instructions_their_design_rests_on(sass):
+    """cheap guards against a silent de-optimisation by a compiler or source change (the kernels' results would stay right)"""
+    def ops(name_part):
+        return [i for n, b in sass.items() if name_part in n for i in b]
+    # programmatic dependent launch: the reductions trigger their dependents at entry (PREEXIT) ...
+    for k in ("blockhash_rows_kernel", "blockhash_sums_kernel", "colordetect_hist_kernel", "colorlut_memo_apply_kernel"):
+        assert any(re.match(r"(@!?U?P\d+\s+)?PREEXIT\b", i) for i in ops(k)), k
+    # ... the row-streaming block sums merge a warp's columns with match.any + redux before the shared atomic
+    rows = ops("blockhash_rows_kernel")
+    assert any("MATCH.ANY" in i for i in rows) and any("REDUX.SUM" in i for i in rows) and any("ATOMS.ADD" in i for i in rows)
+    # luma and the RGB -> YUV matrix are dp4a on packed bytes (unsigned x unsigned for Y, unsigned x signed for chroma)
+    assert any("IDP.4A.U8.U8" in i for i in ops("luma_vresize_kernel"))
+    planar = ops("colorlut_i420_x8_kernel")
+    assert any("IDP.4A.U8.U8" in i for i in planar) and any("IDP.4A.U8.S8" in i for i in planar)
+    # the horizontal resize chain reads its products 16 bytes at a time and adds them with dependent FADDs (never FFMA)
+    hres = ops("luma_hresize_kernel")
+    assert any("LDS.128" in i for i in hres) and not any(re.match(r"(@!?U?P\d+\s+)?FFMA\b", i) for i in hres)
+    assert not any(re.match(r"(@!?U?P\d+\s+)?FFMA\b", i) for i in ops("luma_vresize_kernel"))
+    # 32-byte stores of the fused tile gather, the multicast store path compiles to system-scope 16-byte stores
+    tg = ops("colorlut_tile_gather_kernel")
+    assert any("STG.E.ENL2.256" in i for i in tg) and any("STG.E.128.STRONG.SYS" in i for i in tg)
